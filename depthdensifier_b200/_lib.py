@@ -1,0 +1,123 @@
+"""ctypes binding of libddn_b200.so (the C ABI declared in include/ddn_b200.h).
+
+There is no CPU fallback: if the library is missing, or no CUDA device is present when a compute
+entry point is called, this module raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "libddn_b200.so"
+
+
+class DDNError(RuntimeError):
+    pass
+
+
+class AlignConfig(C.Structure):
+    _fields_ = [
+        ("min_correspondences", C.c_int32),
+        ("edge_margin", C.c_int32),
+        ("robust", C.c_int32),
+        ("outlier_threshold", C.c_float),
+        ("skip_smoothing", C.c_int32),
+        ("adaptive_correspondences", C.c_int32),
+        ("max_pairs", C.c_int32),
+        ("mode", C.c_int32),
+        ("subsample_seed", C.c_uint32),
+        ("zero_unmasked_passthrough", C.c_int32),
+    ]
+
+
+class ViewStats(C.Structure):
+    _fields_ = [
+        ("status", C.c_int32),
+        ("num_correspondences", C.c_int32),
+        ("outliers_removed", C.c_int32),
+        ("num_table", C.c_int32),
+        ("scale_factor", C.c_float),
+        ("affine_scale", C.c_float),
+        ("affine_shift", C.c_float),
+        ("reserved", C.c_int32),
+    ]
+
+
+class FilterConfig(C.Structure):
+    _fields_ = [
+        ("depth_threshold", C.c_float),
+        ("grazing_cos", C.c_float),
+        ("sample_mode", C.c_int32),
+        ("two_sided_tau", C.c_float),
+        ("stride", C.c_int32),
+        ("normals_in_world", C.c_int32),
+    ]
+
+
+class VoxelGrid(C.Structure):
+    _fields_ = [("voxel", C.c_float), ("origin", C.c_float * 3), ("bits", C.c_int32 * 3)]
+
+
+PAIR_TABLE_FLOATS = 24
+
+# every symbol include/ddn_b200.h declares: name -> (restype, argtypes)
+_vp, _i64, _i32 = C.c_void_p, C.c_int64, C.c_int32
+SYMBOLS = {
+    "ddn_version": (C.c_int, []),
+    "ddn_last_error_string": (C.c_char_p, []),
+    "ddn_launch_count": (C.c_int64, []),
+    "ddn_align_config_default": (None, [C.POINTER(AlignConfig)]),
+    "ddn_filter_config_default": (None, [C.POINTER(FilterConfig)]),
+    "ddn_align_workspace_bytes": (C.c_int, [_i64, _i64, C.POINTER(_i64)]),
+    "ddn_align_views": (
+        C.c_int,
+        [C.POINTER(AlignConfig), _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp],
+    ),
+    "ddn_build_pair_tables": (C.c_int, [_i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ddn_backproject_filter": (
+        C.c_int,
+        [C.POINTER(FilterConfig), _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp],
+    ),
+    "ddn_bbox_init": (C.c_int, [_vp, _vp]),
+    "ddn_fuse_workspace_bytes": (C.c_int, [_i64, C.POINTER(_i64)]),
+    "ddn_voxel_fuse": (
+        C.c_int,
+        [C.POINTER(VoxelGrid), _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
+    ),
+    "ddn_voxel_keys": (C.c_int, [C.POINTER(VoxelGrid), _i64, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and declare prototypes.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise DDNError(
+            f"{LIB_PATH} is missing: build it with `python -m depthdensifier_b200.build` "
+            "(nvcc, sm_100a). There is no CPU fallback."
+        )
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.ddn_version() != 100:
+        raise DDNError(f"libddn_b200.so version mismatch: {lib.ddn_version()}")
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().ddn_last_error_string().decode("utf-8", "replace")
+        raise DDNError(f"libddn_b200 error {rc}: {msg}")
+
+
+def launch_count() -> int:
+    return int(load().ddn_launch_count())

@@ -1,0 +1,78 @@
+"""In-tree build of libddn_b200.so (sm_100a only) with nvcc.  No JIT cache: the .so sits next to
+the sources so it travels with the repo snapshot to the GPU box."""
+
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+CSRC = PKG_DIR / "csrc"
+LIB_PATH = PKG_DIR / "libddn_b200.so"
+SOURCES = ["api.cu", "align.cu", "filter.cu", "fuse.cu"]
+NVCC_FLAGS = [
+    "-std=c++17",
+    "-O3",
+    "-gencode",
+    "arch=compute_100a,code=sm_100a",
+    "-lineinfo",
+    "--fmad=true",
+    "-Xcompiler",
+    "-fPIC,-O3,-fvisibility=hidden",
+    "-Xptxas",
+    "-v",
+]
+
+
+def nvcc_path() -> str:
+    cand = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(cand):
+        raise RuntimeError("nvcc not found; libddn_b200.so cannot be built (there is no CPU fallback)")
+    return cand
+
+
+def needs_build() -> bool:
+    if not LIB_PATH.exists():
+        return True
+    t = LIB_PATH.stat().st_mtime
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [PKG_DIR.parent / "include" / "ddn_b200.h"]
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = nvcc_path()
+    objs = []
+    build_dir = PKG_DIR / "build"
+    build_dir.mkdir(exist_ok=True)
+    log = []
+    procs = []
+    for src in SOURCES:
+        obj = build_dir / (src + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, obj, pr in procs:
+        out, _ = pr.communicate()
+        log.append(f"== {src}\n{out}")
+        if pr.returncode != 0:
+            sys.stderr.write("\n".join(log))
+            raise RuntimeError(f"nvcc failed on {src}")
+        objs.append(str(obj))
+    (build_dir / "ptxas.log").write_text("\n".join(log))
+    cmd = [nvcc, "-shared", "-o", str(LIB_PATH), *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("link failed")
+    if verbose:
+        print("\n".join(log))
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    p = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(p)

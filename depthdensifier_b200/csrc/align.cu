@@ -1,0 +1,565 @@
+// Stage 1: per-view alignment of monocular depth to projected COLMAP sparse points.
+//
+// Reference semantics: src/depthdensifier/depth_refiner.py:92-328 (see include/ddn_b200.h).
+//   K1+K2  align_stats_kernel  one CTA per view: project sparse points (float32, :92-115), bounds gate
+//          and bilinear sample (:247-288), IQR outlier rejection on z_colmap/z_mono (:117-139),
+//          min-count gate and <=500 subsample (:296-306), scale_factor (:315), then the lookup table
+//          sorted by x (:148-150) or, in affine mode, the five-sum least squares in float64.
+//   K3     remap_median_kernel  fused per-pixel piecewise-linear remap (:157-176), 3x3 replicate
+//          median (:194-200) and mask (:203): depth+mask are read once, refined written once
+//          (9 B/pixel instead of the reference's 9x unfold blow-up).
+#include "common.cuh"
+
+namespace ddn {
+
+constexpr int kStatsThreads = 1024;
+constexpr int kSortSmemMax = 16384;  // u64 entries sorted in shared memory (128 KB); larger -> global
+
+struct AlignWorkspace {
+  float* zd;     // [V,C] sampled mono depth of the surviving pairs
+  float* zc;     // [V,C] COLMAP depth of the surviving pairs
+  float* ratio;  // [V,C]
+  float* tx;     // [V,C] table x (sorted)
+  float* ty;     // [V,C] table y
+  unsigned long long* sortbuf;  // [V,Cp]
+  int64_t C, Cp;
+};
+
+static int64_t next_pow2(int64_t x) {
+  int64_t p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+static int64_t align_ws_bytes(int64_t V, int64_t C) {
+  const int64_t Cp = next_pow2(C > 1 ? C : 2);
+  return align_up(V * C * 4, 256) * 5 + align_up(V * Cp * 8, 256) + 256;
+}
+
+static AlignWorkspace carve(void* ws, int64_t V, int64_t C) {
+  AlignWorkspace w;
+  w.C = C;
+  w.Cp = next_pow2(C > 1 ? C : 2);
+  char* p = reinterpret_cast<char*>(align_up((int64_t)(uintptr_t)ws, 256));
+  const int64_t fb = align_up(V * C * 4, 256);
+  w.zd = (float*)p; p += fb;
+  w.zc = (float*)p; p += fb;
+  w.ratio = (float*)p; p += fb;
+  w.tx = (float*)p; p += fb;
+  w.ty = (float*)p; p += fb;
+  w.sortbuf = (unsigned long long*)p;
+  return w;
+}
+
+// ---- block-level primitives (blockDim.x == kStatsThreads) ----------------------------------------
+
+// Order-preserving compaction of one <=blockDim chunk; returns this thread's slot or -1. `base` is
+// advanced by the chunk's count (uniform across the block after the call).
+__device__ __forceinline__ int block_compact_slot(bool flag, int& base, int* s_warp) {
+  const unsigned m = __ballot_sync(0xffffffffu, flag);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) s_warp[wid] = __popc(m);
+  __syncthreads();
+  if (wid == 0) {
+    int v = s_warp[lane];
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int n = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += n;
+    }
+    s_warp[lane] = incl - v;
+    if (lane == 31) s_warp[32] = incl;
+  }
+  __syncthreads();
+  const int slot = flag ? base + s_warp[wid] + __popc(m & ((1u << lane) - 1)) : -1;
+  base += s_warp[32];
+  __syncthreads();
+  return slot;
+}
+
+__device__ void block_bitonic_sort(unsigned long long* buf, int n_pow2) {
+  for (int k = 2; k <= n_pow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = buf[i], b = buf[ixj];
+          const bool asc = (i & k) == 0;
+          if ((a > b) == asc) {
+            buf[i] = b;
+            buf[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__device__ __forceinline__ unsigned ordered_bits(float f) {
+  const unsigned b = __float_as_uint(f);
+  return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+}
+
+__device__ __forceinline__ int pow2_at_least(int n) {
+  int p = 2;
+  while (p < n) p <<= 1;
+  return p;
+}
+
+// Sort indices 0..n-1 by (key(i), i) ascending; afterwards low 32 bits of buf[r] = index of rank r.
+template <typename KeyFn>
+__device__ void block_sort_by(unsigned long long* buf, int n, KeyFn key) {
+  const int np = pow2_at_least(n);
+  for (int i = threadIdx.x; i < np; i += blockDim.x)
+    buf[i] = i < n ? (((unsigned long long)key(i) << 32) | (unsigned)i) : ~0ull;
+  __syncthreads();
+  block_bitonic_sort(buf, np);
+}
+
+__device__ __forceinline__ unsigned mix32(unsigned h) {
+  h ^= h >> 16;
+  h *= 0x85ebca6bu;
+  h ^= h >> 13;
+  h *= 0xc2b2ae35u;
+  h ^= h >> 16;
+  return h;
+}
+
+__device__ double block_sum(double v, double* s_red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) s_red[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    double t = s_red[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) s_red[0] = t;
+  }
+  __syncthreads();
+  const double r = s_red[0];
+  __syncthreads();
+  return r;
+}
+
+// ---- K1+K2 ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kStatsThreads, 1)
+align_stats_kernel(ddn_align_config cfg, int H, int W, const float* __restrict__ depth,
+                   const double* __restrict__ poses, const double* __restrict__ kmat,
+                   const double* __restrict__ sparse_xyz, const int64_t* __restrict__ offsets,
+                   AlignWorkspace ws, ddn_view_stats* __restrict__ stats, int sort_in_smem) {
+  extern __shared__ __align__(16) unsigned long long s_sort[];
+  __shared__ int s_warp[33];
+  __shared__ double s_red[32];
+  __shared__ float s_f[4];
+
+  const int v = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int64_t lo = offsets[v];
+  const int n_sparse = (int)(offsets[v + 1] - lo);
+  float* zd = ws.zd + (size_t)v * ws.C;
+  float* zc = ws.zc + (size_t)v * ws.C;
+  float* ratio = ws.ratio + (size_t)v * ws.C;
+  float* tx = ws.tx + (size_t)v * ws.C;
+  float* ty = ws.ty + (size_t)v * ws.C;
+  unsigned long long* sortbuf = sort_in_smem ? s_sort : ws.sortbuf + (size_t)v * ws.Cp;
+  const float* __restrict__ dmap = depth + (size_t)v * H * W;
+
+  ddn_view_stats st;
+  st.status = DDN_VIEW_REFINED;
+  st.num_correspondences = 0;
+  st.outliers_removed = 0;
+  st.num_table = 0;
+  st.scale_factor = 1.0f;
+  st.affine_scale = 1.0f;
+  st.affine_shift = 0.0f;
+  st.reserved = 0;
+
+  if (n_sparse <= 0) {
+    if (tid == 0) {
+      st.status = DDN_VIEW_NO_SPARSE;
+      stats[v] = st;
+    }
+    return;
+  }
+
+  // float32 copies of pose and K (depth_refiner.py:233-236 casts inputs to self.dtype)
+  float T[12], Kf[6];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) T[i] = (float)poses[(size_t)v * 12 + i];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) Kf[i] = (float)kmat[(size_t)v * 9 + i];
+  const float m = (float)cfg.edge_margin;
+  const float wlim = (float)(W - cfg.edge_margin), hlim = (float)(H - cfg.edge_margin);
+
+  // -- A1 + A2: project, gate, bilinear sample, keep sampled > 0 (order preserving) --
+  int n1 = 0;
+  int any_inb = 0;
+  for (int c0 = 0; c0 < n_sparse; c0 += kStatsThreads) {
+    const int i = c0 + tid;
+    bool keep = false;
+    float samp = 0.f, z = 0.f;
+    if (i < n_sparse) {
+      const double* p = sparse_xyz + (size_t)(lo + i) * 3;
+      const float x = (float)p[0], y = (float)p[1], zz = (float)p[2];
+      const float cxm = fmaf(T[3], 1.f, fmaf(T[2], zz, fmaf(T[1], y, T[0] * x)));
+      const float cym = fmaf(T[7], 1.f, fmaf(T[6], zz, fmaf(T[5], y, T[4] * x)));
+      z = fmaf(T[11], 1.f, fmaf(T[10], zz, fmaf(T[9], y, T[8] * x)));
+      float u = 0.f, w = 0.f;
+      if (z > 0.f) {
+        const float xn = __fdiv_rn(cxm, z), yn = __fdiv_rn(cym, z);
+        u = __fadd_rn(fmaf(Kf[1], yn, Kf[0] * xn), Kf[2]);
+        w = __fadd_rn(fmaf(Kf[4], yn, Kf[3] * xn), Kf[5]);
+      }
+      const bool inb = (u >= m) && (u < wlim) && (w >= m) && (w < hlim) && (z > 0.f);
+      if (inb) {
+        any_inb = 1;
+        // grid_sample(bilinear, zeros, align_corners=True) at pixel coords (u, w): normalise and
+        // un-normalise exactly as the reference + ATen do (depth_refiner.py:266-272)
+        const float gx = __fadd_rn(__fmul_rn(__fdiv_rn(u, (float)(W - 1)), 2.f), -1.f);
+        const float gy = __fadd_rn(__fmul_rn(__fdiv_rn(w, (float)(H - 1)), 2.f), -1.f);
+        const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.f), 2.f), (float)(W - 1));
+        const float iy = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.f), 2.f), (float)(H - 1));
+        const float x0 = floorf(ix), y0 = floorf(iy);
+        const float x1 = x0 + 1.f, y1 = y0 + 1.f;
+        const float wnw = __fmul_rn(x1 - ix, y1 - iy), wne = __fmul_rn(ix - x0, y1 - iy);
+        const float wsw = __fmul_rn(x1 - ix, iy - y0), wse = __fmul_rn(ix - x0, iy - y0);
+        const int xi0 = (int)x0, yi0 = (int)y0, xi1 = xi0 + 1, yi1 = yi0 + 1;
+        auto tap = [&](int xx, int yy) -> float {
+          return (xx >= 0 && xx < W && yy >= 0 && yy < H) ? __ldg(dmap + (size_t)yy * W + xx) : 0.f;
+        };
+        samp = __fmul_rn(tap(xi0, yi0), wnw);
+        samp = __fadd_rn(samp, __fmul_rn(tap(xi1, yi0), wne));
+        samp = __fadd_rn(samp, __fmul_rn(tap(xi0, yi1), wsw));
+        samp = __fadd_rn(samp, __fmul_rn(tap(xi1, yi1), wse));
+        keep = samp > 0.f;
+      }
+    }
+    const int slot = block_compact_slot(keep, n1, s_warp);
+    if (slot >= 0) {
+      zd[slot] = samp;
+      zc[slot] = z;
+    }
+  }
+  any_inb = __syncthreads_or(any_inb);
+  if (n1 == 0) {
+    if (tid == 0) {
+      st.status = any_inb ? DDN_VIEW_NO_POSITIVE_SAMPLES : DDN_VIEW_NO_POINTS_IN_BOUNDS;
+      stats[v] = st;
+    }
+    return;
+  }
+  __syncthreads();
+
+  // -- A3: IQR rejection on r = z_colmap / (z_mono + 1e-6) --
+  int n2 = n1;
+  if (cfg.robust && n1 > 10) {
+    for (int i = tid; i < n1; i += kStatsThreads) ratio[i] = __fdiv_rn(zc[i], __fadd_rn(zd[i], 1e-6f));
+    __syncthreads();
+    block_sort_by(sortbuf, n1, [&](int i) { return ordered_bits(ratio[i]); });
+    if (tid == 0) {
+      auto sorted = [&](int r) { return ratio[(unsigned)(sortbuf[r] & 0xffffffffu)]; };
+      const float med = sorted((n1 - 1) >> 1);  // torch.median = lower median
+      float q[2];
+      const float qs[2] = {0.75f, 0.25f};
+      for (int k = 0; k < 2; ++k) {  // torch.quantile, linear interpolation
+        const float rank = __fmul_rn(qs[k], (float)(n1 - 1));
+        const int rb = (int)rank;
+        const int ra = (int)ceilf(rank);
+        const float wgt = __fadd_rn(rank, -(float)rb);
+        const float a = sorted(rb), b = sorted(ra);
+        const float diff = __fadd_rn(b, -a);
+        q[k] = (wgt < 0.5f) ? __fadd_rn(a, __fmul_rn(wgt, diff)) : __fadd_rn(b, -__fmul_rn(diff, __fadd_rn(1.f, -wgt)));
+      }
+      s_f[0] = med;
+      s_f[1] = __fmul_rn(cfg.outlier_threshold, __fadd_rn(q[0], -q[1]));
+    }
+    __syncthreads();
+    const float med = s_f[0], thr = s_f[1];
+    n2 = 0;
+    // in-place order-preserving compaction: slot <= i always, chunks processed in order
+    for (int c0 = 0; c0 < n1; c0 += kStatsThreads) {
+      const int i = c0 + tid;
+      float a = 0.f, b = 0.f;
+      bool keep = false;
+      if (i < n1) {
+        a = zd[i];
+        b = zc[i];
+        keep = fabsf(__fadd_rn(ratio[i], -med)) < thr;
+      }
+      const int slot = block_compact_slot(keep, n2, s_warp);  // contains __syncthreads
+      if (slot >= 0) {
+        zd[slot] = a;
+        zc[slot] = b;
+      }
+      __syncthreads();
+    }
+    st.outliers_removed = n1 - n2;
+  }
+  st.num_correspondences = n2;
+  if (n2 < cfg.min_correspondences || n2 == 0) {
+    if (tid == 0) {
+      st.status = DDN_VIEW_TOO_FEW;
+      stats[v] = st;
+    }
+    return;
+  }
+
+  // -- A4: subsample to max_pairs with the hash permutation (replaces torch.randperm) --
+  int n3 = n2;
+  if (cfg.mode == 0 && cfg.adaptive_correspondences && n2 > cfg.max_pairs) {
+    const unsigned seed = cfg.subsample_seed;
+    block_sort_by(sortbuf, n2, [&](int i) { return mix32((unsigned)i ^ seed); });
+    n3 = cfg.max_pairs;
+    // gather in permutation order into ratio/tx as temporaries, then copy back
+    for (int r = tid; r < n3; r += kStatsThreads) {
+      const unsigned i = (unsigned)(sortbuf[r] & 0xffffffffu);
+      ratio[r] = zd[i];
+      tx[r] = zc[i];
+    }
+    __syncthreads();
+    for (int r = tid; r < n3; r += kStatsThreads) {
+      zd[r] = ratio[r];
+      zc[r] = tx[r];
+    }
+    __syncthreads();
+  }
+  st.num_correspondences = n3;
+
+  // -- A7: scale_factor = lower median of z_colmap / (z_mono + 1e-6) over the final pairs --
+  for (int i = tid; i < n3; i += kStatsThreads) ratio[i] = __fdiv_rn(zc[i], __fadd_rn(zd[i], 1e-6f));
+  __syncthreads();
+  block_sort_by(sortbuf, n3, [&](int i) { return ordered_bits(ratio[i]); });
+  if (tid == 0) st.scale_factor = ratio[(unsigned)(sortbuf[(n3 - 1) >> 1] & 0xffffffffu)];
+  __syncthreads();
+
+  if (cfg.mode == 1) {
+    // -- N1: affine least squares from five float64 sums --
+    double sd = 0, sz = 0, sdd = 0, sdz = 0;
+    for (int i = tid; i < n3; i += kStatsThreads) {
+      const double a = zd[i], b = zc[i];
+      sd += a;
+      sz += b;
+      sdd += a * a;
+      sdz += a * b;
+    }
+    sd = block_sum(sd, s_red);
+    sz = block_sum(sz, s_red);
+    sdd = block_sum(sdd, s_red);
+    sdz = block_sum(sdz, s_red);
+    if (tid == 0) {
+      const double n = (double)n3;
+      const double det = n * sdd - sd * sd;
+      if (det > 0) {
+        st.affine_scale = (float)((n * sdz - sd * sz) / det);
+        st.affine_shift = (float)((sz * sdd - sd * sdz) / det);
+      } else {
+        st.status = DDN_VIEW_DEGENERATE_FIT;
+      }
+      stats[v] = st;
+    }
+    return;
+  }
+
+  // -- A5 (table part): pairs sorted by x = z_mono, ties by original order --
+  block_sort_by(sortbuf, n3, [&](int i) { return ordered_bits(zd[i]); });
+  for (int r = tid; r < n3; r += kStatsThreads) {
+    const unsigned i = (unsigned)(sortbuf[r] & 0xffffffffu);
+    tx[r] = zd[i];
+    ty[r] = zc[i];
+  }
+  if (tid == 0) {
+    st.num_table = n3;
+    stats[v] = st;
+  }
+}
+
+// ---- K3 ---------------------------------------------------------------------------------------------
+constexpr int kTileW = 64, kTileH = 32, kRemapThreads = 256;
+constexpr int kHaloW = kTileW + 2, kHaloH = kTileH + 2;
+constexpr int kLutSmemMax = 4096;  // knots kept in shared memory (32 KB); larger tables read global
+
+__device__ __forceinline__ void cswap(float& a, float& b) {
+  const float lo = fminf(a, b), hi = fmaxf(a, b);
+  a = lo;
+  b = hi;
+}
+// median of 9 (19 compare-exchanges), i.e. the 5th smallest as torch.median(dim) over 9 returns
+__device__ __forceinline__ float median9(float p0, float p1, float p2, float p3, float p4, float p5, float p6,
+                                         float p7, float p8) {
+  cswap(p1, p2); cswap(p4, p5); cswap(p7, p8);
+  cswap(p0, p1); cswap(p3, p4); cswap(p6, p7);
+  cswap(p1, p2); cswap(p4, p5); cswap(p7, p8);
+  cswap(p0, p3); cswap(p5, p8); cswap(p4, p7);
+  cswap(p3, p6); cswap(p1, p4); cswap(p2, p5);
+  cswap(p4, p7); cswap(p4, p2); cswap(p6, p4);
+  cswap(p4, p2);
+  return p4;
+}
+
+__device__ __forceinline__ float pwl_eval(float d, const float* __restrict__ xs, const float* __restrict__ ys, int n) {
+  // i = clamp(searchsorted_left(xs, d), 1, n-1)  (depth_refiner.py:157-158)
+  int lo = 0, len = n;
+  while (len > 0) {
+    const int half = len >> 1;
+    const bool less = xs[lo + half] < d;
+    lo = less ? lo + half + 1 : lo;
+    len = less ? len - half - 1 : half;
+  }
+  const int i = min(max(lo, 1), n - 1);
+  const float x0 = xs[i - 1], x1 = xs[i], y0 = ys[i - 1], y1 = ys[i];
+  float dx = __fadd_rn(x1, -x0);
+  dx = dx == 0.f ? 1e-6f : dx;
+  float t = __fdiv_rn(__fadd_rn(d, -x0), dx);
+  t = fminf(fmaxf(t, 0.f), 1.f);
+  return fmaxf(__fadd_rn(y0, __fmul_rn(t, __fadd_rn(y1, -y0))), 1e-3f);
+}
+
+__global__ void __launch_bounds__(kRemapThreads)
+remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y, const float* __restrict__ depth,
+                    const uint8_t* __restrict__ mask, const ddn_view_stats* __restrict__ stats, AlignWorkspace ws,
+                    float* __restrict__ refined, int lut_cap) {
+  extern __shared__ __align__(16) float s_dyn[];  // LUT xs | ys (when it fits)
+  __shared__ float s_val[kHaloH][kHaloW];
+  __shared__ uint8_t s_msk[kHaloH][kHaloW + 2];
+
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x;
+  const int v = blockIdx.y;
+  const int ty0 = (tile / tiles_x) * kTileH, tx0 = (tile % tiles_x) * kTileW;
+  const size_t HW = (size_t)H * W;
+  const float* __restrict__ dmap = depth + (size_t)v * HW;
+  const uint8_t* __restrict__ mmap = mask ? mask + (size_t)v * HW : nullptr;
+  float* __restrict__ out = refined + (size_t)v * HW;
+  const ddn_view_stats st = stats[v];
+
+  if (st.status != DDN_VIEW_REFINED) {
+    // Views the reference returns unchanged (or skips): copy / zero, no remap.
+    for (int i = tid; i < kTileW * kTileH; i += kRemapThreads) {
+      const int y = ty0 + i / kTileW, x = tx0 + i % kTileW;
+      if (y < H && x < W) {
+        const size_t g = (size_t)y * W + x;
+        float d = dmap[g];
+        if (st.status == DDN_VIEW_NO_SPARSE) d = 0.f;
+        else if (cfg.zero_unmasked_passthrough && !(mmap ? mmap[g] != 0 : d > 0.f)) d = 0.f;
+        out[g] = d;
+      }
+    }
+    return;
+  }
+
+  const int n = st.num_table;
+  const float* xs = ws.tx + (size_t)v * ws.C;
+  const float* ys = ws.ty + (size_t)v * ws.C;
+  if (cfg.mode == 0 && n <= lut_cap) {
+    float* sx = s_dyn;
+    float* sy = s_dyn + n;
+    for (int i = tid; i < n; i += kRemapThreads) {
+      sx[i] = xs[i];
+      sy[i] = ys[i];
+    }
+    xs = sx;
+    ys = sy;
+    __syncthreads();
+  }
+  const float a_s = st.affine_scale, a_t = st.affine_shift;
+
+  // remap tile + 1-pixel replicate halo into shared memory
+  for (int i = tid; i < kHaloW * kHaloH; i += kRemapThreads) {
+    const int hy = i / kHaloW, hx = i - hy * kHaloW;
+    const int y = min(max(ty0 + hy - 1, 0), H - 1), x = min(max(tx0 + hx - 1, 0), W - 1);
+    const size_t g = (size_t)y * W + x;
+    const float d = __ldg(dmap + g);
+    const bool mk = mmap ? (__ldg(mmap + g) != 0) : (d > 0.f);
+    float val = 0.f;
+    if (mk) {
+      if (cfg.mode == 0) {
+        val = (n >= 2) ? pwl_eval(d, xs, ys, n) : __fmul_rn(d, __fdiv_rn(ys[0], __fadd_rn(xs[0], 1e-6f)));
+      } else {
+        val = fmaxf(__fadd_rn(__fmul_rn(d, a_s), a_t), 1e-3f);
+      }
+    }
+    s_val[hy][hx] = val;
+    s_msk[hy][hx] = mk ? 1 : 0;
+  }
+  __syncthreads();
+
+  const int lx = tid & (kTileW - 1);
+  const int x = tx0 + lx;
+  if (x >= W) return;
+#pragma unroll
+  for (int r = 0; r < kTileH / (kRemapThreads / kTileW); ++r) {
+    const int ly = (tid / kTileW) + r * (kRemapThreads / kTileW);
+    const int y = ty0 + ly;
+    if (y >= H) break;
+    float o;
+    if (cfg.skip_smoothing) {
+      o = s_val[ly + 1][lx + 1];
+    } else {
+      o = median9(s_val[ly][lx], s_val[ly][lx + 1], s_val[ly][lx + 2], s_val[ly + 1][lx], s_val[ly + 1][lx + 1],
+                  s_val[ly + 1][lx + 2], s_val[ly + 2][lx], s_val[ly + 2][lx + 1], s_val[ly + 2][lx + 2]);
+    }
+    out[(size_t)y * W + x] = s_msk[ly + 1][lx + 1] ? o : 0.f;
+  }
+}
+
+}  // namespace ddn
+
+extern "C" {
+
+int ddn_align_workspace_bytes(int64_t n_views, int64_t max_sparse_per_view, int64_t* bytes_out) {
+  using namespace ddn;
+  DDN_REQUIRE(bytes_out != nullptr, "null bytes_out");
+  DDN_REQUIRE(n_views >= 0 && max_sparse_per_view >= 0, "negative size");
+  *bytes_out = align_ws_bytes(n_views, max_sparse_per_view > 0 ? max_sparse_per_view : 1);
+  return DDN_OK;
+}
+
+int ddn_align_views(const ddn_align_config* cfg, int64_t n_views, int64_t height, int64_t width,
+                    const float* depth, const uint8_t* mask, const double* cam_from_world,
+                    const double* kmat, const double* sparse_xyz, const int64_t* sparse_offsets,
+                    int64_t max_sparse_per_view, float* refined, ddn_view_stats* stats,
+                    void* workspace, int64_t workspace_bytes, void* stream) {
+  using namespace ddn;
+  DDN_REQUIRE(cfg != nullptr, "null config");
+  DDN_REQUIRE(n_views >= 0 && height > 1 && width > 1, "shape");
+  DDN_REQUIRE(height * width < (1ll << 31), "image too large");
+  DDN_REQUIRE(cfg->mode == 0 || cfg->mode == 1, "mode");
+  DDN_REQUIRE(cfg->max_pairs >= 1, "max_pairs");
+  if (n_views == 0) return DDN_OK;
+  DDN_REQUIRE(n_views <= 65535, "too many views per call");
+  DDN_REQUIRE(depth && cam_from_world && kmat && sparse_offsets && refined && stats && workspace, "null pointer");
+  const int64_t C = max_sparse_per_view > 0 ? max_sparse_per_view : 1;
+  DDN_REQUIRE(C < (1ll << 30), "max_sparse_per_view");
+  if (workspace_bytes < align_ws_bytes(n_views, C)) {
+    set_error("align workspace too small: %lld < %lld", (long long)workspace_bytes, (long long)align_ws_bytes(n_views, C));
+    return DDN_ERR_WORKSPACE_TOO_SMALL;
+  }
+  AlignWorkspace ws = carve(workspace, n_views, C);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int in_smem = ws.Cp <= kSortSmemMax ? 1 : 0;
+  const size_t smem_sort = in_smem ? (size_t)ws.Cp * 8 : 0;
+  DDN_TRY(check_cuda(cudaFuncSetAttribute(align_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sort),
+                     "cudaFuncSetAttribute(align_stats)"));
+  align_stats_kernel<<<(unsigned)n_views, kStatsThreads, smem_sort, st>>>(*cfg, (int)height, (int)width, depth,
+                                                                         cam_from_world, kmat, sparse_xyz,
+                                                                         sparse_offsets, ws, stats, in_smem);
+  DDN_TRY(after_launch("align_stats_kernel"));
+  const int tiles_x = (int)((width + kTileW - 1) / kTileW), tiles_y = (int)((height + kTileH - 1) / kTileH);
+  // largest table any view can have: max_pairs when subsampling, else every surviving pair
+  int64_t lut = (cfg->adaptive_correspondences && cfg->max_pairs < C) ? cfg->max_pairs : C;
+  if (cfg->mode != 0 || lut > kLutSmemMax) lut = 0;  // affine mode has no table; huge tables stay in global
+  const size_t smem_lut = (size_t)lut * 8;
+  DDN_TRY(check_cuda(cudaFuncSetAttribute(remap_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lut),
+                     "cudaFuncSetAttribute(remap_median)"));
+  dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)n_views);
+  remap_median_kernel<<<grid, kRemapThreads, smem_lut, st>>>(*cfg, (int)height, (int)width, tiles_x, tiles_y, depth, mask,
+                                                            stats, ws, refined, (int)lut);
+  return after_launch("remap_median_kernel");
+}
+
+}  // extern "C"

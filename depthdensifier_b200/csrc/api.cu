@@ -1,0 +1,53 @@
+// Library-level entry points of libddn_b200.so: version, error string, launch counter, defaults.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace ddn {
+
+static thread_local char t_error[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_error, sizeof(t_error), fmt, ap);
+  va_end(ap);
+}
+
+}  // namespace ddn
+
+extern "C" {
+
+int ddn_version(void) { return DDN_VERSION; }
+
+const char* ddn_last_error_string(void) { return ddn::t_error; }
+
+int64_t ddn_launch_count(void) { return ddn::g_launches.load(std::memory_order_relaxed); }
+
+void ddn_align_config_default(ddn_align_config* cfg) {
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->min_correspondences = 50;
+  cfg->edge_margin = 10;
+  cfg->robust = 1;
+  cfg->outlier_threshold = 2.5f;
+  cfg->skip_smoothing = 0;
+  cfg->adaptive_correspondences = 1;
+  cfg->max_pairs = 500;
+  cfg->mode = 0;
+  cfg->subsample_seed = 0;
+  cfg->zero_unmasked_passthrough = 0;
+}
+
+void ddn_filter_config_default(ddn_filter_config* cfg) {
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->depth_threshold = 0.7f;
+  cfg->grazing_cos = 0.087f;
+  cfg->sample_mode = 0;
+  cfg->two_sided_tau = 0.0f;
+  cfg->stride = 1;
+  cfg->normals_in_world = 0;
+}
+
+}  // extern "C"

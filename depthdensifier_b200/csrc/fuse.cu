@@ -1,0 +1,271 @@
+// Stage 4: voxel-grid fusion (new capability; the reference only concatenates
+// points, scripts/test.py:353-359).
+//
+//   K5 voxel_key_kernel     quantise kept points to voxel coordinates with IEEE float32
+//                           sub/div/floor (bit-exact with the numpy definition) and pack them into a
+//                           COMPACT key that only spends the bits the bounding box needs, so the
+//                           radix sort runs 4 passes over 32-bit keys instead of 8 over 64-bit ones.
+//   K6 sort                 (key, point index) pairs, least-significant-digit radix sort.
+//   K7 segment_mean_kernel  one run of equal keys = one voxel: integer fixed-point sums of
+//                           (p - voxel centre) and of colours, so the result does not depend on the
+//                           order of points inside a voxel (deterministic across rank counts).
+//
+// Round-1 note: K6 and the run-length/scan steps call CUB device primitives (header-only, shipped with
+// the CUDA toolkit) as a stepping stone; keys, sums and outputs are this library's own kernels.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace ddn {
+
+struct GridDev {
+  float voxel, ox, oy, oz;
+  int bx, by, bz;
+};
+
+constexpr int kKeyThreads = 256;
+
+template <typename KeyT>
+__global__ void __launch_bounds__(kKeyThreads)
+voxel_key_kernel(GridDev g, int64_t n, const float* __restrict__ xyz, const uint8_t* __restrict__ votes, int thr,
+                 KeyT* __restrict__ keys, uint32_t* __restrict__ idx) {
+  const int64_t i = (int64_t)blockIdx.x * kKeyThreads + threadIdx.x;
+  if (i >= n) return;
+  const KeyT sentinel = (KeyT)1 << (g.bx + g.by + g.bz);
+  bool take = votes == nullptr || (int)votes[i] < thr;
+  KeyT key = sentinel;
+  if (take) {
+    const float x = xyz[i * 3 + 0], y = xyz[i * 3 + 1], z = xyz[i * 3 + 2];
+    const float fx = floorf(__fdiv_rn(__fsub_rn(x, g.ox), g.voxel));
+    const float fy = floorf(__fdiv_rn(__fsub_rn(y, g.oy), g.voxel));
+    const float fz = floorf(__fdiv_rn(__fsub_rn(z, g.oz), g.voxel));
+    const bool inside = fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)(1u << g.bx) && fy < (float)(1u << g.by) &&
+                        fz < (float)(1u << g.bz);
+    if (inside) key = (KeyT)(uint32_t)fx | ((KeyT)(uint32_t)fy << g.bx) | ((KeyT)(uint32_t)fz << (g.bx + g.by));
+  }
+  keys[i] = key;
+  idx[i] = (uint32_t)i;
+}
+
+__global__ void canonical_key_kernel(GridDev g, int64_t n, const float* __restrict__ xyz, uint64_t* __restrict__ keys) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = xyz[i * 3 + 0], y = xyz[i * 3 + 1], z = xyz[i * 3 + 2];
+  const int64_t kx = (int64_t)floorf(__fdiv_rn(__fsub_rn(x, g.ox), g.voxel));
+  const int64_t ky = (int64_t)floorf(__fdiv_rn(__fsub_rn(y, g.oy), g.voxel));
+  const int64_t kz = (int64_t)floorf(__fdiv_rn(__fsub_rn(z, g.oz), g.voxel));
+  const bool ok = kx >= 0 && ky >= 0 && kz >= 0 && kx < (1 << 21) && ky < (1 << 21) && kz < (1 << 21);
+  keys[i] = ok ? ((uint64_t)kx | ((uint64_t)ky << 21) | ((uint64_t)kz << 42)) : ~0ull;
+}
+
+template <typename KeyT>
+__global__ void fuse_finalize_kernel(GridDev g, int64_t n, const KeyT* __restrict__ unique_keys,
+                                     const int* __restrict__ run_counts, const int* __restrict__ num_runs,
+                                     int64_t* __restrict__ counts_out) {
+  const int r = *num_runs;
+  const KeyT sentinel = (KeyT)1 << (g.bx + g.by + g.bz);
+  int64_t m = n, mv = r;
+  if (r > 0 && unique_keys[r - 1] == sentinel) {
+    mv = r - 1;
+    m = n - run_counts[r - 1];
+  }
+  counts_out[0] = m;
+  counts_out[1] = mv;
+}
+
+constexpr int kFixShift = 20;  // offsets are stored in units of voxel * 2^-20
+
+template <typename KeyT>
+__global__ void __launch_bounds__(256)
+segment_mean_kernel(GridDev g, const KeyT* __restrict__ unique_keys, const int* __restrict__ run_counts,
+                    const int* __restrict__ run_starts, const int64_t* __restrict__ counts,
+                    const uint32_t* __restrict__ sorted_idx, const float* __restrict__ xyz,
+                    const uint8_t* __restrict__ rgb, uint64_t* __restrict__ out_keys, float* __restrict__ out_xyz,
+                    uint8_t* __restrict__ out_rgb, int32_t* __restrict__ out_count) {
+  const int64_t mv = counts[1];
+  const float scale = (float)(1 << kFixShift);
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < mv; r += (int64_t)gridDim.x * blockDim.x) {
+    const KeyT key = unique_keys[r];
+    const uint32_t kx = (uint32_t)(key & (((KeyT)1 << g.bx) - 1));
+    const uint32_t ky = (uint32_t)((key >> g.bx) & (((KeyT)1 << g.by) - 1));
+    const uint32_t kz = (uint32_t)((key >> (g.bx + g.by)) & (((KeyT)1 << g.bz) - 1));
+    // voxel centre in float32; p - centre is exact in float32 for points inside the voxel
+    const float cx = __fadd_rn(g.ox, __fmul_rn((float)kx + 0.5f, g.voxel));
+    const float cy = __fadd_rn(g.oy, __fmul_rn((float)ky + 0.5f, g.voxel));
+    const float cz = __fadd_rn(g.oz, __fmul_rn((float)kz + 0.5f, g.voxel));
+    const int start = run_starts[r], cnt = run_counts[r];
+    long long sx = 0, sy = 0, sz = 0;
+    unsigned long long sr = 0, sg = 0, sb = 0;
+    for (int j = 0; j < cnt; ++j) {
+      const size_t i = sorted_idx[start + j];
+      const float x = __ldg(xyz + i * 3 + 0), y = __ldg(xyz + i * 3 + 1), z = __ldg(xyz + i * 3 + 2);
+      sx += __float2ll_rn(__fmul_rn(__fdiv_rn(__fsub_rn(x, cx), g.voxel), scale));
+      sy += __float2ll_rn(__fmul_rn(__fdiv_rn(__fsub_rn(y, cy), g.voxel), scale));
+      sz += __float2ll_rn(__fmul_rn(__fdiv_rn(__fsub_rn(z, cz), g.voxel), scale));
+      sr += __ldg(rgb + i * 3 + 0);
+      sg += __ldg(rgb + i * 3 + 1);
+      sb += __ldg(rgb + i * 3 + 2);
+    }
+    const double inv = (double)g.voxel / ((double)cnt * (double)(1 << kFixShift));
+    out_xyz[r * 3 + 0] = (float)((double)cx + (double)sx * inv);
+    out_xyz[r * 3 + 1] = (float)((double)cy + (double)sy * inv);
+    out_xyz[r * 3 + 2] = (float)((double)cz + (double)sz * inv);
+    const unsigned long long c2 = 2ull * (unsigned long long)cnt;
+    out_rgb[r * 3 + 0] = (uint8_t)((2 * sr + cnt) / c2);
+    out_rgb[r * 3 + 1] = (uint8_t)((2 * sg + cnt) / c2);
+    out_rgb[r * 3 + 2] = (uint8_t)((2 * sb + cnt) / c2);
+    out_keys[r] = (uint64_t)kx | ((uint64_t)ky << 21) | ((uint64_t)kz << 42);
+    out_count[r] = cnt;
+  }
+}
+
+struct FuseLayout {
+  size_t keys_a, keys_b, idx_a, idx_b, uniq, run_counts, run_starts, num_runs, cub_temp, total;
+  size_t cub_temp_bytes;
+};
+
+template <typename KeyT>
+static int fuse_layout(int64_t n, FuseLayout* L) {
+  size_t t_sort = 0, t_rle = 0, t_scan = 0;
+  cub::DoubleBuffer<KeyT> dk(nullptr, nullptr);
+  cub::DoubleBuffer<uint32_t> dv(nullptr, nullptr);
+  DDN_TRY(check_cuda(cub::DeviceRadixSort::SortPairs(nullptr, t_sort, dk, dv, (int)n, 0, (int)sizeof(KeyT) * 8),
+                     "cub sort size"));
+  DDN_TRY(check_cuda(cub::DeviceRunLengthEncode::Encode(nullptr, t_rle, (KeyT*)nullptr, (KeyT*)nullptr, (int*)nullptr,
+                                                        (int*)nullptr, (int)n),
+                     "cub rle size"));
+  DDN_TRY(check_cuda(cub::DeviceScan::ExclusiveSum(nullptr, t_scan, (int*)nullptr, (int*)nullptr, (int)n), "cub scan size"));
+  size_t temp = t_sort > t_rle ? t_sort : t_rle;
+  temp = temp > t_scan ? temp : t_scan;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (size_t)align_up((int64_t)bytes, 256);
+    return o;
+  };
+  L->keys_a = take(n * sizeof(KeyT));
+  L->keys_b = take(n * sizeof(KeyT));
+  L->idx_a = take(n * 4);
+  L->idx_b = take(n * 4);
+  L->uniq = take(n * sizeof(KeyT));
+  L->run_counts = take(n * 4);
+  L->run_starts = take((n + 1) * 4);
+  L->num_runs = take(16);
+  L->cub_temp = take(temp);
+  L->cub_temp_bytes = temp;
+  L->total = off + 256;
+  return DDN_OK;
+}
+
+template <typename KeyT>
+static int fuse_impl(const GridDev& g, int64_t n, const float* xyz, const uint8_t* rgb, const uint8_t* votes, int thr,
+                     uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb, int32_t* out_count, int64_t* counts_out,
+                     void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+  FuseLayout L;
+  DDN_TRY(fuse_layout<KeyT>(n, &L));
+  if ((int64_t)L.total > workspace_bytes) {
+    set_error("fuse workspace too small: %lld < %lld", (long long)workspace_bytes, (long long)L.total);
+    return DDN_ERR_WORKSPACE_TOO_SMALL;
+  }
+  char* base = reinterpret_cast<char*>(align_up((int64_t)(uintptr_t)workspace, 256));
+  KeyT* keys_a = (KeyT*)(base + L.keys_a);
+  KeyT* keys_b = (KeyT*)(base + L.keys_b);
+  uint32_t* idx_a = (uint32_t*)(base + L.idx_a);
+  uint32_t* idx_b = (uint32_t*)(base + L.idx_b);
+  KeyT* uniq = (KeyT*)(base + L.uniq);
+  int* run_counts = (int*)(base + L.run_counts);
+  int* run_starts = (int*)(base + L.run_starts);
+  int* num_runs = (int*)(base + L.num_runs);
+  void* temp = base + L.cub_temp;
+  size_t temp_bytes = L.cub_temp_bytes;
+
+  const unsigned blocks = (unsigned)((n + kKeyThreads - 1) / kKeyThreads);
+  voxel_key_kernel<KeyT><<<blocks, kKeyThreads, 0, st>>>(g, n, xyz, votes, thr, keys_a, idx_a);
+  DDN_TRY(after_launch("voxel_key_kernel"));
+
+  cub::DoubleBuffer<KeyT> dk(keys_a, keys_b);
+  cub::DoubleBuffer<uint32_t> dv(idx_a, idx_b);
+  const int end_bit = g.bx + g.by + g.bz + 1;  // + the sentinel bit
+  DDN_TRY(check_cuda(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, dk, dv, (int)n, 0, end_bit, st), "cub sort"));
+  g_launches.fetch_add((end_bit + 7) / 8 + 1, std::memory_order_relaxed);
+  temp_bytes = L.cub_temp_bytes;
+  DDN_TRY(check_cuda(cub::DeviceRunLengthEncode::Encode(temp, temp_bytes, dk.Current(), uniq, run_counts, num_runs, (int)n, st),
+                     "cub rle"));
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  temp_bytes = L.cub_temp_bytes;
+  DDN_TRY(check_cuda(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, run_counts, run_starts, (int)n, st), "cub scan"));
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  fuse_finalize_kernel<KeyT><<<1, 1, 0, st>>>(g, n, uniq, run_counts, num_runs, counts_out);
+  DDN_TRY(after_launch("fuse_finalize_kernel"));
+  segment_mean_kernel<KeyT><<<kNumSMs * 8, 256, 0, st>>>(g, uniq, run_counts, run_starts, counts_out, dv.Current(), xyz,
+                                                        rgb, out_keys, out_xyz, out_rgb, out_count);
+  return after_launch("segment_mean_kernel");
+}
+
+static int grid_from_host(const ddn_voxel_grid* h, GridDev* g) {
+  DDN_REQUIRE(h != nullptr, "null grid");
+  DDN_REQUIRE(h->voxel > 0.f, "voxel size");
+  for (int i = 0; i < 3; ++i) DDN_REQUIRE(h->bits[i] >= 1 && h->bits[i] <= 21, "bits per axis must be in [1,21]");
+  g->voxel = h->voxel;
+  g->ox = h->origin[0];
+  g->oy = h->origin[1];
+  g->oz = h->origin[2];
+  g->bx = h->bits[0];
+  g->by = h->bits[1];
+  g->bz = h->bits[2];
+  return DDN_OK;
+}
+
+}  // namespace ddn
+
+extern "C" {
+
+int ddn_fuse_workspace_bytes(int64_t n_points, int64_t* bytes_out) {
+  using namespace ddn;
+  DDN_REQUIRE(bytes_out != nullptr, "null bytes_out");
+  DDN_REQUIRE(n_points >= 0 && n_points < (1ll << 31) - 1024, "n_points");
+  FuseLayout L;
+  DDN_TRY(fuse_layout<uint64_t>(n_points > 0 ? n_points : 1, &L));  // worst case (64-bit keys)
+  *bytes_out = (int64_t)L.total;
+  return DDN_OK;
+}
+
+int ddn_voxel_fuse(const ddn_voxel_grid* grid_host, int64_t n_points, const float* xyz, const uint8_t* rgb,
+                   const uint8_t* votes, int32_t vote_threshold, uint64_t* out_keys, float* out_xyz,
+                   uint8_t* out_rgb, int32_t* out_count, int64_t* counts_out, void* workspace,
+                   int64_t workspace_bytes, void* stream) {
+  using namespace ddn;
+  GridDev g;
+  DDN_TRY(grid_from_host(grid_host, &g));
+  DDN_REQUIRE(n_points >= 0 && n_points < (1ll << 31) - 1024, "n_points");
+  DDN_REQUIRE(counts_out != nullptr, "null counts_out");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_points == 0) {
+    return check_cuda(cudaMemsetAsync(counts_out, 0, 16, st), "memset counts");
+  }
+  DDN_REQUIRE(xyz && rgb && out_keys && out_xyz && out_rgb && out_count && workspace, "null pointer");
+  const int total_bits = g.bx + g.by + g.bz;
+  if (total_bits <= 31)
+    return fuse_impl<uint32_t>(g, n_points, xyz, rgb, votes, vote_threshold, out_keys, out_xyz, out_rgb, out_count,
+                               counts_out, workspace, workspace_bytes, st);
+  return fuse_impl<uint64_t>(g, n_points, xyz, rgb, votes, vote_threshold, out_keys, out_xyz, out_rgb, out_count,
+                             counts_out, workspace, workspace_bytes, st);
+}
+
+int ddn_voxel_keys(const ddn_voxel_grid* grid_host, int64_t n_points, const float* xyz, uint64_t* keys, void* stream) {
+  using namespace ddn;
+  DDN_REQUIRE(grid_host != nullptr && grid_host->voxel > 0.f, "grid");
+  DDN_REQUIRE(n_points >= 0, "n_points");
+  if (n_points == 0) return DDN_OK;
+  DDN_REQUIRE(xyz && keys, "null pointer");
+  GridDev g;
+  g.voxel = grid_host->voxel;
+  g.ox = grid_host->origin[0];
+  g.oy = grid_host->origin[1];
+  g.oz = grid_host->origin[2];
+  g.bx = g.by = g.bz = 21;
+  canonical_key_kernel<<<(unsigned)((n_points + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g, n_points, xyz, keys);
+  return after_launch("canonical_key_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,268 @@
+"""Device-tensor wrappers around the C ABI.  torch is plumbing only (device memory + streams); every
+op below runs a hand-written sm_100a kernel from libddn_b200.so and raises when no GPU is present."""
+
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import DDNError
+
+STATUS_REFINED = 0
+STATUS_NAMES = {
+    0: "refined",
+    1: "no_points_in_bounds",
+    2: "no_positive_samples",
+    3: "too_few_correspondences",
+    4: "degenerate_fit",
+    5: "no_sparse_points",
+}
+
+
+def _require_cuda(*tensors) -> torch.device:
+    if not torch.cuda.is_available():
+        raise DDNError("no CUDA device available: depthdensifier_b200 has no CPU fallback")
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise DDNError("expected CUDA tensors")
+        if not t.is_contiguous():
+            raise DDNError("expected contiguous tensors")
+        dev = t.device if dev is None else dev
+        if t.device != dev:
+            raise DDNError("tensors on different devices")
+    return dev
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+@dataclass
+class AlignOptions:
+    """RefinerConfig fields (depth_refiner.py:16-31) + the north-star mode switch."""
+
+    min_correspondences: int = 50
+    edge_margin: int = 10
+    robust: bool = True
+    outlier_threshold: float = 2.5
+    skip_smoothing: bool = False
+    adaptive_correspondences: bool = True
+    max_pairs: int = 500
+    align_mode: str = "pwl"
+    subsample_seed: int = 0
+    zero_unmasked_passthrough: bool = False
+
+    def to_c(self) -> _lib.AlignConfig:
+        if self.align_mode not in ("pwl", "affine"):
+            raise ValueError("align_mode must be 'pwl' or 'affine'")
+        return _lib.AlignConfig(
+            int(self.min_correspondences),
+            int(self.edge_margin),
+            int(bool(self.robust)),
+            float(self.outlier_threshold),
+            int(bool(self.skip_smoothing)),
+            int(bool(self.adaptive_correspondences)),
+            int(self.max_pairs),
+            0 if self.align_mode == "pwl" else 1,
+            int(self.subsample_seed) & 0xFFFFFFFF,
+            int(bool(self.zero_unmasked_passthrough)),
+        )
+
+
+@dataclass
+class FilterOptions:
+    depth_threshold: float = 0.7
+    grazing_cos: float = 0.087
+    sample_mode: str = "nearest"
+    two_sided_tau: float = 0.0
+    stride: int = 1
+    normals_in_world: bool = False
+
+    def to_c(self) -> _lib.FilterConfig:
+        if self.sample_mode not in ("nearest", "bilinear"):
+            raise ValueError("sample_mode must be 'nearest' or 'bilinear'")
+        return _lib.FilterConfig(
+            float(self.depth_threshold),
+            float(self.grazing_cos),
+            0 if self.sample_mode == "nearest" else 1,
+            float(self.two_sided_tau),
+            int(self.stride),
+            int(bool(self.normals_in_world)),
+        )
+
+
+def align_views(depth, mask, cam_from_world, kmat, sparse_xyz, sparse_offsets, max_sparse_per_view: int,
+                opts: AlignOptions, out=None):
+    """Stage 1 for V views.  Returns (refined [V,H,W] f32, stats [V,8] int32 raw ddn_view_stats)."""
+    lib = _lib.load()
+    dev = _require_cuda(depth, mask, cam_from_world, kmat, sparse_xyz, sparse_offsets, out)
+    V, H, W = depth.shape
+    assert depth.dtype == torch.float32 and cam_from_world.dtype == torch.float64 and kmat.dtype == torch.float64
+    assert sparse_xyz.dtype == torch.float64 and sparse_offsets.dtype == torch.int64
+    assert mask is None or (mask.dtype in (torch.bool, torch.uint8) and mask.shape == depth.shape)
+    assert tuple(cam_from_world.shape) == (V, 3, 4) and tuple(kmat.shape) == (V, 3, 3)
+    refined = out if out is not None else torch.empty_like(depth)
+    stats = torch.zeros((V, 8), dtype=torch.int32, device=dev)
+    nbytes = C.c_int64(0)
+    _lib.check(lib.ddn_align_workspace_bytes(V, max_sparse_per_view, C.byref(nbytes)))
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+    cfg = opts.to_c()
+    with torch.cuda.device(dev):
+        _lib.check(
+            lib.ddn_align_views(
+                C.byref(cfg), V, H, W, _p(depth), _p(mask), _p(cam_from_world), _p(kmat), _p(sparse_xyz),
+                _p(sparse_offsets), int(max_sparse_per_view), _p(refined), _p(stats), _p(ws), nbytes.value, _stream(),
+            )
+        )
+    return refined, stats
+
+
+def decode_stats(stats: torch.Tensor) -> list[dict]:
+    """Host dicts from the raw [V,8] int32 stats tensor (synchronises)."""
+    s = stats.cpu().numpy()
+    f = s.view(np.float32)
+    out = []
+    for v in range(s.shape[0]):
+        out.append(
+            {
+                "status": int(s[v, 0]),
+                "num_correspondences": int(s[v, 1]),
+                "outliers_removed": int(s[v, 2]),
+                "num_table": int(s[v, 3]),
+                "scale_factor": float(f[v, 4]),
+                "affine_scale": float(f[v, 5]),
+                "affine_shift": float(f[v, 6]),
+            }
+        )
+    return out
+
+
+def build_pair_tables(cam_from_world, intr, nbr, src_begin: int, n_src: int):
+    lib = _lib.load()
+    dev = _require_cuda(cam_from_world, intr, nbr)
+    V = cam_from_world.shape[0]
+    K = nbr.shape[1]
+    assert cam_from_world.dtype == torch.float64 and intr.dtype == torch.float64 and nbr.dtype == torch.int32
+    assert tuple(intr.shape) == (V, 4) and nbr.shape[0] == V
+    pair = torch.empty((n_src, K, _lib.PAIR_TABLE_FLOATS), dtype=torch.float32, device=dev)
+    src = torch.empty((n_src, 16), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ddn_build_pair_tables(V, src_begin, n_src, K, _p(cam_from_world), _p(intr), _p(nbr), _p(pair), _p(src), _stream()))
+    return pair, src
+
+
+def new_bbox(dev) -> torch.Tensor:
+    lib = _lib.load()
+    bbox = torch.empty(6, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ddn_bbox_init(_p(bbox), _stream()))
+    return bbox
+
+
+def decode_bbox(bbox: torch.Tensor) -> np.ndarray:
+    """[6] float32 (min xyz, max xyz) from the order-preserving int encoding (synchronises)."""
+    i = bbox.cpu().numpy().astype(np.int32)
+    i = np.where(i >= 0, i, i ^ np.int32(0x7FFFFFFF))
+    return i.view(np.float32)
+
+
+def backproject_filter(refined_all, normal, nbr, pair_table, src_table, src_begin: int, vote_threshold: int,
+                       opts: FilterOptions, bbox=None, xyz_out=None, votes_out=None):
+    """Stages 2+3 for the source views src_begin..src_begin+n_src (n_src = normal.shape[0])."""
+    lib = _lib.load()
+    dev = _require_cuda(refined_all, normal, nbr, pair_table, src_table, bbox, xyz_out, votes_out)
+    V, H, W = refined_all.shape
+    n_src = normal.shape[0]
+    K = nbr.shape[1]
+    assert refined_all.dtype == torch.float32 and normal.dtype == torch.float32
+    assert tuple(normal.shape) == (n_src, H, W, 3)
+    assert tuple(pair_table.shape) == (n_src, K, _lib.PAIR_TABLE_FLOATS) and tuple(src_table.shape) == (n_src, 16)
+    s = int(opts.stride)
+    Hs, Ws = (H + s - 1) // s, (W + s - 1) // s
+    xyz = xyz_out if xyz_out is not None else torch.empty((n_src, Hs, Ws, 3), dtype=torch.float32, device=dev)
+    votes = votes_out if votes_out is not None else torch.empty((n_src, Hs, Ws), dtype=torch.uint8, device=dev)
+    cfg = opts.to_c()
+    with torch.cuda.device(dev):
+        _lib.check(
+            lib.ddn_backproject_filter(
+                C.byref(cfg), V, src_begin, n_src, H, W, K, _p(refined_all), _p(normal), _p(nbr), _p(pair_table),
+                _p(src_table), int(vote_threshold), _p(xyz), _p(votes), _p(bbox), _stream(),
+            )
+        )
+    return xyz, votes
+
+
+def make_grid(bbox_min, bbox_max, voxel: float):
+    """Voxel grid from a bounding box: origin = floor(min/voxel)*voxel in float32 and the
+    number of significant bits per axis."""
+    v = np.float32(voxel)
+    lo = np.asarray(bbox_min, dtype=np.float32)
+    hi = np.asarray(bbox_max, dtype=np.float32)
+    origin = (np.floor(lo / v) * v).astype(np.float32)
+    cells = np.floor((hi - origin) / v).astype(np.int64) + 2
+    bits = [max(1, int(math.ceil(math.log2(max(int(c), 2))))) for c in cells]
+    if max(bits) > 21:
+        raise DDNError(f"voxel grid needs {bits} bits per axis; the 3x21-bit key allows at most 21")
+    g = _lib.VoxelGrid()
+    g.voxel = float(v)
+    for i in range(3):
+        g.origin[i] = float(origin[i])
+        g.bits[i] = bits[i]
+    return g
+
+
+def voxel_fuse(xyz, rgb, votes, vote_threshold: int, grid: _lib.VoxelGrid, trim: bool = True):
+    """Stage 4.  xyz [N,3] f32, rgb [N,3] u8, votes [N] u8 or None.  Returns keys, xyz, rgb, count
+    (trimmed to the voxel count when ``trim``; that reads the counts back and synchronises) and the
+    device counts tensor [2] = (participating points, voxels)."""
+    lib = _lib.load()
+    dev = _require_cuda(xyz, rgb, votes)
+    N = xyz.shape[0]
+    assert xyz.dtype == torch.float32 and rgb.dtype == torch.uint8 and tuple(rgb.shape) == (N, 3)
+    assert votes is None or (votes.dtype == torch.uint8 and votes.numel() == N)
+    nbytes = C.c_int64(0)
+    _lib.check(lib.ddn_fuse_workspace_bytes(N, C.byref(nbytes)))
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+    out_keys = torch.empty(N, dtype=torch.int64, device=dev)
+    out_xyz = torch.empty((N, 3), dtype=torch.float32, device=dev)
+    out_rgb = torch.empty((N, 3), dtype=torch.uint8, device=dev)
+    out_cnt = torch.empty(N, dtype=torch.int32, device=dev)
+    counts = torch.zeros(2, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(
+            lib.ddn_voxel_fuse(
+                C.byref(grid), N, _p(xyz), _p(rgb), _p(votes), int(vote_threshold), _p(out_keys), _p(out_xyz),
+                _p(out_rgb), _p(out_cnt), _p(counts), _p(ws), nbytes.value, _stream(),
+            )
+        )
+    if trim:
+        mv = int(counts[1].item())
+        return out_keys[:mv], out_xyz[:mv], out_rgb[:mv], out_cnt[:mv], counts
+    return out_keys, out_xyz, out_rgb, out_cnt, counts
+
+
+def voxel_keys(xyz, voxel: float, origin) -> torch.Tensor:
+    """Canonical 3x21-bit keys (int64 view of the uint64 key) for xyz [N,3] f32."""
+    lib = _lib.load()
+    dev = _require_cuda(xyz)
+    g = _lib.VoxelGrid()
+    g.voxel = float(np.float32(voxel))
+    for i in range(3):
+        g.origin[i] = float(np.float32(origin[i]))
+        g.bits[i] = 21
+    keys = torch.empty(xyz.shape[0], dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ddn_voxel_keys(C.byref(g), xyz.shape[0], _p(xyz), _p(keys), _stream()))
+    return keys

@@ -1,0 +1,173 @@
+/*
+ * ddn_b200.h - C ABI of the B200-native DepthDensifier hot path (libddn_b200.so).
+ *
+ * Drop-in boundary.  The reference (OpsiClear/DepthDensifier) has no FFI: the path sits behind
+ * Python calls.  Each entry point below names the reference code it replaces; the Python shim in
+ * depthdensifier_b200/ keeps the reference's names (DepthRefiner.refine_depth, project_points,
+ * unproject_points, main) and binds these symbols with ctypes.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only.  All data pointers are DEVICE pointers unless the
+ *     parameter name ends in _host.  `stream` is a cudaStream_t passed as void*.
+ *   - every call returns 0 (DDN_OK) or a negative DDN_ERR_* code; ddn_last_error_string() gives
+ *     the thread-local message.  Nothing throws across the boundary.
+ *   - the caller owns every buffer (inputs, outputs, workspaces).  A *_workspace_bytes() query
+ *     precedes any call that needs scratch.
+ *   - calls are stream-ordered and asynchronous: no hidden device synchronisation, no global
+ *     mutable state.  Counts are written to device memory; the caller decides when to sync.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef DDN_B200_H_
+#define DDN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define DDN_API __attribute__((visibility("default")))
+#else
+#define DDN_API
+#endif
+
+#define DDN_VERSION 100 /* 0.1.0, mirrors the reference package __version__ (src/depthdensifier/__init__.py:5) */
+
+enum {
+  DDN_OK = 0,
+  DDN_ERR_INVALID_ARGUMENT = -1,
+  DDN_ERR_CUDA = -2,
+  DDN_ERR_WORKSPACE_TOO_SMALL = -3,
+  DDN_ERR_UNSUPPORTED = -4
+};
+
+DDN_API int ddn_version(void);
+DDN_API const char* ddn_last_error_string(void);
+/* Number of kernels this library has launched in the calling process (for bench.py gpu_launches). */
+DDN_API int64_t ddn_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage 1 - per-view alignment of monocular depth to projected sparse points.
+ * Replaces DepthRefiner.refine_depth, src/depthdensifier/depth_refiner.py:207-328
+ * (_project_points :92-115, bounds+grid_sample :247-288, _remove_outliers_fast :117-139,
+ *  min-count gate and subsample :296-306, _pchip_interpolate_optimized :141-178,
+ *  _apply_transformation incl. 3x3 median :180-205), batched over V views.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t min_correspondences;      /* RefinerConfig.min_correspondences (50)  depth_refiner.py:21 */
+  int32_t edge_margin;              /* RefinerConfig.edge_margin (10)          :22 */
+  int32_t robust;                   /* RefinerConfig.robust (1)                :23 */
+  float outlier_threshold;          /* RefinerConfig.outlier_threshold (2.5)   :24 */
+  int32_t skip_smoothing;           /* RefinerConfig.skip_smoothing (0)        :28 */
+  int32_t adaptive_correspondences; /* RefinerConfig.adaptive_correspondences (1) :29 */
+  int32_t max_pairs;                /* 500, depth_refiner.py:302-306 */
+  int32_t mode;                     /* 0 = piecewise-linear LUT (reference); 1 = affine scale/shift LSQ (new) */
+  uint32_t subsample_seed;          /* seed of the hash permutation that replaces torch.randperm (:304) */
+  int32_t zero_unmasked_passthrough; /* 1: pass-through views are also zeroed outside the mask (scripts/test.py:194) */
+} ddn_align_config;
+
+/* status values in ddn_view_stats */
+enum {
+  DDN_VIEW_REFINED = 0,
+  DDN_VIEW_NO_POINTS_IN_BOUNDS = 1, /* depth_refiner.py:256-259 */
+  DDN_VIEW_NO_POSITIVE_SAMPLES = 2, /* :275-285 */
+  DDN_VIEW_TOO_FEW = 3,             /* :296-299 */
+  DDN_VIEW_DEGENERATE_FIT = 4,      /* affine mode only */
+  DDN_VIEW_NO_SPARSE = 5            /* scripts/test.py:136-137: view skipped by the pipeline */
+};
+
+typedef struct {
+  int32_t status;
+  int32_t num_correspondences; /* refine_depth()["num_correspondences"] */
+  int32_t outliers_removed;    /* refine_depth()["outliers_removed"] */
+  int32_t num_table;           /* knots in the view's lookup table */
+  float scale_factor;          /* refine_depth()["scale_factor"]: lower median of z_colmap/(z_depth+1e-6) */
+  float affine_scale;          /* mode 1 */
+  float affine_shift;          /* mode 1 */
+  int32_t reserved;
+} ddn_view_stats;
+
+DDN_API void ddn_align_config_default(ddn_align_config* cfg);
+
+DDN_API int ddn_align_workspace_bytes(int64_t n_views, int64_t max_sparse_per_view, int64_t* bytes_out);
+
+/* depth [V,H,W] f32; mask [V,H,W] u8 or NULL (=> depth > 0, depth_refiner.py:238-241);
+ * cam_from_world [V,3,4] f64 row-major; kmat [V,3,3] f64 (only the top two rows are used, :112);
+ * sparse_xyz [S,3] f64 world, CSR sparse_offsets [V+1] i64; refined [V,H,W] f32 out;
+ * stats [V] out.  A view with no sparse points gets status DDN_VIEW_NO_SPARSE and an all-zero map.
+ * Views that the reference returns unchanged get a copy of their input depth. */
+DDN_API int ddn_align_views(const ddn_align_config* cfg, int64_t n_views, int64_t height, int64_t width,
+                    const float* depth, const uint8_t* mask, const double* cam_from_world,
+                    const double* kmat, const double* sparse_xyz, const int64_t* sparse_offsets,
+                    int64_t max_sparse_per_view, float* refined, ddn_view_stats* stats,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stages 2+3 - pixel back-projection fused with the multi-view consistency vote.
+ * Replaces scripts/test.py:205-233 (pixel grid, unproject_points :79-90, cam_from_world().inverse())
+ * and scripts/test.py:273-330 (project_points :58-76, grazing gate, nearest lookup, floater vote),
+ * evaluated against a neighbour table nbr[V,K] instead of all views.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  float depth_threshold;   /* FilteringConfig.depth_threshold (0.7) scripts/test.py:45 */
+  float grazing_cos;       /* 0.087, scripts/test.py:295 */
+  int32_t sample_mode;     /* 0 = nearest/truncate (reference, :308-309); 1 = bilinear 4-tap (new) */
+  float two_sided_tau;     /* <= 0: one-sided z < thr*D (reference, :319-321); > 0: |z-D| > tau*D (new) */
+  int32_t stride;          /* ProcessingConfig.downsample_density (scripts/test.py:37); 1 = densest */
+  int32_t normals_in_world; /* 0 = reference quirk (camera-frame normal vs world dir, :291); 1 = rotate by R_src^T */
+} ddn_filter_config;
+
+DDN_API void ddn_filter_config_default(ddn_filter_config* cfg);
+
+#define DDN_PAIR_TABLE_FLOATS 24
+/* pair_table [n_src,K,DDN_PAIR_TABLE_FLOATS] f32 and src_table [n_src,16] f32 are computed in float64
+ * on the device from the poses (cam_from_world [V,3,4] f64) and PINHOLE intrinsics
+ * (intr [V,4] f64: fx, fy, cx, cy - scripts/test.py:81) and rounded once. */
+DDN_API int ddn_build_pair_tables(int64_t n_views_total, int64_t src_begin, int64_t n_src, int64_t k_nbr,
+                          const double* cam_from_world, const double* intr, const int32_t* nbr,
+                          float* pair_table, float* src_table, void* stream);
+
+/* refined_all [V,H,W] f32 (zero outside the mask); normal [n_src,H,W,3] f32 for the source views
+ * src_begin..src_begin+n_src; outputs on the strided grid Hs=ceil(H/stride), Ws=ceil(W/stride):
+ * xyz [n_src,Hs,Ws,3] f32 world, votes [n_src,Hs,Ws] u8 (255 = pixel has no point, i.e. depth<=0).
+ * bbox [6] f32 (optional, may be NULL): running min xyz / max xyz over points with
+ * votes < vote_threshold; must be initialised to +inf/-inf by ddn_bbox_init. */
+DDN_API int ddn_backproject_filter(const ddn_filter_config* cfg, int64_t n_views_total, int64_t src_begin,
+                           int64_t n_src, int64_t height, int64_t width, int64_t k_nbr,
+                           const float* refined_all, const float* normal, const int32_t* nbr,
+                           const float* pair_table, const float* src_table, int32_t vote_threshold,
+                           float* xyz, uint8_t* votes, float* bbox, void* stream);
+
+DDN_API int ddn_bbox_init(float* bbox, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage 4 - voxel-grid fusion (new capability; the reference only concatenates,
+ * scripts/test.py:353-359).  key = kx | ky<<21 | kz<<42 with k = floor((p - origin)/voxel) in
+ * IEEE float32.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  float voxel;
+  float origin[3];
+  int32_t bits[3]; /* significant bits per axis (from the bounding box); sum <= 63 */
+} ddn_voxel_grid;
+
+DDN_API int ddn_fuse_workspace_bytes(int64_t n_points, int64_t* bytes_out);
+
+/* xyz [N,3] f32, rgb [N,3] u8, votes [N] u8 (point i participates iff votes[i] < vote_threshold;
+ * votes may be NULL => all).  Outputs sized for the worst case N: out_keys [N] u64 ascending,
+ * out_xyz [N,3] f32, out_rgb [N,3] u8, out_count [N] i32; counts_out [2] i64 device:
+ * {number of participating points, number of voxels}. */
+DDN_API int ddn_voxel_fuse(const ddn_voxel_grid* grid_host, int64_t n_points, const float* xyz,
+                   const uint8_t* rgb, const uint8_t* votes, int32_t vote_threshold,
+                   uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb, int32_t* out_count,
+                   int64_t* counts_out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Stand-alone pieces of stage 4 (used by the multi-GPU path and by tests). */
+DDN_API int ddn_voxel_keys(const ddn_voxel_grid* grid_host, int64_t n_points, const float* xyz,
+                   uint64_t* keys, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDN_B200_H_ */
