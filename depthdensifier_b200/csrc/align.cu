@@ -232,10 +232,9 @@ align_stats_kernel(ddn_align_config cfg, int H, int W, const float* __restrict__
         auto tap = [&](int xx, int yy) -> float {
           return (xx >= 0 && xx < W && yy >= 0 && yy < H) ? __ldg(dmap + (size_t)yy * W + xx) : 0.f;
         };
-        samp = __fmul_rn(tap(xi0, yi0), wnw);
-        samp = __fadd_rn(samp, __fmul_rn(tap(xi1, yi0), wne));
-        samp = __fadd_rn(samp, __fmul_rn(tap(xi0, yi1), wsw));
-        samp = __fadd_rn(samp, __fmul_rn(tap(xi1, yi1), wse));
+        // ATen's CPU kernel accumulates the four taps as one forward FMA chain (verified bit for bit
+        // against F.grid_sample on the build host)
+        samp = fmaf(tap(xi1, yi1), wse, fmaf(tap(xi0, yi1), wsw, fmaf(tap(xi1, yi0), wne, __fmul_rn(tap(xi0, yi0), wnw))));
         keep = samp > 0.f;
       }
     }

@@ -293,11 +293,12 @@ __global__ void __launch_bounds__(kFilterThreads, 3) backproject_filter_kernel(c
       float zq = Z;
       float D = 0.f;
       if (own) {
-        // Own view: the reference's u = fx*x/(z+1e-8)+cx lands 1e-8*(x-cx)/z BELOW the integer x for
-        // x > cx (and above it for x < cx), so truncation looks up x-1 / y-1 there
-        // (scripts/test.py:71, 308-309).  Reproduced in integer arithmetic; z is the pixel's own depth.
-        const int ux = px[j] - ((float)px[j] > kk.z ? 1 : 0);
-        const int vy = py[j] - ((float)py[j] > kk.w ? 1 : 0);
+        // Own view: the reference normalises by (z + 1e-8) before applying K (scripts/test.py:71-75), so
+        // u = x * z/(z+1e-8) lands ~x*1e-8/z BELOW the integer x (far above float64 round-off) and the
+        // truncation at :308-309 looks up pixel (x-1, y-1) for x, y >= 1.  Reproduced in integer
+        // arithmetic; z is the pixel's own depth.  (x == 0 or y == 0 is a round-off tie in the reference.)
+        const int ux = max(px[j] - 1, 0);
+        const int vy = max(py[j] - 1, 0);
         zq = d[j];
         if (ok) D = __ldg(depth_t + (size_t)vy * p.W + ux);
       } else {

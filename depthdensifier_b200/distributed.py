@@ -1,0 +1,266 @@
+"""View-sharded densification: one process per GPU, views in contiguous blocks.
+
+Stage 1 is independent per view and stage 2 per pixel; stage 3 needs read-only access to the refined
+depth of each source view's K neighbours, stage 4 is a global group-by on the voxel key
+(SURVEY.md §8e).  So there are exactly two exchange steps:
+
+* halo exchange of refined depth: a rank receives only the neighbour views its own rows of the
+  neighbour table reference (with ring-ordered cameras that is <= K maps per shard boundary instead
+  of the all-gather of all V maps), as one NCCL all-to-all-v;
+* voxel exchange: every rank fuses its own points into per-voxel PARTIAL SUMS (integer fixed point,
+  so the result does not depend on how points are split over ranks), the sorted partials are cut at
+  R-1 sampled splitter keys - each rank owns one disjoint key range, so the cut is R contiguous slices
+  and needs no pack kernel - and exchanged with an all-to-all-v; the owner merges its R sorted runs.
+
+With world == 1 both exchanges vanish and this is the single-GPU pipeline.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import ops
+from .engine import DensifyConfig, DensifyResult
+from .neighbours import default_vote_threshold
+
+
+def shard_bounds(n_views: int, world: int) -> list[tuple[int, int]]:
+    """Contiguous equal shards [lo, hi) per rank (the last ranks may be short or empty)."""
+    per = (n_views + world - 1) // world
+    return [(min(r * per, n_views), min((r + 1) * per, n_views)) for r in range(world)]
+
+
+@dataclass
+class HaloPlan:
+    """Who sends which refined-depth maps to whom; computed identically on every rank from the
+    replicated neighbour table, so no communication is needed to build it."""
+
+    slots: np.ndarray  # global view id of every local slot: own views first, then halo views
+    nbr_slots: np.ndarray  # [n_local, K] neighbour table in slot space (-1 = unused)
+    send_views: list[np.ndarray]  # per peer: LOCAL indices of own views to send
+    recv_counts: list[int]  # per peer: number of halo views received (stored in slot order)
+
+    @property
+    def n_local(self) -> int:
+        return self.nbr_slots.shape[0]
+
+
+def needed_views(nbr: np.ndarray, lo: int, hi: int) -> np.ndarray:
+    need = np.unique(nbr[lo:hi])
+    return need[need >= 0]
+
+
+def make_halo_plan(nbr: np.ndarray, bounds: list[tuple[int, int]], rank: int) -> HaloPlan:
+    lo, hi = bounds[rank]
+    world = len(bounds)
+
+    def owner(v: int) -> int:
+        for r, (a, b) in enumerate(bounds):
+            if a <= v < b:
+                return r
+        raise ValueError(f"view {v} has no owner")
+
+    need = needed_views(nbr, lo, hi)
+    halo = [int(v) for v in need if not (lo <= v < hi)]
+    halo_by_peer: list[list[int]] = [[] for _ in range(world)]
+    for v in halo:
+        halo_by_peer[owner(v)].append(v)
+    halo_sorted = [v for q in range(world) for v in sorted(halo_by_peer[q])]
+    slots = np.array(list(range(lo, hi)) + halo_sorted, dtype=np.int64)
+    slot_of = {int(v): i for i, v in enumerate(slots)}
+    nbr_slots = np.full((hi - lo, nbr.shape[1]), -1, dtype=np.int32)
+    for i in range(hi - lo):
+        for k, t in enumerate(nbr[lo + i]):
+            if t >= 0:
+                nbr_slots[i, k] = slot_of[int(t)]
+    send_views = []
+    for q in range(world):
+        qlo, qhi = bounds[q]
+        if q == rank or qhi <= qlo:
+            send_views.append(np.zeros(0, dtype=np.int64))
+            continue
+        qneed = needed_views(nbr, qlo, qhi)
+        mine = np.array(sorted(int(v) for v in qneed if lo <= v < hi), dtype=np.int64)
+        send_views.append(mine - lo)
+    return HaloPlan(slots=slots, nbr_slots=nbr_slots, send_views=send_views, recv_counts=[len(h) for h in halo_by_peer])
+
+
+@dataclass
+class ShardResult(DensifyResult):
+    events: dict = field(default_factory=dict)
+
+
+class ShardedDensifier:
+    """Pipeline of one rank.  ``cam_from_world`` / ``intr`` cover ALL views (replicated, tiny);
+    the per-view maps passed to ``run`` cover the rank's own views [lo, hi)."""
+
+    def __init__(self, cfg: DensifyConfig, device, rank: int, world: int, n_views_total: int, lo: int, hi: int,
+                 cam_from_world: torch.Tensor, intr: torch.Tensor, nbr: np.ndarray, height: int, width: int, group=None):
+        if not torch.cuda.is_available():
+            raise ops.DDNError("ShardedDensifier needs a CUDA device: depthdensifier_b200 has no CPU fallback")
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.rank, self.world, self.group = rank, world, group
+        self.V, self.lo, self.hi, self.H, self.W = n_views_total, lo, hi, height, width
+        self.K = nbr.shape[1]
+        self.thr = cfg.vote_threshold if cfg.vote_threshold is not None else default_vote_threshold(self.K)
+        bounds = shard_bounds(n_views_total, world) if world > 1 else [(lo, hi)]
+        if world > 1 and bounds[rank] != (lo, hi):
+            raise ValueError(f"rank {rank}: shard {(lo, hi)} does not match the contiguous layout {bounds[rank]}")
+        self.plan = make_halo_plan(nbr, bounds, rank if world > 1 else 0)
+        slots = torch.from_numpy(self.plan.slots).to(self.device)
+        self.poses_slots = cam_from_world.to(self.device)[slots].contiguous()
+        self.intr_slots = intr.to(self.device)[slots].contiguous()
+        self.nbr_slots = torch.from_numpy(self.plan.nbr_slots).to(self.device).contiguous()
+        self.n_local = hi - lo
+        self.n_slots = len(self.plan.slots)
+        kmat = torch.zeros((self.n_local, 3, 3), dtype=torch.float64, device=self.device)
+        il = self.intr_slots[: self.n_local]
+        kmat[:, 0, 0], kmat[:, 1, 1], kmat[:, 0, 2], kmat[:, 1, 2], kmat[:, 2, 2] = il[:, 0], il[:, 1], il[:, 2], il[:, 3], 1.0
+        self.kmat = kmat
+        self._max_sparse = None
+        self._host_out = None
+
+    # -- exchange steps -------------------------------------------------------------------------------
+    def _exchange_halo(self, refined_slots: torch.Tensor) -> None:
+        """Fill refined_slots[n_local:] with the neighbour maps owned by other ranks (all-to-all-v)."""
+        if self.world == 1:
+            return
+        import torch.distributed as dist
+
+        hw = self.H * self.W
+        send_idx = np.concatenate(self.plan.send_views) if self.plan.send_views else np.zeros(0, np.int64)
+        if len(send_idx):
+            send = refined_slots[torch.from_numpy(send_idx).to(self.device)].reshape(-1)
+        else:
+            send = refined_slots.new_empty(0)
+        recv = refined_slots[self.n_local:].reshape(-1)
+        dist.all_to_all_single(recv, send, output_split_sizes=[c * hw for c in self.plan.recv_counts],
+                               input_split_sizes=[len(s) * hw for s in self.plan.send_views], group=self.group)
+
+    def _global_bbox(self, bbox: torch.Tensor) -> np.ndarray:
+        bb = ops.decode_bbox(bbox) if self.world == 1 else None
+        if self.world > 1:
+            import torch.distributed as dist
+
+            # order-preserving int encoding: min/max of the encodings == encodings of the min/max
+            lo3, hi3 = bbox[:3].clone(), bbox[3:].clone()
+            dist.all_reduce(lo3, op=dist.ReduceOp.MIN, group=self.group)
+            dist.all_reduce(hi3, op=dist.ReduceOp.MAX, group=self.group)
+            bb = ops.decode_bbox(torch.cat([lo3, hi3]))
+        return bb
+
+    # -- pipeline ---------------------------------------------------------------------------------------
+    def run(self, depth, normal, mask, rgb, sparse_xyz, sparse_offsets, record_events: bool = False, grid=None) -> ShardResult:
+        cfg = self.cfg
+        ev = {}
+
+        def mark(name, fn):
+            if not record_events:
+                return fn()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            out = fn()
+            b.record()
+            ev[name] = (a, b)
+            return out
+
+        if self._max_sparse is None:
+            off = sparse_offsets.cpu().numpy()
+            self._max_sparse = max(int(np.max(np.diff(off))) if len(off) > 1 else 1, 1)
+        refined_slots = torch.empty((self.n_slots, self.H, self.W), dtype=torch.float32, device=self.device)
+        _, stats = mark("align", lambda: ops.align_views(
+            depth, mask, self.poses_slots[: self.n_local].contiguous(), self.kmat, sparse_xyz, sparse_offsets,
+            self._max_sparse, cfg.align, out=refined_slots[: self.n_local]))
+        mark("halo_exchange", lambda: self._exchange_halo(refined_slots))
+        pair, src = mark("pair_tables", lambda: ops.build_pair_tables(self.poses_slots, self.intr_slots, self._nbr_full(), 0, self.n_local))
+        bbox = ops.new_bbox(self.device)
+        xyz, votes = mark("backproject_filter", lambda: ops.backproject_filter(
+            refined_slots, normal, self.nbr_slots, pair, src, 0, self.thr, cfg.filter, bbox=bbox))
+        res = ShardResult(refined=refined_slots[: self.n_local], stats=stats, xyz=xyz, votes=votes, vote_threshold=self.thr,
+                          bbox=bbox, events=ev)
+        if cfg.voxel is None:
+            return res
+        if grid is None:
+            bb = mark("bbox_sync", lambda: self._global_bbox(bbox))
+            if not np.all(np.isfinite(bb)):
+                res.counts = torch.zeros(2, dtype=torch.int64, device=self.device)
+                return res
+            grid = ops.make_grid(bb[:3], bb[3:], cfg.voxel)
+        s = cfg.filter.stride
+        rgb_s = rgb if s == 1 else rgb[:, ::s, ::s].contiguous()
+        if self.world == 1:
+            k, x, c, n, counts = mark("voxel_fuse", lambda: ops.voxel_fuse(
+                xyz.view(-1, 3), rgb_s.view(-1, 3), votes.view(-1), self.thr, grid, trim=False))
+        else:
+            k, x, c, n, counts = mark("voxel_fuse", lambda: self._fuse_sharded(xyz, rgb_s, votes, grid))
+        res.grid, res.voxel_keys, res.voxel_xyz, res.voxel_rgb, res.voxel_count, res.counts = grid, k, x, c, n, counts
+        return res
+
+    def _nbr_full(self) -> torch.Tensor:
+        """Neighbour table padded to n_slots rows (build_pair_tables indexes it by global slot)."""
+        if self.n_slots == self.n_local:
+            return self.nbr_slots
+        pad = torch.full((self.n_slots - self.n_local, self.K), -1, dtype=torch.int32, device=self.device)
+        return torch.cat([self.nbr_slots, pad], 0).contiguous()
+
+    def _fuse_sharded(self, xyz, rgb, votes, grid):
+        import torch.distributed as dist
+
+        pk, psum, prgb, pcnt, counts = ops.voxel_fuse_partial(xyz.view(-1, 3), rgb.view(-1, 3), votes.view(-1), self.thr, grid)
+        mv = int(counts[1].item())
+        pk, psum, prgb, pcnt = pk[:mv], psum[:mv], prgb[:mv], pcnt[:mv]
+        R = self.world
+        # sampled splitters: R-1 local quantile keys per rank -> global quantiles of the R*(R-1) samples
+        if mv > 0:
+            q = torch.linspace(0, mv - 1, R + 1, device=self.device)[1:-1].round().long()
+            samples = pk[q]
+        else:
+            samples = torch.full((R - 1,), torch.iinfo(torch.int64).max, dtype=torch.int64, device=self.device)
+        allsamp = torch.empty(R * (R - 1), dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(allsamp, samples.contiguous(), group=self.group)
+        allsamp, _ = torch.sort(allsamp)
+        splitters = allsamp[torch.arange(1, R, device=self.device) * (R - 1) - 1]
+        cuts = torch.searchsorted(pk, splitters)  # local sorted keys: slice r = [cuts[r-1], cuts[r])
+        bnd = torch.cat([torch.zeros(1, dtype=torch.int64, device=self.device), cuts, torch.tensor([mv], device=self.device)])
+        send_counts = (bnd[1:] - bnd[:-1]).contiguous()
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts, group=self.group)
+        sc, rc = send_counts.cpu().tolist(), recv_counts.cpu().tolist()
+        n_recv = int(sum(rc))
+
+        def exchange(t, width):
+            out = torch.empty((n_recv,) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device)
+            dist.all_to_all_single(out.view(-1), t.contiguous().view(-1), output_split_sizes=[c * width for c in rc],
+                                   input_split_sizes=[c * width for c in sc], group=self.group)
+            return out
+
+        rk, rsum, rrgb, rcnt = exchange(pk, 1), exchange(psum, 3), exchange(prgb, 3), exchange(pcnt, 1)
+        k, x, c, n, mcounts = ops.voxel_merge_partials(rk, rsum, rrgb, rcnt, grid)
+        counts2 = torch.stack([counts[0], mcounts[1]])  # (points fused locally, voxels owned)
+        return k, x, c, n, counts2
+
+    # -- end-to-end with host buffers -----------------------------------------------------------------
+    def pin_host_inputs(self, depth, normal, mask, rgb, sparse_xyz, sparse_offsets):
+        return tuple(t.contiguous().pin_memory() for t in (depth, normal, mask, rgb, sparse_xyz, sparse_offsets))
+
+    def run_host(self, depth, normal, mask, rgb, sparse_xyz, sparse_offsets):
+        """Public end-to-end call: host (pinned) arrays in, fused cloud back on the host."""
+        dev_in = [t.to(self.device, non_blocking=True) for t in (depth, normal, mask, rgb, sparse_xyz, sparse_offsets)]
+        res = self.run(*dev_in)
+        if res.counts is None:
+            torch.cuda.synchronize(self.device)
+            return {"d2h_bytes": 0}
+        mv = int(res.counts[1].item())
+        out = {}
+        nbytes = 0
+        for name, t in (("keys", res.voxel_keys), ("xyz", res.voxel_xyz), ("rgb", res.voxel_rgb), ("count", res.voxel_count)):
+            h = t[:mv].cpu()
+            out[name] = h
+            nbytes += h.numel() * h.element_size()
+        out["num_points"] = int(res.counts[0].item())
+        out["d2h_bytes"] = nbytes + 16
+        return out

@@ -108,9 +108,15 @@ def _raycast(c: torch.Tensor, dw: torch.Tensor, max_depth: float):
     return best, n, hit
 
 
-def make_scene(cfg: SceneConfig, device: str | torch.device = "cpu") -> Scene:
+def make_scene(cfg: SceneConfig, device: str | torch.device = "cpu", views: range | None = None) -> Scene:
+    """Generate the scene.  ``views`` restricts the per-view maps and sparse points to a sub-range of
+    the ``cfg.n_views`` ring (multi-GPU shards, CPU-baseline samples); poses and intrinsics always
+    cover the whole ring.  A view's content depends only on (cfg, view index) when the device is
+    the same, because each view draws from its own seeded generators."""
     dev = torch.device(device)
     V, H, W = cfg.n_views, cfg.height, cfg.width
+    vlist = list(range(V)) if views is None else list(views)
+    nv = len(vlist)
     poses_np = ring_poses(cfg)
     poses = torch.from_numpy(poses_np).to(dev)
     fx = fy = 0.8 * W
@@ -118,14 +124,14 @@ def make_scene(cfg: SceneConfig, device: str | torch.device = "cpu") -> Scene:
     intr = torch.tensor([[fx, fy, cx, cy]] * V, dtype=torch.float64, device=dev)
 
     scale_np = np.random.default_rng(cfg.seed + 1).uniform(0.5, 2.0, V)
-    g_float = torch.Generator(device=dev).manual_seed(cfg.seed + 2)
-    g_sparse = torch.Generator(device=dev).manual_seed(cfg.seed + 3)
+    g_float = torch.Generator(device=dev)
+    g_sparse = torch.Generator(device=dev)
 
-    mono = torch.empty((V, H, W), dtype=torch.float32, device=dev)
-    true = torch.empty((V, H, W), dtype=torch.float32, device=dev)
-    normal = torch.empty((V, H, W, 3), dtype=torch.float32, device=dev)
-    mask = torch.empty((V, H, W), dtype=torch.bool, device=dev)
-    rgb = torch.empty((V, H, W, 3), dtype=torch.uint8, device=dev)
+    mono = torch.empty((nv, H, W), dtype=torch.float32, device=dev)
+    true = torch.empty((nv, H, W), dtype=torch.float32, device=dev)
+    normal = torch.empty((nv, H, W, 3), dtype=torch.float32, device=dev)
+    mask = torch.empty((nv, H, W), dtype=torch.bool, device=dev)
+    rgb = torch.empty((nv, H, W, 3), dtype=torch.uint8, device=dev)
     sparse = []
     offsets = [0]
 
@@ -136,7 +142,9 @@ def make_scene(cfg: SceneConfig, device: str | torch.device = "cpu") -> Scene:
     )
     dir_cam = torch.stack([(xs - cx) / fx, (ys - cy) / fy, torch.ones_like(xs)], dim=-1)
     bh, bw = (H + 7) // 8, (W + 7) // 8
-    for v in range(V):
+    for slot, v in enumerate(vlist):
+        g_float.manual_seed(cfg.seed * 1000003 + 2 * v + 1)
+        g_sparse.manual_seed(cfg.seed * 1000003 + 2 * v + 2)
         R = poses[v, :, :3]
         t = poses[v, :, 3]
         c = -(R.T @ t)
@@ -150,13 +158,13 @@ def make_scene(cfg: SceneConfig, device: str | torch.device = "cpu") -> Scene:
         blocks = torch.rand((bh, bw), generator=g_float, device=dev) < cfg.floater_fraction
         fl = blocks.repeat_interleave(8, 0).repeat_interleave(8, 1)[:H, :W]
         m = torch.where(fl, m * cfg.floater_scale, m)
-        mono[v] = torch.where(hit, m, torch.zeros_like(m)).float()
-        true[v] = d.float()
-        normal[v] = torch.where(hit.unsqueeze(-1), n_c, torch.zeros_like(n_c)).float()
-        mask[v] = hit
+        mono[slot] = torch.where(hit, m, torch.zeros_like(m)).float()
+        true[slot] = d.float()
+        normal[slot] = torch.where(hit.unsqueeze(-1), n_c, torch.zeros_like(n_c)).float()
+        mask[slot] = hit
         q = torch.floor(p_w / 0.05).to(torch.int64)
         hsh = (q[..., 0] * 73856093) ^ (q[..., 1] * 19349663) ^ (q[..., 2] * 83492791)
-        rgb[v] = torch.stack([hsh & 255, (hsh >> 8) & 255, (hsh >> 16) & 255], dim=-1).to(torch.uint8)
+        rgb[slot] = torch.stack([hsh & 255, (hsh >> 8) & 255, (hsh >> 16) & 255], dim=-1).to(torch.uint8)
 
         # sparse "COLMAP" points: continuous image positions, exact surface hits, world float64
         ncand = 2 * cfg.n_sparse

@@ -63,8 +63,8 @@ def bilinear_align_corners(depth: np.ndarray, u: np.ndarray, v: np.ndarray) -> n
     """Explicit form of ``grid_sample(bilinear, zeros, align_corners=True)`` as used at
     depth_refiner.py:266-272: bilinear at pixel coordinates (u, v), integer = pixel centre,
     out-of-image taps contribute zero.  Kept in float32 with the same operation order as ATen's
-    CPU kernel so tests can compare it with ``F.grid_sample`` to the last ulp or two; the CUDA
-    kernel K1 follows this function."""
+    CPU kernel (bit-identical to ``F.grid_sample`` in tests); the CUDA kernel K1 follows this
+    function."""
     h, w = depth.shape
     f32 = np.float32
     gx = (u.astype(f32) / f32(w - 1)) * f32(2) - f32(1)
@@ -86,10 +86,11 @@ def bilinear_align_corners(depth: np.ndarray, u: np.ndarray, v: np.ndarray) -> n
         yi = np.clip(yy, 0, h - 1).astype(np.int64)
         return np.where(ok, depth[yi, xi], f32(0)).astype(f32)
 
-    out = tap(x0, y0) * w_nw
-    out = out + tap(x1, y0) * w_ne
-    out = out + tap(x0, y1) * w_sw
-    out = out + tap(x1, y1) * w_se
+    def fma(a, b, c):  # float32 fused multiply-add (product of two float32 is exact in float64)
+        return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(f32)
+
+    # ATen's CPU kernel accumulates the taps as a forward FMA chain
+    out = fma(tap(x1, y1), w_se, fma(tap(x0, y1), w_sw, fma(tap(x1, y0), w_ne, tap(x0, y0) * w_nw)))
     return out.astype(f32)
 
 

@@ -63,10 +63,13 @@ def pair_ties(points, normals, src_view, t, refined_t, pose_t, intr_t, depth_thr
         if sel.any():
             alt, near_alt = decide(ui + du, vi + dv)
             tie |= sel & ((alt != base) | near_alt)
-    # own view: only the threshold band applies (the lookup pixel is deterministic)
+    # own view: u = x*(1 - 1e-8/z) sits a deterministic ~1e-9 px below the integer x, so the lookup
+    # pixel is (x-1, y-1) except in column/row 0 where float64 round-off decides (tie); otherwise
+    # only the threshold band applies
     if own.any():
         D = det["D"]
         tie |= own & det["inb"] & (D > 0) & (np.abs(z - thr32 * D.astype(np.float64)) < EPS_REL * D)
+        tie |= own & ((np.abs(u) < 0.5) | (np.abs(v) < 0.5))
     return vote, tie
 
 

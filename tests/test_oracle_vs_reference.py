@@ -118,6 +118,7 @@ def test_explicit_bilinear_matches_grid_sample():
     grid = torch.stack([torch.from_numpy(u) / 52 * 2 - 1, torch.from_numpy(v) / 36 * 2 - 1], -1)[None, None]
     ref = F.grid_sample(torch.from_numpy(d)[None, None], grid, mode="bilinear", padding_mode="zeros", align_corners=True).squeeze().numpy()
     mine = R.bilinear_align_corners(d, u, v)
+    assert (mine == ref).mean() > 0.999  # same operation order as ATen's CPU kernel
     np.testing.assert_allclose(mine, ref, rtol=3e-6, atol=1e-6)
 
 
