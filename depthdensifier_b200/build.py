@@ -46,6 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
         return LIB_PATH
     nvcc = nvcc_path()
+    extra = os.environ.get("DDN_NVCC_EXTRA", "").split()  # tuning experiments, e.g. -DDDN_K4_MINBLOCKS=4
     objs = []
     build_dir = PKG_DIR / "build"
     build_dir.mkdir(exist_ok=True)
@@ -53,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     procs = []
     for src in SOURCES:
         obj = build_dir / (src + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", str(CSRC / src), "-o", str(obj)]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, obj, pr in procs:
         out, _ = pr.communicate()

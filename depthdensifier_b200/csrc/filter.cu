@@ -19,6 +19,9 @@
 
 namespace ddn {
 
+#ifndef DDN_K4_MINBLOCKS
+#define DDN_K4_MINBLOCKS 5
+#endif
 constexpr int kFilterThreads = 256;
 constexpr int kFilterPX = 4;  // pixels per thread
 constexpr int kFilterChunk = kFilterThreads * kFilterPX;
@@ -128,41 +131,95 @@ __device__ __forceinline__ float sqrt_approx(float x) {
 __device__ __forceinline__ int trunc_biased(float u) { return __float_as_int(__fadd_rz(u, 8388608.0f)); }
 constexpr int kTruncBias = 0x4B000000;
 
-// Cooperative global<->shared copy of n floats, float4 when the global address is 16 B aligned.
+// Cooperative global<->shared copy of n floats, float4 when the global address is 16 B aligned.  The
+// common case (full chunk, aligned) is three straight-line float4 moves per thread.
 template <bool kLoad>
 __device__ __forceinline__ void stage_floats(float* smem, float* gptr, int n) {
   const int tid = threadIdx.x;
-  if ((reinterpret_cast<uintptr_t>(gptr) & 15) == 0) {
-    const int n4 = n >> 2;
-    float4* g4 = reinterpret_cast<float4*>(gptr);
-    float4* s4 = reinterpret_cast<float4*>(smem);
-    for (int i = tid; i < n4; i += kFilterThreads) {
-      if (kLoad)
-        s4[i] = __ldcs(g4 + i);
-      else
-        __stcs(g4 + i, s4[i]);
+  const bool aligned = (reinterpret_cast<uintptr_t>(gptr) & 15) == 0;
+  float4* g4 = reinterpret_cast<float4*>(gptr);
+  float4* s4 = reinterpret_cast<float4*>(smem);
+  if (aligned && n == kFilterChunk * 3) {
+    if (kLoad) {
+      const float4 a = __ldcs(g4 + tid), b = __ldcs(g4 + tid + kFilterThreads), c = __ldcs(g4 + tid + 2 * kFilterThreads);
+      s4[tid] = a;
+      s4[tid + kFilterThreads] = b;
+      s4[tid + 2 * kFilterThreads] = c;
+    } else {
+      const float4 a = s4[tid], b = s4[tid + kFilterThreads], c = s4[tid + 2 * kFilterThreads];
+      __stcs(g4 + tid, a);
+      __stcs(g4 + tid + kFilterThreads, b);
+      __stcs(g4 + tid + 2 * kFilterThreads, c);
     }
-    for (int i = (n4 << 2) + tid; i < n; i += kFilterThreads) {
-      if (kLoad)
-        smem[i] = __ldcs(gptr + i);
-      else
-        __stcs(gptr + i, smem[i]);
-    }
-  } else {
-    for (int i = tid; i < n; i += kFilterThreads) {
-      if (kLoad)
-        smem[i] = __ldcs(gptr + i);
-      else
-        __stcs(gptr + i, smem[i]);
-    }
+    return;
+  }
+  const int n4 = aligned ? (n >> 2) : 0;
+#pragma unroll 1
+  for (int i = tid; i < n4; i += kFilterThreads) {
+    if (kLoad)
+      s4[i] = __ldcs(g4 + i);
+    else
+      __stcs(g4 + i, s4[i]);
+  }
+#pragma unroll 1
+  for (int i = (n4 << 2) + tid; i < n; i += kFilterThreads) {
+    if (kLoad)
+      smem[i] = __ldcs(gptr + i);
+    else
+      __stcs(gptr + i, smem[i]);
   }
 }
 
-template <bool kBilinear, bool kStride1>
-__global__ void __launch_bounds__(kFilterThreads, 3) backproject_filter_kernel(const FilterParams p) {
+// One (pixel, neighbour) evaluation up to the depth lookup: returns the candidate flag ("would vote if
+// the grazing gate passes") and leaves the target-frame point in X, Y, Z.
+template <bool kBilinear, bool kTwoSided>
+__device__ __forceinline__ bool pair_candidate(const float4& r0, const float4& r1, const float4& r2, const float4& kk,
+                                               float P, float Q, float d, const float* __restrict__ depth_all,
+                                               unsigned map_off, unsigned W, int H, unsigned wbits, unsigned hbits,
+                                               unsigned idx_bias, float thr, float tau, float& X, float& Y,
+                                               float& Z) {
+  X = fmaf(r0.x, P, fmaf(r0.y, Q, fmaf(r0.z, d, r0.w)));
+  Y = fmaf(r1.x, P, fmaf(r1.y, Q, fmaf(r1.z, d, r1.w)));
+  Z = fmaf(r2.x, P, fmaf(r2.y, Q, fmaf(r2.z, d, r2.w)));
+  const float inv = rcp_approx(Z);
+  const float u = fmaf(kk.x, X * inv, kk.z);
+  const float v = fmaf(kk.y, Y * inv, kk.w);
+  // 0 <= u < W and 0 <= v < H on the raw bits (negative floats and NaN compare as huge unsigned);
+  // invalid pixels carry NaN depth, so Z > 0 rejects them too.
+  const bool inb = (__float_as_uint(u) < wbits) & (__float_as_uint(v) < hbits) & (Z > 0.f);
+  const unsigned ub = (unsigned)trunc_biased(u), vb = (unsigned)trunc_biased(v);
+  float D;
+  if (!kBilinear) {
+    // 32-bit element offset from the start of refined_all (modular arithmetic removes the 2^23 biases);
+    // out-of-bounds lanes read the first pixel of the map and are masked by `inb`.
+    const unsigned off = inb ? vb * W + ub + (map_off - idx_bias) : map_off;
+    D = __ldg(depth_all + off);
+  } else {
+    const float* __restrict__ depth_t = depth_all + map_off;
+    // N3: 4 taps at floor(u), floor(v), +1 clamped; all taps must be > 0
+    const int x0 = inb ? ub - kTruncBias : 0, y0 = inb ? vb - kTruncBias : 0;
+    const int x1 = min(x0 + 1, (int)W - 1), y1 = min(y0 + 1, H - 1);
+    const float ta = __ldg(depth_t + y0 * W + x0), tb = __ldg(depth_t + y0 * W + x1);
+    const float tc = __ldg(depth_t + y1 * W + x0), td = __ldg(depth_t + y1 * W + x1);
+    const float fxw = u - (float)x0, fyw = v - (float)y0;
+    const float gx = 1.f - fxw, gy = 1.f - fyw;
+    const float acc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(gx, gy), ta), __fmul_rn(__fmul_rn(fxw, gy), tb)),
+                                          __fmul_rn(__fmul_rn(gx, fyw), tc)),
+                                __fmul_rn(__fmul_rn(fxw, fyw), td));
+    D = ((ta > 0.f) & (tb > 0.f) & (tc > 0.f) & (td > 0.f)) ? acc : 0.f;
+  }
+  if (kTwoSided) return inb & (D > 0.f) & (fabsf(Z - D) > tau * D);
+  // one-sided floater test z < float32(thr * D) (scripts/test.py:319-321, NEP-50 product in float32).
+  // The lookup-valid gate D > 0 (:315) is implied: inb has Z > 0 and thr > 0, so Z < thr*D needs D > 0.
+  return inb & (Z < __fmul_rn(thr, D));
+}
+
+template <bool kBilinear, bool kStride1, bool kTwoSided>
+__global__ void __launch_bounds__(kFilterThreads, kBilinear ? 3 : DDN_K4_MINBLOCKS) backproject_filter_kernel(const FilterParams p) {
   extern __shared__ __align__(16) float smem[];
-  float* s_stage = smem;                          // kFilterChunk*3 floats
-  float* s_src = smem + kFilterChunk * 3;         // 16 floats
+  float* s_nrm = smem;                            // kFilterChunk*3 floats: normals (staged in)
+  float* s_xyz = smem + kFilterChunk * 3;         // kFilterChunk*3 floats: world xyz (staged out)
+  float* s_src = s_xyz + kFilterChunk * 3;        // 16 floats
   float* s_pair = s_src + 16;                     // K*24 floats
   __shared__ int s_bbox[6];
 
@@ -180,204 +237,181 @@ __global__ void __launch_bounds__(kFilterThreads, 3) backproject_filter_kernel(c
   if (tid < 16) s_src[tid] = __ldg(p.src_table + (size_t)sl * 16 + tid);
   if (tid < 6) s_bbox[tid] = tid < 3 ? 0x7fffffff : (int)0x80000000;
   if (kStride1) {
-    stage_floats<true>(s_stage, const_cast<float*>(p.normal) + ((size_t)sl * HW + chunk0) * 3, n_here * 3);
+    stage_floats<true>(s_nrm, const_cast<float*>(p.normal) + ((size_t)sl * HW + chunk0) * 3, n_here * 3);
+  } else {
+    for (int l = tid; l < n_here; l += kFilterThreads) {
+      const int pix = chunk0 + l;
+      const int ys = pix / p.Ws, xs = pix - ys * p.Ws;
+      const float* np_ = p.normal + ((size_t)sl * HW + (size_t)ys * p.stride * p.W + xs * p.stride) * 3;
+      s_nrm[l * 3 + 0] = __ldg(np_ + 0);
+      s_nrm[l * 3 + 1] = __ldg(np_ + 1);
+      s_nrm[l * 3 + 2] = __ldg(np_ + 2);
+    }
   }
   __syncthreads();
 
-  float d[kFilterPX], P[kFilterPX], Q[kFilterPX], nx[kFilterPX], ny[kFilterPX], nz[kFilterPX], nXw[kFilterPX];
-  int px[kFilterPX], py[kFilterPX];
+  // Per-pixel state kept in registers: depth d (NaN = no point), P = d*x, Q = d*y, vote count.
+  float d[kFilterPX], P[kFilterPX], Q[kFilterPX];
   int nvotes[kFilterPX];
-  float bmin[3] = {INFINITY, INFINITY, INFINITY}, bmax[3] = {-INFINITY, -INFINITY, -INFINITY};
-  float kx[kFilterPX], ky[kFilterPX], kz[kFilterPX];
+  const float qnan = __int_as_float(0x7fc00000);
 
+  // (row, column) of the thread's first pixel: one integer division per thread, then +256 steps
+  int ys_run = (chunk0 + tid) / p.Ws;
+  int xs_run = (chunk0 + tid) - ys_run * p.Ws;
 #pragma unroll
   for (int j = 0; j < kFilterPX; ++j) {
     const int l = j * kFilterThreads + tid;
     const int pix = chunk0 + l;
     const bool in = l < n_here;
-    int x = 0, y = 0;
+    const int x = kStride1 ? xs_run : xs_run * p.stride;
+    const int y = kStride1 ? ys_run : ys_run * p.stride;
     float dd = 0.f;
-    float n0 = 0.f, n1 = 0.f, n2 = 0.f;
-    if (in) {
-      const int ys = pix / p.Ws;
-      const int xs = pix - ys * p.Ws;
-      if (kStride1) {
-        x = xs;
-        y = ys;
-        dd = __ldg(depth_s + pix);
-        n0 = s_stage[l * 3 + 0];
-        n1 = s_stage[l * 3 + 1];
-        n2 = s_stage[l * 3 + 2];
-      } else {
-        x = xs * p.stride;
-        y = ys * p.stride;
-        const size_t g = (size_t)y * p.W + x;
-        dd = __ldg(depth_s + g);
-        const float* np_ = p.normal + ((size_t)sl * HW + g) * 3;
-        n0 = __ldg(np_ + 0);
-        n1 = __ldg(np_ + 1);
-        n2 = __ldg(np_ + 2);
-      }
+    if (in) dd = __ldg(depth_s + (kStride1 ? (size_t)pix : (size_t)y * p.W + x));
+    xs_run += kFilterThreads;
+    while (xs_run >= p.Ws) {
+      xs_run -= p.Ws;
+      ++ys_run;
     }
     const bool valid = in && dd > 0.f;
-    d[j] = valid ? dd : 0.f;
-    px[j] = x;
-    py[j] = y;
+    const float dv = valid ? dd : 0.f;
+    const float Pv = dv * (float)x, Qv = dv * (float)y;
+    // world position (scripts/test.py:79-90 then :233), fp32 with float64-precomputed rows
+    const float X = fmaf(s_src[0], Pv, fmaf(s_src[1], Qv, fmaf(s_src[2], dv, s_src[3])));
+    const float Y = fmaf(s_src[4], Pv, fmaf(s_src[5], Qv, fmaf(s_src[6], dv, s_src[7])));
+    const float Z = fmaf(s_src[8], Pv, fmaf(s_src[9], Qv, fmaf(s_src[10], dv, s_src[11])));
+    if (in) {
+      s_xyz[l * 3 + 0] = valid ? X : 0.f;
+      s_xyz[l * 3 + 1] = valid ? Y : 0.f;
+      s_xyz[l * 3 + 2] = valid ? Z : 0.f;
+      if (p.normals_in_world) {
+        // n_w = R_s^T n_c; recover the rows of R_s^T from the source table
+        const float fx = s_src[14], fy = s_src[15], cx = s_src[12], cy = s_src[13];
+        const float n0 = s_nrm[l * 3 + 0], n1 = s_nrm[l * 3 + 1], n2 = s_nrm[l * 3 + 2];
+        float w[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const float ra = s_src[i * 4 + 0] * fx, rb = s_src[i * 4 + 1] * fy;
+          const float rc = s_src[i * 4 + 2] + s_src[i * 4 + 0] * cx + s_src[i * 4 + 1] * cy;
+          w[i] = ra * n0 + rb * n1 + rc * n2;
+        }
+        s_nrm[l * 3 + 0] = w[0];
+        s_nrm[l * 3 + 1] = w[1];
+        s_nrm[l * 3 + 2] = w[2];
+      }
+    }
+    d[j] = valid ? dd : qnan;
     P[j] = d[j] * (float)x;
     Q[j] = d[j] * (float)y;
-    // world position (scripts/test.py:79-90 then :233), fp32 with float64-precomputed rows
-    const float X = fmaf(s_src[0], P[j], fmaf(s_src[1], Q[j], fmaf(s_src[2], d[j], s_src[3])));
-    const float Y = fmaf(s_src[4], P[j], fmaf(s_src[5], Q[j], fmaf(s_src[6], d[j], s_src[7])));
-    const float Z = fmaf(s_src[8], P[j], fmaf(s_src[9], Q[j], fmaf(s_src[10], d[j], s_src[11])));
-    kx[j] = X;
-    ky[j] = Y;
-    kz[j] = Z;
-    if (p.normals_in_world) {
-      // n_w = R_s^T n_c; rows of R_s^T are (src[0]*fx, src[1]*fy, ...) - recover from the table
-      const float fx = s_src[14], fy = s_src[15], cx = s_src[12], cy = s_src[13];
-      float r[3][3];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        r[i][0] = s_src[i * 4 + 0] * fx;
-        r[i][1] = s_src[i * 4 + 1] * fy;
-        r[i][2] = s_src[i * 4 + 2] + r[i][0] * cx / fx + r[i][1] * cy / fy;
-      }
-      const float w0 = r[0][0] * n0 + r[0][1] * n1 + r[0][2] * n2;
-      const float w1 = r[1][0] * n0 + r[1][1] * n1 + r[1][2] * n2;
-      const float w2 = r[2][0] * n0 + r[2][1] * n1 + r[2][2] * n2;
-      n0 = w0;
-      n1 = w1;
-      n2 = w2;
-    }
-    nx[j] = n0;
-    ny[j] = n1;
-    nz[j] = n2;
-    nXw[j] = fmaf(n0, X, fmaf(n1, Y, n2 * Z));
-    nvotes[j] = valid ? 0 : 255;
-    if (in) {
-      if (kStride1) {
-        s_stage[l * 3 + 0] = valid ? X : 0.f;
-        s_stage[l * 3 + 1] = valid ? Y : 0.f;
-        s_stage[l * 3 + 2] = valid ? Z : 0.f;
-      } else {
-        float* o = p.xyz + ((size_t)sl * Ps + pix) * 3;
-        o[0] = valid ? X : 0.f;
-        o[1] = valid ? Y : 0.f;
-        o[2] = valid ? Z : 0.f;
-      }
-    }
+    nvotes[j] = 0;
   }
 
-  const float Wf = (float)p.W, Hf = (float)p.H;
-  const float thr = p.depth_threshold;
-  const float gcos = p.grazing_cos;
-  const float tau = p.two_sided_tau;
+  const unsigned wbits = __float_as_uint((float)p.W), hbits = __float_as_uint((float)p.H);
+  const unsigned idx_bias = (unsigned)kTruncBias * (unsigned)(p.W + 1);
+  const float thr = p.depth_threshold, gcos = p.grazing_cos, tau = p.two_sided_tau;
+  bool any_own = false;
 
   for (int k = 0; k < p.K; ++k) {
     const float4* t4 = reinterpret_cast<const float4*>(s_pair + k * DDN_PAIR_TABLE_FLOATS);
-    const float4 r0 = t4[0], r1 = t4[1], r2 = t4[2], cc = t4[3], kk = t4[4];
-    const int t = __float_as_int(cc.w);
+    const int t = __float_as_int(t4[3].w);
     if (t < 0) continue;
-    const bool own = s_pair[k * DDN_PAIR_TABLE_FLOATS + 20] != 0.f;
-    const float* __restrict__ depth_t = p.refined_all + (size_t)t * HW;
+    if (t4[5].x != 0.f) {  // own view: handled after the main loop
+      any_own = true;
+      continue;
+    }
+    const float4 r0 = t4[0], r1 = t4[1], r2 = t4[2], kk = t4[4];
+    const unsigned map_off = (unsigned)t * (unsigned)HW;
+    float X[kFilterPX], Y[kFilterPX], Z[kFilterPX];
+    bool cand[kFilterPX];
+    bool any = false;
 #pragma unroll
     for (int j = 0; j < kFilterPX; ++j) {
-      const float X = fmaf(r0.x, P[j], fmaf(r0.y, Q[j], fmaf(r0.z, d[j], r0.w)));
-      const float Y = fmaf(r1.x, P[j], fmaf(r1.y, Q[j], fmaf(r1.z, d[j], r1.w)));
-      const float Z = fmaf(r2.x, P[j], fmaf(r2.y, Q[j], fmaf(r2.z, d[j], r2.w)));
-      // grazing gate (scripts/test.py:284-295): dot(n, -(Xw - c_t)/|Xw - c_t|) > cos
-      const float nc = fmaf(nx[j], cc.x, fmaf(ny[j], cc.y, nz[j] * cc.z));
-      const float dn = nc - nXw[j];
-      const float len = sqrt_approx(fmaf(X, X, fmaf(Y, Y, Z * Z)));
-      bool ok = (d[j] > 0.f) && (dn > gcos * len);
-      float zq = Z;
-      float D = 0.f;
-      if (own) {
-        // Own view: the reference normalises by (z + 1e-8) before applying K (scripts/test.py:71-75), so
-        // u = x * z/(z+1e-8) lands ~x*1e-8/z BELOW the integer x (far above float64 round-off) and the
-        // truncation at :308-309 looks up pixel (x-1, y-1) for x, y >= 1.  Reproduced in integer
-        // arithmetic; z is the pixel's own depth.  (x == 0 or y == 0 is a round-off tie in the reference.)
-        const int ux = max(px[j] - 1, 0);
-        const int vy = max(py[j] - 1, 0);
-        zq = d[j];
-        if (ok) D = __ldg(depth_t + (size_t)vy * p.W + ux);
-      } else {
-        const float inv = rcp_approx(Z);
-        const float u = fmaf(kk.x, X * inv, kk.z);
-        const float v = fmaf(kk.y, Y * inv, kk.w);
-        ok = ok && (Z > 0.f) && (u >= 0.f) && (u < Wf) && (v >= 0.f) && (v < Hf);
-        if (!kBilinear) {
-          if (ok) {
-            const int ui = trunc_biased(u) - kTruncBias;
-            const int vi = trunc_biased(v) - kTruncBias;
-            D = __ldg(depth_t + vi * p.W + ui);
-          }
-        } else {
-          if (ok) {
-            // N3: 4 taps at floor(u), floor(v), +1 clamped; all taps must be > 0
-            const int x0 = trunc_biased(u) - kTruncBias;
-            const int y0 = trunc_biased(v) - kTruncBias;
-            const int x1 = min(x0 + 1, p.W - 1);
-            const int y1 = min(y0 + 1, p.H - 1);
-            const float fxw = u - (float)x0, fyw = v - (float)y0;
-            const float ta = __ldg(depth_t + y0 * p.W + x0);
-            const float tb = __ldg(depth_t + y0 * p.W + x1);
-            const float tc = __ldg(depth_t + y1 * p.W + x0);
-            const float td = __ldg(depth_t + y1 * p.W + x1);
-            const bool all = (ta > 0.f) && (tb > 0.f) && (tc > 0.f) && (td > 0.f);
-            const float gx = 1.f - fxw, gy = 1.f - fyw;
-            const float acc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(gx, gy), ta), __fmul_rn(__fmul_rn(fxw, gy), tb)),
-                                                  __fmul_rn(__fmul_rn(gx, fyw), tc)),
-                                        __fmul_rn(__fmul_rn(fxw, fyw), td));
-            D = all ? acc : 0.f;
-          }
+      cand[j] = pair_candidate<kBilinear, kTwoSided>(r0, r1, r2, kk, P[j], Q[j], d[j], p.refined_all, map_off,
+                                                     (unsigned)p.W, p.H, wbits, hbits, idx_bias, thr, tau, X[j], Y[j],
+                                                     Z[j]);
+      any |= cand[j];
+    }
+    // Candidates are rare (floaters): evaluate the grazing gate (scripts/test.py:284-295) only in warps
+    // that have one.  dot(n, -(Xw - c_t)/|Xw - c_t|) > cos with |Xw - c_t| = |X_t|.
+    if (__any_sync(0xffffffffu, any)) {
+      const float4 cc = t4[3];
+#pragma unroll
+      for (int j = 0; j < kFilterPX; ++j) {
+        if (cand[j]) {
+          const int l = j * kFilterThreads + tid;
+          const float n0 = s_nrm[l * 3 + 0], n1 = s_nrm[l * 3 + 1], n2 = s_nrm[l * 3 + 2];
+          const float dn = fmaf(n0, cc.x - s_xyz[l * 3 + 0], fmaf(n1, cc.y - s_xyz[l * 3 + 1], n2 * (cc.z - s_xyz[l * 3 + 2])));
+          const float len = sqrt_approx(fmaf(X[j], X[j], fmaf(Y[j], Y[j], Z[j] * Z[j])));
+          nvotes[j] += (dn > gcos * len) ? 1 : 0;
         }
       }
-      bool bad;
-      if (tau > 0.f)
-        bad = fabsf(zq - D) > tau * D;
-      else
-        bad = zq < __fmul_rn(thr, D);  // float32 product, NEP-50 (scripts/test.py:320)
-      nvotes[j] += (ok && D > 0.f && bad) ? 1 : 0;
     }
   }
 
+  if (any_own) {
+    // Own view (only present in the reference-parity table K = V).  The reference normalises by (z + 1e-8)
+    // before applying K (scripts/test.py:71-75), so u = x * z/(z+1e-8) lands ~x*1e-8/z BELOW the integer x
+    // (far above float64 round-off) and the truncation at :308-309 looks up pixel (x-1, y-1) for
+    // x, y >= 1.  Reproduced in integer arithmetic; z is the pixel's own depth.  (x == 0 or y == 0 is a
+    // round-off tie in the reference.)
+    for (int k = 0; k < p.K; ++k) {
+      const float4* t4 = reinterpret_cast<const float4*>(s_pair + k * DDN_PAIR_TABLE_FLOATS);
+      if (__float_as_int(t4[3].w) < 0 || t4[5].x == 0.f) continue;
+      const float4 cc = t4[3];
+#pragma unroll
+      for (int j = 0; j < kFilterPX; ++j) {
+        const int l = j * kFilterThreads + tid;
+        if (l < n_here && d[j] > 0.f) {
+          const int pix = chunk0 + l;
+          const int ys = pix / p.Ws, xs = pix - ys * p.Ws;
+          const int ux = max(xs * p.stride - 1, 0), vy = max(ys * p.stride - 1, 0);
+          const float D = __ldg(depth_s + (size_t)vy * p.W + ux);
+          const float n0 = s_nrm[l * 3 + 0], n1 = s_nrm[l * 3 + 1], n2 = s_nrm[l * 3 + 2];
+          const float ex = cc.x - s_xyz[l * 3 + 0], ey = cc.y - s_xyz[l * 3 + 1], ez = cc.z - s_xyz[l * 3 + 2];
+          const float dn = fmaf(n0, ex, fmaf(n1, ey, n2 * ez));
+          const float len = sqrt_approx(fmaf(ex, ex, fmaf(ey, ey, ez * ez)));
+          const bool bad = kTwoSided ? (fabsf(d[j] - D) > tau * D) : (d[j] < __fmul_rn(thr, D));
+          nvotes[j] += (D > 0.f && bad && dn > gcos * len) ? 1 : 0;
+        }
+      }
+    }
+  }
+
+  float bmin[3] = {INFINITY, INFINITY, INFINITY}, bmax[3] = {-INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
   for (int j = 0; j < kFilterPX; ++j) {
     const int l = j * kFilterThreads + tid;
     if (l < n_here) {
-      p.votes[(size_t)sl * Ps + chunk0 + l] = (uint8_t)min(nvotes[j], 255);
-      if (nvotes[j] < p.vote_threshold) {
-        bmin[0] = fminf(bmin[0], kx[j]);
-        bmin[1] = fminf(bmin[1], ky[j]);
-        bmin[2] = fminf(bmin[2], kz[j]);
-        bmax[0] = fmaxf(bmax[0], kx[j]);
-        bmax[1] = fmaxf(bmax[1], ky[j]);
-        bmax[2] = fmaxf(bmax[2], kz[j]);
-      }
-    }
-  }
-  if (p.bbox != nullptr) {
+      const bool valid = d[j] > 0.f;
+      p.votes[(size_t)sl * Ps + chunk0 + l] = valid ? (uint8_t)min(nvotes[j], 254) : (uint8_t)255;
+      if (p.bbox != nullptr && valid && nvotes[j] < p.vote_threshold) {
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        bmin[i] = fminf(bmin[i], __shfl_xor_sync(0xffffffffu, bmin[i], o));
-        bmax[i] = fmaxf(bmax[i], __shfl_xor_sync(0xffffffffu, bmax[i], o));
-      }
-    }
-    if ((tid & 31) == 0) {
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        if (bmin[i] <= bmax[i]) {
-          atomicMin(&s_bbox[i], float_to_ordered(bmin[i]));
-          atomicMax(&s_bbox[3 + i], float_to_ordered(bmax[i]));
+        for (int i = 0; i < 3; ++i) {
+          const float c = s_xyz[l * 3 + i];
+          bmin[i] = fminf(bmin[i], c);
+          bmax[i] = fmaxf(bmax[i], c);
         }
       }
     }
   }
+  if (p.bbox != nullptr) {
+    // warp reduction with REDUX on the order-preserving int encoding, then one shared atomic per warp
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int lo = __reduce_min_sync(0xffffffffu, float_to_ordered(bmin[i]));
+      const int hi = __reduce_max_sync(0xffffffffu, float_to_ordered(bmax[i]));
+      if ((tid & 31) == 0 && lo <= hi) {
+        atomicMin(&s_bbox[i], lo);
+        atomicMax(&s_bbox[3 + i], hi);
+      }
+    }
+  }
   __syncthreads();
-  if (kStride1) stage_floats<false>(s_stage, p.xyz + ((size_t)sl * Ps + chunk0) * 3, n_here * 3);
+  if (kStride1) {
+    stage_floats<false>(s_xyz, p.xyz + ((size_t)sl * Ps + chunk0) * 3, n_here * 3);
+  } else {
+    float* o = p.xyz + ((size_t)sl * Ps + chunk0) * 3;
+    for (int i = tid; i < n_here * 3; i += kFilterThreads) __stcs(o + i, s_xyz[i]);
+  }
   if (p.bbox != nullptr && tid < 6) {
     if (tid < 3) {
       if (s_bbox[tid] != 0x7fffffff) atomicMin(p.bbox + tid, s_bbox[tid]);
@@ -428,6 +462,7 @@ int ddn_backproject_filter(const ddn_filter_config* cfg, int64_t n_views_total, 
   DDN_REQUIRE(n_views_total > 0 && n_src >= 0 && k_nbr > 0 && k_nbr <= 1024, "view counts");
   DDN_REQUIRE(src_begin >= 0 && src_begin + n_src <= n_views_total, "source range");
   DDN_REQUIRE(height > 0 && width > 0 && height * width < (1ll << 31), "image size");
+  DDN_REQUIRE(n_views_total * height * width < (1ll << 32), "refined_all must hold fewer than 2^32 pixels (32-bit gather offsets)");
   DDN_REQUIRE(width < (1 << 22) && height < (1 << 22), "image side too large for the truncation trick");
   DDN_REQUIRE(cfg->stride >= 1, "stride");
   DDN_REQUIRE(refined_all && normal && pair_table && src_table && xyz && votes, "null pointer");
@@ -456,21 +491,30 @@ int ddn_backproject_filter(const ddn_filter_config* cfg, int64_t n_views_total, 
   const int Ps = p.Hs * p.Ws;
   dim3 grid((Ps + kFilterChunk - 1) / kFilterChunk, (unsigned)n_src);
   DDN_REQUIRE(n_src <= 65535, "too many source views per call");
-  const size_t smem = (size_t)(kFilterChunk * 3 + 16 + p.K * DDN_PAIR_TABLE_FLOATS) * sizeof(float);
+  const size_t smem = (size_t)(kFilterChunk * 6 + 16 + p.K * DDN_PAIR_TABLE_FLOATS) * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
   const bool bil = cfg->sample_mode == 1;
   const bool s1 = cfg->stride == 1;
-#define DDN_LAUNCH_FILTER(B, S)                                                                            \
+  const bool two = cfg->two_sided_tau > 0.f;
+  DDN_REQUIRE(two || cfg->depth_threshold > 0.f, "depth_threshold must be positive");
+#define DDN_LAUNCH_FILTER(B, S, T)                                                                         \
   do {                                                                                                     \
-    DDN_TRY(check_cuda(cudaFuncSetAttribute(backproject_filter_kernel<B, S>,                               \
+    DDN_TRY(check_cuda(cudaFuncSetAttribute(backproject_filter_kernel<B, S, T>,                            \
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),       \
                        "cudaFuncSetAttribute"));                                                           \
-    backproject_filter_kernel<B, S><<<grid, kFilterThreads, smem, st>>>(p);                                \
+    backproject_filter_kernel<B, S, T><<<grid, kFilterThreads, smem, st>>>(p);                             \
   } while (0)
-  if (bil && s1) DDN_LAUNCH_FILTER(true, true);
-  else if (bil) DDN_LAUNCH_FILTER(true, false);
-  else if (s1) DDN_LAUNCH_FILTER(false, true);
-  else DDN_LAUNCH_FILTER(false, false);
+  if (two) {
+    if (bil && s1) DDN_LAUNCH_FILTER(true, true, true);
+    else if (bil) DDN_LAUNCH_FILTER(true, false, true);
+    else if (s1) DDN_LAUNCH_FILTER(false, true, true);
+    else DDN_LAUNCH_FILTER(false, false, true);
+  } else {
+    if (bil && s1) DDN_LAUNCH_FILTER(true, true, false);
+    else if (bil) DDN_LAUNCH_FILTER(true, false, false);
+    else if (s1) DDN_LAUNCH_FILTER(false, true, false);
+    else DDN_LAUNCH_FILTER(false, false, false);
+  }
 #undef DDN_LAUNCH_FILTER
   return after_launch("backproject_filter_kernel");
 }
