@@ -86,6 +86,14 @@ SYMBOLS = {
         C.c_int,
         [C.POINTER(VoxelGrid), _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     ),
+    "ddn_voxel_partials": (
+        C.c_int,
+        [C.POINTER(VoxelGrid), _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
+    ),
+    "ddn_voxel_merge": (
+        C.c_int,
+        [C.POINTER(VoxelGrid), _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
+    ),
     "ddn_voxel_keys": (C.c_int, [C.POINTER(VoxelGrid), _i64, _vp, _vp, _vp]),
 }
 

@@ -75,13 +75,35 @@ __global__ void fuse_finalize_kernel(GridDev g, int64_t n, const KeyT* __restric
 
 constexpr int kFixShift = 20;  // offsets are stored in units of voxel * 2^-20
 
-template <typename KeyT>
+__device__ __forceinline__ float voxel_centre(float o, uint32_t k, float voxel) {
+  return __fadd_rn(o, __fmul_rn((float)k + 0.5f, voxel));
+}
+
+// mean position = centre + (sum / count) * voxel * 2^-20 (float64, once per voxel); colour = round-half-up
+__device__ __forceinline__ void finalize_voxel(const GridDev& g, float cx, float cy, float cz, long long sx, long long sy,
+                                               long long sz, unsigned long long sr, unsigned long long sg,
+                                               unsigned long long sb, long long cnt, float* __restrict__ oxyz,
+                                               uint8_t* __restrict__ orgb) {
+  const double inv = (double)g.voxel / ((double)cnt * (double)(1 << kFixShift));
+  oxyz[0] = (float)((double)cx + (double)sx * inv);
+  oxyz[1] = (float)((double)cy + (double)sy * inv);
+  oxyz[2] = (float)((double)cz + (double)sz * inv);
+  const unsigned long long c2 = 2ull * (unsigned long long)cnt;
+  orgb[0] = (uint8_t)((2 * sr + cnt) / c2);
+  orgb[1] = (uint8_t)((2 * sg + cnt) / c2);
+  orgb[2] = (uint8_t)((2 * sb + cnt) / c2);
+}
+
+// One thread per run of equal keys.  kPartialOut = false: write the voxel mean (single GPU).
+// kPartialOut = true: write the raw integer sums so that another rank can merge them.
+template <typename KeyT, bool kPartialOut>
 __global__ void __launch_bounds__(256)
 segment_mean_kernel(GridDev g, const KeyT* __restrict__ unique_keys, const int* __restrict__ run_counts,
                     const int* __restrict__ run_starts, const int64_t* __restrict__ counts,
                     const uint32_t* __restrict__ sorted_idx, const float* __restrict__ xyz,
                     const uint8_t* __restrict__ rgb, uint64_t* __restrict__ out_keys, float* __restrict__ out_xyz,
-                    uint8_t* __restrict__ out_rgb, int32_t* __restrict__ out_count) {
+                    uint8_t* __restrict__ out_rgb, int32_t* __restrict__ out_count, long long* __restrict__ part_sums,
+                    uint32_t* __restrict__ part_rgb) {
   const int64_t mv = counts[1];
   const float scale = (float)(1 << kFixShift);
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < mv; r += (int64_t)gridDim.x * blockDim.x) {
@@ -90,9 +112,7 @@ segment_mean_kernel(GridDev g, const KeyT* __restrict__ unique_keys, const int* 
     const uint32_t ky = (uint32_t)((key >> g.bx) & (((KeyT)1 << g.by) - 1));
     const uint32_t kz = (uint32_t)((key >> (g.bx + g.by)) & (((KeyT)1 << g.bz) - 1));
     // voxel centre in float32; p - centre is exact in float32 for points inside the voxel
-    const float cx = __fadd_rn(g.ox, __fmul_rn((float)kx + 0.5f, g.voxel));
-    const float cy = __fadd_rn(g.oy, __fmul_rn((float)ky + 0.5f, g.voxel));
-    const float cz = __fadd_rn(g.oz, __fmul_rn((float)kz + 0.5f, g.voxel));
+    const float cx = voxel_centre(g.ox, kx, g.voxel), cy = voxel_centre(g.oy, ky, g.voxel), cz = voxel_centre(g.oz, kz, g.voxel);
     const int start = run_starts[r], cnt = run_counts[r];
     long long sx = 0, sy = 0, sz = 0;
     unsigned long long sr = 0, sg = 0, sb = 0;
@@ -106,16 +126,70 @@ segment_mean_kernel(GridDev g, const KeyT* __restrict__ unique_keys, const int* 
       sg += __ldg(rgb + i * 3 + 1);
       sb += __ldg(rgb + i * 3 + 2);
     }
-    const double inv = (double)g.voxel / ((double)cnt * (double)(1 << kFixShift));
-    out_xyz[r * 3 + 0] = (float)((double)cx + (double)sx * inv);
-    out_xyz[r * 3 + 1] = (float)((double)cy + (double)sy * inv);
-    out_xyz[r * 3 + 2] = (float)((double)cz + (double)sz * inv);
-    const unsigned long long c2 = 2ull * (unsigned long long)cnt;
-    out_rgb[r * 3 + 0] = (uint8_t)((2 * sr + cnt) / c2);
-    out_rgb[r * 3 + 1] = (uint8_t)((2 * sg + cnt) / c2);
-    out_rgb[r * 3 + 2] = (uint8_t)((2 * sb + cnt) / c2);
     out_keys[r] = (uint64_t)kx | ((uint64_t)ky << 21) | ((uint64_t)kz << 42);
     out_count[r] = cnt;
+    if (kPartialOut) {
+      part_sums[r * 3 + 0] = sx;
+      part_sums[r * 3 + 1] = sy;
+      part_sums[r * 3 + 2] = sz;
+      part_rgb[r * 3 + 0] = (uint32_t)sr;
+      part_rgb[r * 3 + 1] = (uint32_t)sg;
+      part_rgb[r * 3 + 2] = (uint32_t)sb;
+    } else {
+      finalize_voxel(g, cx, cy, cz, sx, sy, sz, sr, sg, sb, (long long)cnt, out_xyz + r * 3, out_rgb + r * 3);
+    }
+  }
+}
+
+// ---- merge of partial records (multi-GPU owner side) ----------------------------------------------
+template <typename KeyT>
+__global__ void compact_key_kernel(GridDev g, int64_t n, const uint64_t* __restrict__ canon, KeyT* __restrict__ keys,
+                                   uint32_t* __restrict__ idx) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t c = canon[i];
+  const uint64_t kx = c & 0x1fffff, ky = (c >> 21) & 0x1fffff, kz = (c >> 42) & 0x1fffff;
+  keys[i] = (KeyT)kx | ((KeyT)ky << g.bx) | ((KeyT)kz << (g.bx + g.by));
+  idx[i] = (uint32_t)i;
+}
+
+template <typename KeyT>
+__global__ void merge_finalize_counts_kernel(int64_t n, const int* __restrict__ num_runs, int64_t* __restrict__ counts_out) {
+  counts_out[0] = n;
+  counts_out[1] = *num_runs;
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(256)
+merge_segments_kernel(GridDev g, const KeyT* __restrict__ unique_keys, const int* __restrict__ run_counts,
+                      const int* __restrict__ run_starts, const int64_t* __restrict__ counts,
+                      const uint32_t* __restrict__ sorted_idx, const long long* __restrict__ in_sums,
+                      const uint32_t* __restrict__ in_rgb, const int32_t* __restrict__ in_count,
+                      uint64_t* __restrict__ out_keys, float* __restrict__ out_xyz, uint8_t* __restrict__ out_rgb,
+                      int32_t* __restrict__ out_count) {
+  const int64_t mv = counts[1];
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < mv; r += (int64_t)gridDim.x * blockDim.x) {
+    const KeyT key = unique_keys[r];
+    const uint32_t kx = (uint32_t)(key & (((KeyT)1 << g.bx) - 1));
+    const uint32_t ky = (uint32_t)((key >> g.bx) & (((KeyT)1 << g.by) - 1));
+    const uint32_t kz = (uint32_t)((key >> (g.bx + g.by)) & (((KeyT)1 << g.bz) - 1));
+    const float cx = voxel_centre(g.ox, kx, g.voxel), cy = voxel_centre(g.oy, ky, g.voxel), cz = voxel_centre(g.oz, kz, g.voxel);
+    const int start = run_starts[r], nrec = run_counts[r];
+    long long sx = 0, sy = 0, sz = 0, cnt = 0;
+    unsigned long long sr = 0, sg = 0, sb = 0;
+    for (int j = 0; j < nrec; ++j) {
+      const size_t i = sorted_idx[start + j];
+      sx += in_sums[i * 3 + 0];
+      sy += in_sums[i * 3 + 1];
+      sz += in_sums[i * 3 + 2];
+      sr += in_rgb[i * 3 + 0];
+      sg += in_rgb[i * 3 + 1];
+      sb += in_rgb[i * 3 + 2];
+      cnt += in_count[i];
+    }
+    out_keys[r] = (uint64_t)kx | ((uint64_t)ky << 21) | ((uint64_t)kz << 42);
+    out_count[r] = (int32_t)cnt;
+    finalize_voxel(g, cx, cy, cz, sx, sy, sz, sr, sg, sb, cnt, out_xyz + r * 3, out_rgb + r * 3);
   }
 }
 
@@ -160,7 +234,8 @@ static int fuse_layout(int64_t n, FuseLayout* L) {
 template <typename KeyT>
 static int fuse_impl(const GridDev& g, int64_t n, const float* xyz, const uint8_t* rgb, const uint8_t* votes, int thr,
                      uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb, int32_t* out_count, int64_t* counts_out,
-                     void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+                     void* workspace, int64_t workspace_bytes, cudaStream_t st, long long* part_sums = nullptr,
+                     uint32_t* part_rgb = nullptr) {
   FuseLayout L;
   DDN_TRY(fuse_layout<KeyT>(n, &L));
   if ((int64_t)L.total > workspace_bytes) {
@@ -197,9 +272,57 @@ static int fuse_impl(const GridDev& g, int64_t n, const float* xyz, const uint8_
   g_launches.fetch_add(2, std::memory_order_relaxed);
   fuse_finalize_kernel<KeyT><<<1, 1, 0, st>>>(g, n, uniq, run_counts, num_runs, counts_out);
   DDN_TRY(after_launch("fuse_finalize_kernel"));
-  segment_mean_kernel<KeyT><<<kNumSMs * 8, 256, 0, st>>>(g, uniq, run_counts, run_starts, counts_out, dv.Current(), xyz,
-                                                        rgb, out_keys, out_xyz, out_rgb, out_count);
+  if (part_sums != nullptr)
+    segment_mean_kernel<KeyT, true><<<kNumSMs * 8, 256, 0, st>>>(g, uniq, run_counts, run_starts, counts_out, dv.Current(),
+                                                                xyz, rgb, out_keys, out_xyz, out_rgb, out_count, part_sums,
+                                                                part_rgb);
+  else
+    segment_mean_kernel<KeyT, false><<<kNumSMs * 8, 256, 0, st>>>(g, uniq, run_counts, run_starts, counts_out, dv.Current(),
+                                                                 xyz, rgb, out_keys, out_xyz, out_rgb, out_count, nullptr,
+                                                                 nullptr);
   return after_launch("segment_mean_kernel");
+}
+
+template <typename KeyT>
+static int merge_impl(const GridDev& g, int64_t n, const uint64_t* in_keys, const long long* in_sums, const uint32_t* in_rgb,
+                      const int32_t* in_count, uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb, int32_t* out_count,
+                      int64_t* counts_out, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+  FuseLayout L;
+  DDN_TRY(fuse_layout<KeyT>(n, &L));
+  if ((int64_t)L.total > workspace_bytes) {
+    set_error("merge workspace too small: %lld < %lld", (long long)workspace_bytes, (long long)L.total);
+    return DDN_ERR_WORKSPACE_TOO_SMALL;
+  }
+  char* base = reinterpret_cast<char*>(align_up((int64_t)(uintptr_t)workspace, 256));
+  KeyT* keys_a = (KeyT*)(base + L.keys_a);
+  KeyT* keys_b = (KeyT*)(base + L.keys_b);
+  uint32_t* idx_a = (uint32_t*)(base + L.idx_a);
+  uint32_t* idx_b = (uint32_t*)(base + L.idx_b);
+  KeyT* uniq = (KeyT*)(base + L.uniq);
+  int* run_counts = (int*)(base + L.run_counts);
+  int* run_starts = (int*)(base + L.run_starts);
+  int* num_runs = (int*)(base + L.num_runs);
+  void* temp = base + L.cub_temp;
+  size_t temp_bytes = L.cub_temp_bytes;
+  compact_key_kernel<KeyT><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, n, in_keys, keys_a, idx_a);
+  DDN_TRY(after_launch("compact_key_kernel"));
+  cub::DoubleBuffer<KeyT> dk(keys_a, keys_b);
+  cub::DoubleBuffer<uint32_t> dv(idx_a, idx_b);
+  const int end_bit = g.bx + g.by + g.bz;
+  DDN_TRY(check_cuda(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, dk, dv, (int)n, 0, end_bit, st), "cub sort"));
+  g_launches.fetch_add((end_bit + 7) / 8 + 1, std::memory_order_relaxed);
+  temp_bytes = L.cub_temp_bytes;
+  DDN_TRY(check_cuda(cub::DeviceRunLengthEncode::Encode(temp, temp_bytes, dk.Current(), uniq, run_counts, num_runs, (int)n, st),
+                     "cub rle"));
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  temp_bytes = L.cub_temp_bytes;
+  DDN_TRY(check_cuda(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, run_counts, run_starts, (int)n, st), "cub scan"));
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  merge_finalize_counts_kernel<KeyT><<<1, 1, 0, st>>>(n, num_runs, counts_out);
+  DDN_TRY(after_launch("merge_finalize_counts_kernel"));
+  merge_segments_kernel<KeyT><<<kNumSMs * 8, 256, 0, st>>>(g, uniq, run_counts, run_starts, counts_out, dv.Current(), in_sums,
+                                                          in_rgb, in_count, out_keys, out_xyz, out_rgb, out_count);
+  return after_launch("merge_segments_kernel");
 }
 
 static int grid_from_host(const ddn_voxel_grid* h, GridDev* g) {
@@ -250,6 +373,45 @@ int ddn_voxel_fuse(const ddn_voxel_grid* grid_host, int64_t n_points, const floa
                                counts_out, workspace, workspace_bytes, st);
   return fuse_impl<uint64_t>(g, n_points, xyz, rgb, votes, vote_threshold, out_keys, out_xyz, out_rgb, out_count,
                              counts_out, workspace, workspace_bytes, st);
+}
+
+int ddn_voxel_partials(const ddn_voxel_grid* grid_host, int64_t n_points, const float* xyz, const uint8_t* rgb,
+                       const uint8_t* votes, int32_t vote_threshold, uint64_t* part_keys, int64_t* part_sums,
+                       uint32_t* part_rgb, int32_t* part_count, int64_t* counts_out, void* workspace,
+                       int64_t workspace_bytes, void* stream) {
+  using namespace ddn;
+  GridDev g;
+  DDN_TRY(grid_from_host(grid_host, &g));
+  DDN_REQUIRE(n_points >= 0 && n_points < (1ll << 31) - 1024, "n_points");
+  DDN_REQUIRE(counts_out != nullptr, "null counts_out");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_points == 0) return check_cuda(cudaMemsetAsync(counts_out, 0, 16, st), "memset counts");
+  DDN_REQUIRE(xyz && rgb && part_keys && part_sums && part_rgb && part_count && workspace, "null pointer");
+  if (g.bx + g.by + g.bz <= 31)
+    return fuse_impl<uint32_t>(g, n_points, xyz, rgb, votes, vote_threshold, part_keys, nullptr, nullptr, part_count,
+                               counts_out, workspace, workspace_bytes, st, (long long*)part_sums, part_rgb);
+  return fuse_impl<uint64_t>(g, n_points, xyz, rgb, votes, vote_threshold, part_keys, nullptr, nullptr, part_count,
+                             counts_out, workspace, workspace_bytes, st, (long long*)part_sums, part_rgb);
+}
+
+int ddn_voxel_merge(const ddn_voxel_grid* grid_host, int64_t n_records, const uint64_t* part_keys,
+                    const int64_t* part_sums, const uint32_t* part_rgb, const int32_t* part_count,
+                    uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb, int32_t* out_count, int64_t* counts_out,
+                    void* workspace, int64_t workspace_bytes, void* stream) {
+  using namespace ddn;
+  GridDev g;
+  DDN_TRY(grid_from_host(grid_host, &g));
+  DDN_REQUIRE(n_records >= 0 && n_records < (1ll << 31) - 1024, "n_records");
+  DDN_REQUIRE(counts_out != nullptr, "null counts_out");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_records == 0) return check_cuda(cudaMemsetAsync(counts_out, 0, 16, st), "memset counts");
+  DDN_REQUIRE(part_keys && part_sums && part_rgb && part_count && out_keys && out_xyz && out_rgb && out_count && workspace,
+              "null pointer");
+  if (g.bx + g.by + g.bz <= 32)
+    return merge_impl<uint32_t>(g, n_records, part_keys, (const long long*)part_sums, part_rgb, part_count, out_keys, out_xyz,
+                                out_rgb, out_count, counts_out, workspace, workspace_bytes, st);
+  return merge_impl<uint64_t>(g, n_records, part_keys, (const long long*)part_sums, part_rgb, part_count, out_keys, out_xyz,
+                              out_rgb, out_count, counts_out, workspace, workspace_bytes, st);
 }
 
 int ddn_voxel_keys(const ddn_voxel_grid* grid_host, int64_t n_points, const float* xyz, uint64_t* keys, void* stream) {

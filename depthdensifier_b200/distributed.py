@@ -98,9 +98,16 @@ class ShardedDensifier:
     the per-view maps passed to ``run`` cover the rank's own views [lo, hi)."""
 
     def __init__(self, cfg: DensifyConfig, device, rank: int, world: int, n_views_total: int, lo: int, hi: int,
-                 cam_from_world: torch.Tensor, intr: torch.Tensor, nbr: np.ndarray, height: int, width: int, group=None):
-        if not torch.cuda.is_available():
-            raise ops.DDNError("ShardedDensifier needs a CUDA device: depthdensifier_b200 has no CPU fallback")
+                 cam_from_world: torch.Tensor, intr: torch.Tensor, nbr: np.ndarray, height: int, width: int, group=None,
+                 backend=None):
+        # `backend` is the module providing the device ops; the product always uses `ops` (CUDA, no CPU
+        # fallback).  Tests inject an object with the same functions to exercise the exchange logic on
+        # CPU with the gloo backend.
+        if backend is None:
+            if not torch.cuda.is_available():
+                raise ops.DDNError("ShardedDensifier needs a CUDA device: depthdensifier_b200 has no CPU fallback")
+            backend = ops
+        self.ops = backend
         self.cfg = cfg
         self.device = torch.device(device)
         self.rank, self.world, self.group = rank, world, group
@@ -142,7 +149,7 @@ class ShardedDensifier:
                                input_split_sizes=[len(s) * hw for s in self.plan.send_views], group=self.group)
 
     def _global_bbox(self, bbox: torch.Tensor) -> np.ndarray:
-        bb = ops.decode_bbox(bbox) if self.world == 1 else None
+        bb = self.ops.decode_bbox(bbox) if self.world == 1 else None
         if self.world > 1:
             import torch.distributed as dist
 
@@ -150,7 +157,7 @@ class ShardedDensifier:
             lo3, hi3 = bbox[:3].clone(), bbox[3:].clone()
             dist.all_reduce(lo3, op=dist.ReduceOp.MIN, group=self.group)
             dist.all_reduce(hi3, op=dist.ReduceOp.MAX, group=self.group)
-            bb = ops.decode_bbox(torch.cat([lo3, hi3]))
+            bb = self.ops.decode_bbox(torch.cat([lo3, hi3]))
         return bb
 
     # -- pipeline ---------------------------------------------------------------------------------------
@@ -159,7 +166,7 @@ class ShardedDensifier:
         ev = {}
 
         def mark(name, fn):
-            if not record_events:
+            if not record_events or self.device.type != "cuda":
                 return fn()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
@@ -172,13 +179,13 @@ class ShardedDensifier:
             off = sparse_offsets.cpu().numpy()
             self._max_sparse = max(int(np.max(np.diff(off))) if len(off) > 1 else 1, 1)
         refined_slots = torch.empty((self.n_slots, self.H, self.W), dtype=torch.float32, device=self.device)
-        _, stats = mark("align", lambda: ops.align_views(
+        _, stats = mark("align", lambda: self.ops.align_views(
             depth, mask, self.poses_slots[: self.n_local].contiguous(), self.kmat, sparse_xyz, sparse_offsets,
             self._max_sparse, cfg.align, out=refined_slots[: self.n_local]))
         mark("halo_exchange", lambda: self._exchange_halo(refined_slots))
-        pair, src = mark("pair_tables", lambda: ops.build_pair_tables(self.poses_slots, self.intr_slots, self._nbr_full(), 0, self.n_local))
-        bbox = ops.new_bbox(self.device)
-        xyz, votes = mark("backproject_filter", lambda: ops.backproject_filter(
+        pair, src = mark("pair_tables", lambda: self.ops.build_pair_tables(self.poses_slots, self.intr_slots, self._nbr_full(), 0, self.n_local))
+        bbox = self.ops.new_bbox(self.device)
+        xyz, votes = mark("backproject_filter", lambda: self.ops.backproject_filter(
             refined_slots, normal, self.nbr_slots, pair, src, 0, self.thr, cfg.filter, bbox=bbox))
         res = ShardResult(refined=refined_slots[: self.n_local], stats=stats, xyz=xyz, votes=votes, vote_threshold=self.thr,
                           bbox=bbox, events=ev)
@@ -189,11 +196,11 @@ class ShardedDensifier:
             if not np.all(np.isfinite(bb)):
                 res.counts = torch.zeros(2, dtype=torch.int64, device=self.device)
                 return res
-            grid = ops.make_grid(bb[:3], bb[3:], cfg.voxel)
+            grid = self.ops.make_grid(bb[:3], bb[3:], cfg.voxel)
         s = cfg.filter.stride
         rgb_s = rgb if s == 1 else rgb[:, ::s, ::s].contiguous()
         if self.world == 1:
-            k, x, c, n, counts = mark("voxel_fuse", lambda: ops.voxel_fuse(
+            k, x, c, n, counts = mark("voxel_fuse", lambda: self.ops.voxel_fuse(
                 xyz.view(-1, 3), rgb_s.view(-1, 3), votes.view(-1), self.thr, grid, trim=False))
         else:
             k, x, c, n, counts = mark("voxel_fuse", lambda: self._fuse_sharded(xyz, rgb_s, votes, grid))
@@ -210,7 +217,7 @@ class ShardedDensifier:
     def _fuse_sharded(self, xyz, rgb, votes, grid):
         import torch.distributed as dist
 
-        pk, psum, prgb, pcnt, counts = ops.voxel_fuse_partial(xyz.view(-1, 3), rgb.view(-1, 3), votes.view(-1), self.thr, grid)
+        pk, psum, prgb, pcnt, counts = self.ops.voxel_fuse_partial(xyz.view(-1, 3), rgb.view(-1, 3), votes.view(-1), self.thr, grid)
         mv = int(counts[1].item())
         pk, psum, prgb, pcnt = pk[:mv], psum[:mv], prgb[:mv], pcnt[:mv]
         R = self.world
@@ -239,7 +246,7 @@ class ShardedDensifier:
             return out
 
         rk, rsum, rrgb, rcnt = exchange(pk, 1), exchange(psum, 3), exchange(prgb, 3), exchange(pcnt, 1)
-        k, x, c, n, mcounts = ops.voxel_merge_partials(rk, rsum, rrgb, rcnt, grid)
+        k, x, c, n, mcounts = self.ops.voxel_merge_partials(rk, rsum, rrgb, rcnt, grid)
         counts2 = torch.stack([counts[0], mcounts[1]])  # (points fused locally, voxels owned)
         return k, x, c, n, counts2
 
@@ -252,7 +259,8 @@ class ShardedDensifier:
         dev_in = [t.to(self.device, non_blocking=True) for t in (depth, normal, mask, rgb, sparse_xyz, sparse_offsets)]
         res = self.run(*dev_in)
         if res.counts is None:
-            torch.cuda.synchronize(self.device)
+            if self.device.type == "cuda":
+                torch.cuda.synchronize(self.device)
             return {"d2h_bytes": 0}
         mv = int(res.counts[1].item())
         out = {}

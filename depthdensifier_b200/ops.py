@@ -253,6 +253,61 @@ def voxel_fuse(xyz, rgb, votes, vote_threshold: int, grid: _lib.VoxelGrid, trim:
     return out_keys, out_xyz, out_rgb, out_cnt, counts
 
 
+def voxel_fuse_partial(xyz, rgb, votes, vote_threshold: int, grid: _lib.VoxelGrid):
+    """Rank-local stage 4: per-voxel partial sums (keys ascending).  Returns part_keys [N] i64,
+    part_sums [N,3] i64, part_rgb [N,3] i32 (uint32 bits), part_count [N] i32 (all sized for the worst
+    case N) and the device counts [2] = (participating points, local voxels)."""
+    lib = _lib.load()
+    dev = _require_cuda(xyz, rgb, votes)
+    N = xyz.shape[0]
+    assert xyz.dtype == torch.float32 and rgb.dtype == torch.uint8 and tuple(rgb.shape) == (N, 3)
+    nbytes = C.c_int64(0)
+    _lib.check(lib.ddn_fuse_workspace_bytes(N, C.byref(nbytes)))
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+    pk = torch.empty(N, dtype=torch.int64, device=dev)
+    ps = torch.empty((N, 3), dtype=torch.int64, device=dev)
+    pr = torch.empty((N, 3), dtype=torch.int32, device=dev)
+    pc = torch.empty(N, dtype=torch.int32, device=dev)
+    counts = torch.zeros(2, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(
+            lib.ddn_voxel_partials(
+                C.byref(grid), N, _p(xyz), _p(rgb), _p(votes), int(vote_threshold), _p(pk), _p(ps), _p(pr), _p(pc),
+                _p(counts), _p(ws), nbytes.value, _stream(),
+            )
+        )
+    return pk, ps, pr, pc, counts
+
+
+def voxel_merge_partials(part_keys, part_sums, part_rgb, part_count, grid: _lib.VoxelGrid, trim: bool = False):
+    """Owner-side merge of partial records (any order) into final voxels."""
+    lib = _lib.load()
+    dev = _require_cuda(part_keys, part_sums, part_rgb, part_count)
+    n = part_keys.shape[0]
+    assert part_keys.dtype == torch.int64 and part_sums.dtype == torch.int64 and part_rgb.dtype == torch.int32
+    assert part_count.dtype == torch.int32 and tuple(part_sums.shape) == (n, 3) and tuple(part_rgb.shape) == (n, 3)
+    nbytes = C.c_int64(0)
+    _lib.check(lib.ddn_fuse_workspace_bytes(max(n, 1), C.byref(nbytes)))
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+    m = max(n, 1)
+    out_keys = torch.empty(m, dtype=torch.int64, device=dev)
+    out_xyz = torch.empty((m, 3), dtype=torch.float32, device=dev)
+    out_rgb = torch.empty((m, 3), dtype=torch.uint8, device=dev)
+    out_cnt = torch.empty(m, dtype=torch.int32, device=dev)
+    counts = torch.zeros(2, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(
+            lib.ddn_voxel_merge(
+                C.byref(grid), n, _p(part_keys), _p(part_sums), _p(part_rgb), _p(part_count), _p(out_keys), _p(out_xyz),
+                _p(out_rgb), _p(out_cnt), _p(counts), _p(ws), nbytes.value, _stream(),
+            )
+        )
+    if trim:
+        mv = int(counts[1].item())
+        return out_keys[:mv], out_xyz[:mv], out_rgb[:mv], out_cnt[:mv], counts
+    return out_keys, out_xyz, out_rgb, out_cnt, counts
+
+
 def voxel_keys(xyz, voxel: float, origin) -> torch.Tensor:
     """Canonical 3x21-bit keys (int64 view of the uint64 key) for xyz [N,3] f32."""
     lib = _lib.load()

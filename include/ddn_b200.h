@@ -163,6 +163,21 @@ DDN_API int ddn_voxel_fuse(const ddn_voxel_grid* grid_host, int64_t n_points, co
                    uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb, int32_t* out_count,
                    int64_t* counts_out, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Multi-GPU form of stage 4.  ddn_voxel_partials fuses the rank's own points into per-voxel PARTIAL
+ * sums (keys ascending): part_sums [N,3] i64 = sum of (p - voxel centre) in units of voxel * 2^-20,
+ * part_rgb [N,3] u32 colour sums, part_count [N] i32.  Integer sums make the final means independent
+ * of how points are split over ranks.  ddn_voxel_merge adds the records of equal key (any input
+ * order, e.g. the concatenation of the sorted runs received from R ranks) and finalises them. */
+DDN_API int ddn_voxel_partials(const ddn_voxel_grid* grid_host, int64_t n_points, const float* xyz,
+                       const uint8_t* rgb, const uint8_t* votes, int32_t vote_threshold,
+                       uint64_t* part_keys, int64_t* part_sums, uint32_t* part_rgb, int32_t* part_count,
+                       int64_t* counts_out, void* workspace, int64_t workspace_bytes, void* stream);
+
+DDN_API int ddn_voxel_merge(const ddn_voxel_grid* grid_host, int64_t n_records, const uint64_t* part_keys,
+                    const int64_t* part_sums, const uint32_t* part_rgb, const int32_t* part_count,
+                    uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb, int32_t* out_count,
+                    int64_t* counts_out, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Stand-alone pieces of stage 4 (used by the multi-GPU path and by tests). */
 DDN_API int ddn_voxel_keys(const ddn_voxel_grid* grid_host, int64_t n_points, const float* xyz,
                    uint64_t* keys, void* stream);
