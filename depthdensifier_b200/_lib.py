@@ -57,7 +57,7 @@ class FilterConfig(C.Structure):
 
 
 class VoxelGrid(C.Structure):
-    _fields_ = [("voxel", C.c_float), ("origin", C.c_float * 3), ("bits", C.c_int32 * 3)]
+    _fields_ = [("voxel", C.c_float), ("origin", C.c_float * 3), ("bits", C.c_int32 * 3), ("dims", C.c_int32 * 3)]
 
 
 PAIR_TABLE_FLOATS = 24
@@ -81,7 +81,7 @@ SYMBOLS = {
         [C.POINTER(FilterConfig), _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp],
     ),
     "ddn_bbox_init": (C.c_int, [_vp, _vp]),
-    "ddn_fuse_workspace_bytes": (C.c_int, [_i64, C.POINTER(_i64)]),
+    "ddn_fuse_workspace_bytes": (C.c_int, [C.POINTER(VoxelGrid), _i64, C.POINTER(_i64)]),
     "ddn_voxel_fuse": (
         C.c_int,
         [C.POINTER(VoxelGrid), _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],

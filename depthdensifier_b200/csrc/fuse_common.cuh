@@ -1,0 +1,84 @@
+// Shared definitions of stage 4 (voxel-grid fusion): grid description, IEEE-exact voxel coordinates,
+// fixed-point offsets and the finalisation of one voxel.  Used by the dense-rank path (fuse.cu) and by
+// the sort path kept for grids too large for a dense occupancy bitmap (fuse_sort.cu).
+#pragma once
+
+#include "common.cuh"
+
+namespace ddn {
+
+struct GridDev {
+  float voxel, ox, oy, oz;
+  int bx, by, bz;  // significant bits per axis (sort path key packing)
+  int nx, ny, nz;  // cells per axis; a point outside [0, n) on any axis does not participate
+};
+
+inline int grid_from_host(const ddn_voxel_grid* h, GridDev* g) {
+  DDN_REQUIRE(h != nullptr, "null grid");
+  DDN_REQUIRE(h->voxel > 0.f, "voxel size");
+  for (int i = 0; i < 3; ++i) DDN_REQUIRE(h->bits[i] >= 1 && h->bits[i] <= 21, "bits per axis must be in [1,21]");
+  for (int i = 0; i < 3; ++i)
+    DDN_REQUIRE(h->dims[i] >= 0 && h->dims[i] <= (1 << h->bits[i]), "dims per axis must be in [0, 2^bits]");
+  g->voxel = h->voxel;
+  g->ox = h->origin[0];
+  g->oy = h->origin[1];
+  g->oz = h->origin[2];
+  g->bx = h->bits[0];
+  g->by = h->bits[1];
+  g->bz = h->bits[2];
+  g->nx = h->dims[0] > 0 ? h->dims[0] : (1 << h->bits[0]);
+  g->ny = h->dims[1] > 0 ? h->dims[1] : (1 << h->bits[1]);
+  g->nz = h->dims[2] > 0 ? h->dims[2] : (1 << h->bits[2]);
+  return DDN_OK;
+}
+
+// k = floor((p - o) / voxel) with IEEE float32 sub and div (bit-exact with the numpy definition,
+// x/v and x*(1/v) round differently).  The quotient is first estimated with one multiply
+// by the rounded reciprocal; the two can only floor differently when the estimate sits within a few
+// ulp of an integer, and only then is the IEEE division issued.
+__device__ __forceinline__ float voxel_coord(float p, float o, float voxel, float rvoxel) {
+  const float a = __fsub_rn(p, o);
+  const float t = __fmul_rn(a, rvoxel);
+  const float k = floorf(t);
+  const float r = t - k;
+  const float eps = fmaxf(fabsf(t), 1.f) * 1e-6f;
+  if (r < eps || r > 1.f - eps || !(fabsf(t) < 4194304.f)) return floorf(__fdiv_rn(a, voxel));
+  return k;
+}
+
+constexpr int kFixShift = 20;  // offsets are stored in units of voxel * 2^-20
+
+__device__ __forceinline__ float voxel_centre(float o, uint32_t k, float voxel) {
+  return __fadd_rn(o, __fmul_rn((float)k + 0.5f, voxel));
+}
+
+// (p - voxel centre) / voxel * 2^20, rounded to nearest: the integer a point adds to its voxel's sum
+__device__ __forceinline__ long long voxel_offset_fix(float p, float centre, float voxel) {
+  return __float2ll_rn(__fmul_rn(__fdiv_rn(__fsub_rn(p, centre), voxel), (float)(1 << kFixShift)));
+}
+
+// mean position = centre + (sum / count) * voxel * 2^-20 (float64, once per voxel); colour = round-half-up
+__device__ __forceinline__ void finalize_voxel(const GridDev& g, float cx, float cy, float cz, long long sx, long long sy,
+                                               long long sz, unsigned long long sr, unsigned long long sg,
+                                               unsigned long long sb, long long cnt, float* __restrict__ oxyz,
+                                               uint8_t* __restrict__ orgb) {
+  const double inv = (double)g.voxel / ((double)cnt * (double)(1 << kFixShift));
+  oxyz[0] = (float)((double)cx + (double)sx * inv);
+  oxyz[1] = (float)((double)cy + (double)sy * inv);
+  oxyz[2] = (float)((double)cz + (double)sz * inv);
+  const unsigned long long c2 = 2ull * (unsigned long long)cnt;
+  orgb[0] = (uint8_t)((2 * sr + cnt) / c2);
+  orgb[1] = (uint8_t)((2 * sg + cnt) / c2);
+  orgb[2] = (uint8_t)((2 * sb + cnt) / c2);
+}
+
+// ---- sort path (fuse_sort.cu) -------------------------------------------------------------------
+int sort_fuse_workspace_bytes(int64_t n_points, int64_t* bytes_out);
+int sort_fuse_points(const GridDev& g, int64_t n, const float* xyz, const uint8_t* rgb, const uint8_t* votes, int thr,
+                     uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb, int32_t* out_count, int64_t* counts_out,
+                     void* workspace, int64_t workspace_bytes, cudaStream_t st, long long* part_sums, uint32_t* part_rgb);
+int sort_merge_records(const GridDev& g, int64_t n, const uint64_t* in_keys, const long long* in_sums, const uint32_t* in_rgb,
+                       const int32_t* in_count, uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb, int32_t* out_count,
+                       int64_t* counts_out, void* workspace, int64_t workspace_bytes, cudaStream_t st);
+
+}  // namespace ddn

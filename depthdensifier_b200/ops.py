@@ -220,7 +220,16 @@ def make_grid(bbox_min, bbox_max, voxel: float):
     for i in range(3):
         g.origin[i] = float(origin[i])
         g.bits[i] = bits[i]
+        g.dims[i] = int(cells[i])
     return g
+
+
+def checked_voxel_count(counts: torch.Tensor) -> int:
+    """Number of voxels from the device counts [2] (synchronises); raises on the colour-sum overflow flag."""
+    n_pts, mv = (int(x) for x in counts.cpu().tolist())
+    if n_pts < 0:
+        raise DDNError("voxel fusion: a voxel collected 2^24 or more points (32-bit colour sums); use a smaller voxel")
+    return mv
 
 
 def voxel_fuse(xyz, rgb, votes, vote_threshold: int, grid: _lib.VoxelGrid, trim: bool = True):
@@ -233,7 +242,7 @@ def voxel_fuse(xyz, rgb, votes, vote_threshold: int, grid: _lib.VoxelGrid, trim:
     assert xyz.dtype == torch.float32 and rgb.dtype == torch.uint8 and tuple(rgb.shape) == (N, 3)
     assert votes is None or (votes.dtype == torch.uint8 and votes.numel() == N)
     nbytes = C.c_int64(0)
-    _lib.check(lib.ddn_fuse_workspace_bytes(N, C.byref(nbytes)))
+    _lib.check(lib.ddn_fuse_workspace_bytes(C.byref(grid), N, C.byref(nbytes)))
     ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
     out_keys = torch.empty(N, dtype=torch.int64, device=dev)
     out_xyz = torch.empty((N, 3), dtype=torch.float32, device=dev)
@@ -248,7 +257,7 @@ def voxel_fuse(xyz, rgb, votes, vote_threshold: int, grid: _lib.VoxelGrid, trim:
             )
         )
     if trim:
-        mv = int(counts[1].item())
+        mv = checked_voxel_count(counts)
         return out_keys[:mv], out_xyz[:mv], out_rgb[:mv], out_cnt[:mv], counts
     return out_keys, out_xyz, out_rgb, out_cnt, counts
 
@@ -262,7 +271,7 @@ def voxel_fuse_partial(xyz, rgb, votes, vote_threshold: int, grid: _lib.VoxelGri
     N = xyz.shape[0]
     assert xyz.dtype == torch.float32 and rgb.dtype == torch.uint8 and tuple(rgb.shape) == (N, 3)
     nbytes = C.c_int64(0)
-    _lib.check(lib.ddn_fuse_workspace_bytes(N, C.byref(nbytes)))
+    _lib.check(lib.ddn_fuse_workspace_bytes(C.byref(grid), N, C.byref(nbytes)))
     ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
     pk = torch.empty(N, dtype=torch.int64, device=dev)
     ps = torch.empty((N, 3), dtype=torch.int64, device=dev)
@@ -287,7 +296,7 @@ def voxel_merge_partials(part_keys, part_sums, part_rgb, part_count, grid: _lib.
     assert part_keys.dtype == torch.int64 and part_sums.dtype == torch.int64 and part_rgb.dtype == torch.int32
     assert part_count.dtype == torch.int32 and tuple(part_sums.shape) == (n, 3) and tuple(part_rgb.shape) == (n, 3)
     nbytes = C.c_int64(0)
-    _lib.check(lib.ddn_fuse_workspace_bytes(max(n, 1), C.byref(nbytes)))
+    _lib.check(lib.ddn_fuse_workspace_bytes(C.byref(grid), max(n, 1), C.byref(nbytes)))
     ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
     m = max(n, 1)
     out_keys = torch.empty(m, dtype=torch.int64, device=dev)
@@ -303,7 +312,7 @@ def voxel_merge_partials(part_keys, part_sums, part_rgb, part_count, grid: _lib.
             )
         )
     if trim:
-        mv = int(counts[1].item())
+        mv = checked_voxel_count(counts)
         return out_keys[:mv], out_xyz[:mv], out_rgb[:mv], out_cnt[:mv], counts
     return out_keys, out_xyz, out_rgb, out_cnt, counts
 
@@ -317,6 +326,7 @@ def voxel_keys(xyz, voxel: float, origin) -> torch.Tensor:
     for i in range(3):
         g.origin[i] = float(np.float32(origin[i]))
         g.bits[i] = 21
+        g.dims[i] = 0
     keys = torch.empty(xyz.shape[0], dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
         _lib.check(lib.ddn_voxel_keys(C.byref(g), xyz.shape[0], _p(xyz), _p(keys), _stream()))

@@ -150,14 +150,20 @@ typedef struct {
   float voxel;
   float origin[3];
   int32_t bits[3]; /* significant bits per axis (from the bounding box); sum <= 63 */
+  int32_t dims[3]; /* cells per axis, <= 2^bits (0 => 2^bits); points outside do not participate */
 } ddn_voxel_grid;
 
-DDN_API int ddn_fuse_workspace_bytes(int64_t n_points, int64_t* bytes_out);
+/* Scratch for ddn_voxel_fuse / ddn_voxel_partials / ddn_voxel_merge on `grid_host` with up to
+ * n_points points (or records).  Grids of up to 2^35 cells use a dense occupancy bitmap
+ * (cells/8 bytes + 40 B per possible voxel); larger grids (or grid_host == NULL: worst case of the
+ * sort path) use a radix sort. */
+DDN_API int ddn_fuse_workspace_bytes(const ddn_voxel_grid* grid_host, int64_t n_points, int64_t* bytes_out);
 
 /* xyz [N,3] f32, rgb [N,3] u8, votes [N] u8 (point i participates iff votes[i] < vote_threshold;
  * votes may be NULL => all).  Outputs sized for the worst case N: out_keys [N] u64 ascending,
  * out_xyz [N,3] f32, out_rgb [N,3] u8, out_count [N] i32; counts_out [2] i64 device:
- * {number of participating points, number of voxels}. */
+ * {number of participating points, number of voxels}; the first is -1 if a voxel collected 2^24 or
+ * more points (colour sums are 32-bit). */
 DDN_API int ddn_voxel_fuse(const ddn_voxel_grid* grid_host, int64_t n_points, const float* xyz,
                    const uint8_t* rgb, const uint8_t* votes, int32_t vote_threshold,
                    uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb, int32_t* out_count,
