@@ -1,16 +1,17 @@
 // Stage 4: voxel-grid fusion (new capability; the reference only concatenates
 // points, scripts/test.py:353-359).  DENSE-RANK PATH - no sort.
 //
-// The voxel grid of a scene is small enough for one occupancy BIT per cell (cfg 2: 2400 x 2400 x 600
-// cells = 0.43 GB of bits in 180 GB of HBM).  Bit order == key order (x fastest, then y, then z), so
+// The voxel grid of a scene is small enough for one occupancy BIT per cell (cfg 2: about 2400 x 2400 x 600
+// cells = 0.6 GB of occupancy units in 180 GB of HBM).  Bit order == key order (x fastest, then y, then z), so
 // the rank of a set bit among all set bits IS the voxel's position in the key-sorted output.  That
 // replaces the radix sort of 168 M (key, index) pairs by streaming passes:
 //
-//   mark        every participating point sets the bit of its cell (RED.OR; lane-neighbour dedupe)
-//   rank        popcount scan over the bitmap: one exclusive prefix per 256-bit group (= one 32 B
-//               sector); the pass also emits the sorted keys and zeroes the accumulators it hands out
-//   accumulate  every point looks up its slot (sector + prefix, both L2-resident because consecutive
-//               pixels fall into neighbouring cells) and adds integer fixed-point sums with 64-bit
+//   mark        every participating point sets the bit of its cell (RED.OR; a cell equal to the
+//               previous point's is skipped)
+//   rank        popcount scan over the occupancy: one exclusive prefix per 96-bit unit, stored in the
+//               unit's fourth word; the pass also emits the sorted keys
+//   accumulate  every point looks up its slot (ONE 16 B load: 96 bits + prefix; L2-resident because
+//               consecutive pixels fall into neighbouring cells) and adds integer fixed-point sums with 64-bit
 //               RED.ADD.  A thread owns 8 consecutive points and merges runs of equal cells in
 //               registers first, which removes about half of the atomics.
 //   finalize    one thread per voxel: mean = centre + sum/count, colour = round-half-up
@@ -22,11 +23,14 @@
 
 namespace ddn {
 
-constexpr int kGroupBits = 256;              // rank granularity: 8 words = one 32 B sector
-constexpr int kTileGroups = 2048;            // groups per CTA in the rank passes (64 KB of bitmap)
+// Occupancy + rank live in ONE array of 16-byte units: words x, y, z = 96 occupancy bits, word w = the
+// exclusive rank prefix of the unit (written by the rank pass).  A slot lookup is a single LDG.128.
+constexpr int kUnitBits = 96;
+constexpr int kUnitsPerThread = 8;
 constexpr int kScanThreads = 256;
-constexpr int kAccWords = 5;                 // sx, sy, sz, r:g, b:count (u64 each)
-constexpr uint64_t kDenseMaxCells = 1ull << 35;  // 4 GiB of bits
+constexpr int kTileUnits = kScanThreads * kUnitsPerThread;  // units per CTA in the rank passes (32 KB)
+constexpr int kAccWords = 5;                                // sx, sy, sz, r:g, b:count (u64 each)
+constexpr uint64_t kDenseMaxCells = 1ull << 35;             // 5.7 GB of units
 constexpr uint64_t kNoCell = ~0ull;
 
 __device__ __forceinline__ uint64_t cell_of_point(const GridDev& g, float rv, float x, float y, float z, uint32_t& kx,
@@ -48,62 +52,99 @@ __device__ __forceinline__ uint64_t cell_of_key(const GridDev& g, uint64_t key) 
   return kx + (uint64_t)g.nx * (ky + (uint64_t)g.ny * kz);
 }
 
-// Set the bit of `cell`; lanes whose left neighbour holds the same cell skip the atomic.  Returns the
-// number of participating lanes of the warp (valid in every lane).
-__device__ __forceinline__ int mark_cell(uint32_t* __restrict__ bitmap, uint64_t cell) {
-  const uint64_t prev = __shfl_up_sync(0xffffffffu, cell, 1);
-  const bool valid = cell != kNoCell;
-  const bool first = (threadIdx.x & 31) == 0 || prev != cell;
-  if (valid && first) atomicOr(bitmap + (cell >> 5), 1u << (cell & 31));
-  return __popc(__ballot_sync(0xffffffffu, valid));
+__device__ __forceinline__ void set_cell_bit(uint32_t* __restrict__ units, uint64_t cell) {
+  const uint32_t w32 = (uint32_t)(cell >> 5);  // word index in a plain bitmap
+  const uint32_t unit = w32 / 3u;
+  atomicOr(units + (size_t)unit * 4 + (w32 - unit * 3u), 1u << (cell & 31));
 }
 
+constexpr int kMarkPX = 4;  // consecutive points per thread
+
+// mark: a thread owns 4 consecutive points; a cell equal to its predecessor (in the thread, or the last
+// cell of the previous lane) is not marked again.  Consecutive pixels of a depth map fall into the same
+// or neighbouring voxels, so this removes most of the atomics.
+template <bool kVec>
 __global__ void __launch_bounds__(256)
 mark_points_kernel(GridDev g, float rv, int64_t n, const float* __restrict__ xyz, const uint8_t* __restrict__ votes, int thr,
-                   uint32_t* __restrict__ bitmap, unsigned long long* __restrict__ n_in) {
+                   uint32_t* __restrict__ units, unsigned long long* __restrict__ n_in) {
   __shared__ int s_count;
   if (threadIdx.x == 0) s_count = 0;
   __syncthreads();
-  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  uint64_t cell = kNoCell;
-  if (i < n && (votes == nullptr || (int)__ldg(votes + i) < thr)) {
-    uint32_t kx, ky, kz;
-    cell = cell_of_point(g, rv, __ldg(xyz + i * 3 + 0), __ldg(xyz + i * 3 + 1), __ldg(xyz + i * 3 + 2), kx, ky, kz);
+  const int64_t base = ((int64_t)blockIdx.x * 256 + threadIdx.x) * kMarkPX;
+  uint64_t cell[kMarkPX];
+  int mine = 0;
+  bool take[kMarkPX];
+  if (kVec && base + kMarkPX <= n) {
+    uint32_t vv = 0;
+    if (votes != nullptr) vv = __ldcs(reinterpret_cast<const uint32_t*>(votes + base));
+#pragma unroll
+    for (int j = 0; j < kMarkPX; ++j) take[j] = votes == nullptr || (int)((vv >> (8 * j)) & 0xff) < thr;
+    if (take[0] | take[1] | take[2] | take[3]) {
+      const float4* x4 = reinterpret_cast<const float4*>(xyz + base * 3);
+      const float4 a = __ldcs(x4), b = __ldcs(x4 + 1), c = __ldcs(x4 + 2);
+      const float p[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+      uint32_t kx, ky, kz;
+#pragma unroll
+      for (int j = 0; j < kMarkPX; ++j)
+        cell[j] = take[j] ? cell_of_point(g, rv, p[j * 3], p[j * 3 + 1], p[j * 3 + 2], kx, ky, kz) : kNoCell;
+    } else {
+#pragma unroll
+      for (int j = 0; j < kMarkPX; ++j) cell[j] = kNoCell;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < kMarkPX; ++j) {
+      const int64_t i = base + j;
+      cell[j] = kNoCell;
+      if (i < n && (votes == nullptr || (int)__ldg(votes + i) < thr)) {
+        uint32_t kx, ky, kz;
+        cell[j] = cell_of_point(g, rv, __ldg(xyz + i * 3 + 0), __ldg(xyz + i * 3 + 1), __ldg(xyz + i * 3 + 2), kx, ky, kz);
+      }
+    }
   }
-  const int c = mark_cell(bitmap, cell);
-  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_count, c);
+  uint64_t prev = __shfl_up_sync(0xffffffffu, cell[kMarkPX - 1], 1);
+  if ((threadIdx.x & 31) == 0) prev = kNoCell;
+#pragma unroll
+  for (int j = 0; j < kMarkPX; ++j) {
+    if (cell[j] != kNoCell) {
+      ++mine;
+      if (cell[j] != prev) set_cell_bit(units, cell[j]);
+    }
+    prev = cell[j];
+  }
+  mine = __reduce_add_sync(0xffffffffu, mine);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_count, mine);
   __syncthreads();
   if (threadIdx.x == 0 && s_count) atomicAdd(n_in, (unsigned long long)s_count);
 }
 
 __global__ void __launch_bounds__(256)
-mark_records_kernel(GridDev g, int64_t n, const uint64_t* __restrict__ keys, uint32_t* __restrict__ bitmap,
+mark_records_kernel(GridDev g, int64_t n, const uint64_t* __restrict__ keys, uint32_t* __restrict__ units,
                     unsigned long long* __restrict__ n_in) {
   __shared__ int s_count;
   if (threadIdx.x == 0) s_count = 0;
   __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   const uint64_t cell = i < n ? cell_of_key(g, __ldg(keys + i)) : kNoCell;
-  const int c = mark_cell(bitmap, cell);
+  if (cell != kNoCell) set_cell_bit(units, cell);
+  const int c = __popc(__ballot_sync(0xffffffffu, cell != kNoCell));
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_count, c);
   __syncthreads();
   if (threadIdx.x == 0 && s_count) atomicAdd(n_in, (unsigned long long)s_count);
 }
 
-// ---- rank: popcount scan over the bitmap ---------------------------------------------------------
-__device__ __forceinline__ int popc8(const uint4& a, const uint4& b) {
-  return __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w);
-}
+// ---- rank: popcount scan over the units --------------------------------------------------------
+__device__ __forceinline__ int popc3(const uint4& u) { return __popc(u.x) + __popc(u.y) + __popc(u.z); }
 
 __global__ void __launch_bounds__(kScanThreads)
-tile_count_kernel(const uint4* __restrict__ bitmap4, uint32_t groups, uint32_t* __restrict__ tile_sums) {
+tile_count_kernel(const uint4* __restrict__ units, uint32_t n_units, uint32_t* __restrict__ tile_sums) {
   __shared__ int s_warp[kScanThreads / 32];
-  const uint32_t base = blockIdx.x * kTileGroups;
+  const uint32_t base = blockIdx.x * kTileUnits;
   int sum = 0;
 #pragma unroll
-  for (int j = 0; j < kTileGroups / kScanThreads; ++j) {
-    const uint32_t gi = base + j * kScanThreads + threadIdx.x;
-    if (gi < groups) sum += popc8(__ldg(bitmap4 + 2 * (size_t)gi), __ldg(bitmap4 + 2 * (size_t)gi + 1));
+  for (int j = 0; j < kUnitsPerThread; ++j) {
+    const uint32_t ui = base + j * kScanThreads + threadIdx.x;
+    if (ui < n_units) sum += popc3(__ldg(units + ui));
   }
   sum = __reduce_add_sync(0xffffffffu, sum);
   if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = sum;
@@ -154,27 +195,22 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t* __restrict__ 
   if (threadIdx.x == 0) counts_out[1] = (int64_t)s_carry;
 }
 
-// Per group: exclusive rank prefix.  Per set bit: canonical key of the cell -> keys[slot], and the
-// slot's accumulators are zeroed (so no separate memset sized by a device-side count is needed).
+// Per unit: exclusive rank prefix -> word w of the unit.  Per set bit: canonical key of the cell ->
+// keys[slot].  The cell coordinates are decoded once per non-empty unit and then stepped along x.
 __global__ void __launch_bounds__(kScanThreads)
-group_prefix_kernel(GridDev g, const uint4* __restrict__ bitmap4, uint32_t groups, const uint32_t* __restrict__ tile_excl,
-                    uint32_t* __restrict__ group_prefix, uint64_t* __restrict__ keys, unsigned long long* __restrict__ accum) {
+unit_prefix_kernel(GridDev g, uint4* __restrict__ units, uint32_t n_units, const uint32_t* __restrict__ tile_excl,
+                   uint64_t* __restrict__ keys) {
   __shared__ uint32_t s_warp[kScanThreads / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t base = blockIdx.x * kTileGroups;
+  const uint32_t base = blockIdx.x * kTileUnits;
   uint32_t carry = tile_excl[blockIdx.x];
   const uint64_t nxy = (uint64_t)g.nx * (uint64_t)g.ny;
 #pragma unroll 1
-  for (int j = 0; j < kTileGroups / kScanThreads; ++j) {
-    const uint32_t gi = base + j * kScanThreads + threadIdx.x;
-    uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (gi < groups) {
-      const uint4 a = __ldg(bitmap4 + 2 * (size_t)gi), b = __ldg(bitmap4 + 2 * (size_t)gi + 1);
-      w[0] = a.x, w[1] = a.y, w[2] = a.z, w[3] = a.w, w[4] = b.x, w[5] = b.y, w[6] = b.z, w[7] = b.w;
-    }
-    uint32_t cnt = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) cnt += __popc(w[i]);
+  for (int j = 0; j < kUnitsPerThread; ++j) {
+    const uint32_t ui = base + j * kScanThreads + threadIdx.x;
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (ui < n_units) u = __ldg(units + ui);
+    const uint32_t cnt = (uint32_t)popc3(u);
     uint32_t inc = cnt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -193,43 +229,51 @@ group_prefix_kernel(GridDev g, const uint4* __restrict__ bitmap4, uint32_t group
     __syncthreads();
     uint32_t slot = carry + before + inc - cnt;
     carry += total;
-    if (gi < groups) group_prefix[gi] = slot;
+    if (ui < n_units) units[ui].w = slot;
     if (cnt) {
+      const uint64_t cell0 = (uint64_t)ui * kUnitBits;
+      uint32_t kz = (uint32_t)(cell0 / nxy);
+      const uint64_t rem = cell0 - (uint64_t)kz * nxy;
+      uint32_t ky = (uint32_t)(rem / (uint64_t)g.nx);
+      const uint32_t kx0 = (uint32_t)(rem - (uint64_t)ky * (uint64_t)g.nx);
+      const uint32_t w[3] = {u.x, u.y, u.z};
+      uint32_t row_off = 0;  // bits of this unit that belong to earlier rows
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 3; ++i) {
         uint32_t bits = w[i];
         while (bits) {
           const int b = __ffs(bits) - 1;
           bits &= bits - 1;
-          const uint64_t cell = (uint64_t)gi * kGroupBits + i * 32 + b;
-          const uint64_t kz = cell / nxy, rem = cell - kz * nxy;
-          const uint64_t ky = rem / (uint64_t)g.nx, kx = rem - ky * (uint64_t)g.nx;
-          keys[slot] = kx | (ky << 21) | (kz << 42);
-          if (accum != nullptr) {
-            unsigned long long* a = accum + (size_t)slot * kAccWords;
-#pragma unroll
-            for (int q = 0; q < kAccWords; ++q) a[q] = 0ull;
+          uint32_t kx = kx0 + (uint32_t)(i * 32 + b) - row_off;
+          while (kx >= (uint32_t)g.nx) {  // the unit straddles a row end
+            kx -= (uint32_t)g.nx;
+            row_off += (uint32_t)g.nx;
+            if (++ky >= (uint32_t)g.ny) ky = 0, ++kz;
           }
-          ++slot;
+          keys[slot++] = (uint64_t)kx | ((uint64_t)ky << 21) | ((uint64_t)kz << 42);
         }
       }
     }
   }
 }
 
-__device__ __forceinline__ uint32_t slot_of_cell(uint64_t cell, const uint4* __restrict__ bitmap4,
-                                                 const uint32_t* __restrict__ group_prefix) {
-  const size_t gi = (size_t)(cell >> 8);
-  const int wi = (int)(cell >> 5) & 7;
+// accumulators of the counts[1] voxels -> 0 (device-side count, no host round trip)
+__global__ void __launch_bounds__(256) zero_accum_kernel(ulonglong2* __restrict__ accum2, const int64_t* __restrict__ counts) {
+  const int64_t n2 = (counts[1] * kAccWords + 1) / 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x)
+    accum2[i] = make_ulonglong2(0ull, 0ull);
+}
+
+__device__ __forceinline__ uint32_t slot_of_cell(uint64_t cell, const uint4* __restrict__ units) {
+  const uint32_t w32 = (uint32_t)(cell >> 5);
+  const uint32_t unit = w32 / 3u;
+  const int wi = (int)(w32 - unit * 3u);
   const uint32_t below = (1u << (cell & 31)) - 1u;
-  const uint4 a = __ldg(bitmap4 + 2 * gi), b = __ldg(bitmap4 + 2 * gi + 1);
-  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-  uint32_t s = __ldg(group_prefix + gi);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const uint32_t m = i < wi ? 0xffffffffu : (i == wi ? below : 0u);
-    s += __popc(w[i] & m);
-  }
+  const uint4 u = __ldg(units + unit);
+  uint32_t s = u.w;
+  s += __popc(u.x & (wi > 0 ? 0xffffffffu : below));
+  s += wi > 0 ? __popc(u.y & (wi > 1 ? 0xffffffffu : below)) : 0;
+  s += wi > 1 ? __popc(u.z & below) : 0;
   return s;
 }
 
@@ -238,10 +282,10 @@ struct RunAcc {
   uint32_t r, g, b, n;
 };
 
-__device__ __forceinline__ void flush_run(uint64_t cell, const RunAcc& acc, const uint4* __restrict__ bitmap4,
-                                          const uint32_t* __restrict__ group_prefix, unsigned long long* __restrict__ accum) {
+__device__ __forceinline__ void flush_run(uint64_t cell, const RunAcc& acc, const uint4* __restrict__ units,
+                                          unsigned long long* __restrict__ accum) {
   if (cell == kNoCell || acc.n == 0) return;
-  unsigned long long* a = accum + (size_t)slot_of_cell(cell, bitmap4, group_prefix) * kAccWords;
+  unsigned long long* a = accum + (size_t)slot_of_cell(cell, units) * kAccWords;
   atomicAdd(a + 0, (unsigned long long)acc.sx);
   atomicAdd(a + 1, (unsigned long long)acc.sy);
   atomicAdd(a + 2, (unsigned long long)acc.sz);
@@ -254,8 +298,8 @@ constexpr int kAccPX = 8;  // consecutive points per thread
 template <bool kVec>
 __global__ void __launch_bounds__(256)
 accumulate_points_kernel(GridDev g, float rv, int64_t n, const float* __restrict__ xyz, const uint8_t* __restrict__ rgb,
-                         const uint8_t* __restrict__ votes, int thr, const uint4* __restrict__ bitmap4,
-                         const uint32_t* __restrict__ group_prefix, unsigned long long* __restrict__ accum) {
+                         const uint8_t* __restrict__ votes, int thr, const uint4* __restrict__ units,
+                         unsigned long long* __restrict__ accum) {
   const int64_t base = ((int64_t)blockIdx.x * 256 + threadIdx.x) * kAccPX;
   if (base >= n) return;
   float p[kAccPX * 3];
@@ -301,7 +345,7 @@ accumulate_points_kernel(GridDev g, float rv, int64_t n, const float* __restrict
     uint32_t kx = 0, ky = 0, kz = 0;
     const uint64_t cell = take ? cell_of_point(g, rv, p[j * 3 + 0], p[j * 3 + 1], p[j * 3 + 2], kx, ky, kz) : kNoCell;
     if (cell != cur) {
-      flush_run(cur, acc, bitmap4, group_prefix, accum);
+      flush_run(cur, acc, units, accum);
       acc = {0, 0, 0, 0, 0, 0, 0};
       cur = cell;
     }
@@ -316,14 +360,13 @@ accumulate_points_kernel(GridDev g, float rv, int64_t n, const float* __restrict
       acc.n += 1;
     }
   }
-  flush_run(cur, acc, bitmap4, group_prefix, accum);
+  flush_run(cur, acc, units, accum);
 }
 
 __global__ void __launch_bounds__(256)
 accumulate_records_kernel(GridDev g, int64_t n, const uint64_t* __restrict__ keys, const long long* __restrict__ in_sums,
                           const uint32_t* __restrict__ in_rgb, const int32_t* __restrict__ in_count,
-                          const uint4* __restrict__ bitmap4, const uint32_t* __restrict__ group_prefix,
-                          unsigned long long* __restrict__ accum) {
+                          const uint4* __restrict__ units, unsigned long long* __restrict__ accum) {
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
   const uint64_t cell = cell_of_key(g, __ldg(keys + i));
@@ -331,7 +374,7 @@ accumulate_records_kernel(GridDev g, int64_t n, const uint64_t* __restrict__ key
   acc.sx = in_sums[i * 3 + 0], acc.sy = in_sums[i * 3 + 1], acc.sz = in_sums[i * 3 + 2];
   acc.r = in_rgb[i * 3 + 0], acc.g = in_rgb[i * 3 + 1], acc.b = in_rgb[i * 3 + 2];
   acc.n = (uint32_t)in_count[i];
-  flush_run(cell, acc, bitmap4, group_prefix, accum);
+  flush_run(cell, acc, units, accum);
 }
 
 // One thread per voxel.  The colour fields are 32 bits wide: a voxel with 2^24 or more points could
@@ -378,8 +421,8 @@ __global__ void canonical_key_kernel(GridDev g, int64_t n, const float* __restri
 
 // ---- host side ---------------------------------------------------------------------------------
 struct DenseLayout {
-  uint64_t cells, groups, tiles;
-  size_t bitmap, bitmap_bytes, prefix, tile_sums, accum, total;
+  uint64_t cells, n_units, tiles;
+  size_t units, units_bytes, tile_sums, accum, total;
 };
 
 static uint64_t grid_cells(const GridDev& g) { return (uint64_t)g.nx * (uint64_t)g.ny * (uint64_t)g.nz; }
@@ -387,8 +430,8 @@ static bool use_dense(const GridDev& g) { return grid_cells(g) <= kDenseMaxCells
 
 static void dense_layout(const GridDev& g, int64_t n, DenseLayout* L) {
   L->cells = grid_cells(g);
-  L->groups = (L->cells + kGroupBits - 1) / kGroupBits;
-  L->tiles = (L->groups + kTileGroups - 1) / kTileGroups;
+  L->n_units = (L->cells + kUnitBits - 1) / kUnitBits;
+  L->tiles = (L->n_units + kTileUnits - 1) / kTileUnits;
   const uint64_t max_vox = (uint64_t)n < L->cells ? (uint64_t)n : L->cells;
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -396,11 +439,10 @@ static void dense_layout(const GridDev& g, int64_t n, DenseLayout* L) {
     off += (size_t)align_up((int64_t)bytes, 256);
     return o;
   };
-  L->bitmap_bytes = (size_t)L->groups * (kGroupBits / 8);
-  L->bitmap = take(L->bitmap_bytes);
-  L->prefix = take((size_t)L->groups * 4);
+  L->units_bytes = (size_t)L->n_units * 16;
+  L->units = take(L->units_bytes);
   L->tile_sums = take((size_t)(L->tiles + 1) * 4);
-  L->accum = take((size_t)max_vox * kAccWords * 8);
+  L->accum = take((size_t)max_vox * kAccWords * 8 + 16);
   L->total = off + 256;
 }
 
@@ -427,38 +469,45 @@ static int dense_fuse(const GridDev& g, int64_t n, const DenseSource& src, uint6
     return DDN_ERR_WORKSPACE_TOO_SMALL;
   }
   char* base = reinterpret_cast<char*>(align_up((int64_t)(uintptr_t)workspace, 256));
-  uint32_t* bitmap = (uint32_t*)(base + L.bitmap);
-  const uint4* bitmap4 = (const uint4*)bitmap;
-  uint32_t* prefix = (uint32_t*)(base + L.prefix);
+  uint4* units = (uint4*)(base + L.units);
   uint32_t* tile_sums = (uint32_t*)(base + L.tile_sums);
   unsigned long long* accum = (unsigned long long*)(base + L.accum);
   const float rv = 1.0f / g.voxel;
   const unsigned blocks = (unsigned)((n + 255) / 256);
   const bool points = src.rec_keys == nullptr;
+  const bool vec = points && ((uintptr_t)src.xyz % 16 == 0) && ((uintptr_t)src.rgb % 8 == 0) &&
+                   (src.votes == nullptr || (uintptr_t)src.votes % 8 == 0);
 
-  DDN_TRY(check_cuda(cudaMemsetAsync(bitmap, 0, L.bitmap_bytes, st), "memset bitmap"));
+  DDN_TRY(check_cuda(cudaMemsetAsync(units, 0, L.units_bytes, st), "memset occupancy"));
   DDN_TRY(check_cuda(cudaMemsetAsync(counts_out, 0, 16, st), "memset counts"));
-  if (points)
-    mark_points_kernel<<<blocks, 256, 0, st>>>(g, rv, n, src.xyz, src.votes, src.thr, bitmap, (unsigned long long*)counts_out);
-  else
-    mark_records_kernel<<<blocks, 256, 0, st>>>(g, n, src.rec_keys, bitmap, (unsigned long long*)counts_out);
+  if (points) {
+    const unsigned mblocks = (unsigned)((n + 256 * kMarkPX - 1) / (256 * kMarkPX));
+    if (vec)
+      mark_points_kernel<true><<<mblocks, 256, 0, st>>>(g, rv, n, src.xyz, src.votes, src.thr, (uint32_t*)units,
+                                                        (unsigned long long*)counts_out);
+    else
+      mark_points_kernel<false><<<mblocks, 256, 0, st>>>(g, rv, n, src.xyz, src.votes, src.thr, (uint32_t*)units,
+                                                         (unsigned long long*)counts_out);
+  } else {
+    mark_records_kernel<<<blocks, 256, 0, st>>>(g, n, src.rec_keys, (uint32_t*)units, (unsigned long long*)counts_out);
+  }
   DDN_TRY(after_launch("mark_kernel"));
-  tile_count_kernel<<<(unsigned)L.tiles, kScanThreads, 0, st>>>(bitmap4, (uint32_t)L.groups, tile_sums);
+  tile_count_kernel<<<(unsigned)L.tiles, kScanThreads, 0, st>>>(units, (uint32_t)L.n_units, tile_sums);
   DDN_TRY(after_launch("tile_count_kernel"));
   tile_scan_kernel<<<1, 1024, 0, st>>>(tile_sums, (int)L.tiles, counts_out);
   DDN_TRY(after_launch("tile_scan_kernel"));
-  group_prefix_kernel<<<(unsigned)L.tiles, kScanThreads, 0, st>>>(g, bitmap4, (uint32_t)L.groups, tile_sums, prefix, out_keys, accum);
-  DDN_TRY(after_launch("group_prefix_kernel"));
+  unit_prefix_kernel<<<(unsigned)L.tiles, kScanThreads, 0, st>>>(g, units, (uint32_t)L.n_units, tile_sums, out_keys);
+  DDN_TRY(after_launch("unit_prefix_kernel"));
+  zero_accum_kernel<<<kNumSMs * 8, 256, 0, st>>>((ulonglong2*)accum, counts_out);
+  DDN_TRY(after_launch("zero_accum_kernel"));
   if (points) {
     const unsigned ablocks = (unsigned)((n + 256 * kAccPX - 1) / (256 * kAccPX));
-    const bool vec = ((uintptr_t)src.xyz % 16 == 0) && ((uintptr_t)src.rgb % 8 == 0) && (src.votes == nullptr || (uintptr_t)src.votes % 8 == 0);
     if (vec)
-      accumulate_points_kernel<true><<<ablocks, 256, 0, st>>>(g, rv, n, src.xyz, src.rgb, src.votes, src.thr, bitmap4, prefix, accum);
+      accumulate_points_kernel<true><<<ablocks, 256, 0, st>>>(g, rv, n, src.xyz, src.rgb, src.votes, src.thr, units, accum);
     else
-      accumulate_points_kernel<false><<<ablocks, 256, 0, st>>>(g, rv, n, src.xyz, src.rgb, src.votes, src.thr, bitmap4, prefix, accum);
+      accumulate_points_kernel<false><<<ablocks, 256, 0, st>>>(g, rv, n, src.xyz, src.rgb, src.votes, src.thr, units, accum);
   } else {
-    accumulate_records_kernel<<<blocks, 256, 0, st>>>(g, n, src.rec_keys, src.rec_sums, src.rec_rgb, src.rec_count, bitmap4, prefix,
-                                                      accum);
+    accumulate_records_kernel<<<blocks, 256, 0, st>>>(g, n, src.rec_keys, src.rec_sums, src.rec_rgb, src.rec_count, units, accum);
   }
   DDN_TRY(after_launch("accumulate_kernel"));
   if (part_sums != nullptr)
