@@ -10,10 +10,10 @@
 //               previous point's is skipped)
 //   rank        popcount scan over the occupancy: one exclusive prefix per 96-bit unit, stored in the
 //               unit's fourth word; the pass also emits the sorted keys
-//   accumulate  every point looks up its slot (ONE 16 B load: 96 bits + prefix; L2-resident because
-//               consecutive pixels fall into neighbouring cells) and adds integer fixed-point sums with 64-bit
-//               RED.ADD.  A thread owns 8 consecutive points and merges runs of equal cells in
-//               registers first, which removes about half of the atomics.
+//   accumulate  integer fixed-point sums per voxel with 64-bit RED.ADD.  The L2 atomic units bound this
+//               pass, so a warp first merges the points of its 8 x 4 pixel tile that share a cell
+//               (MATCH.ANY + shuffles); the group's first lane looks the slot up (ONE 16 B load:
+//               96 bits + prefix) and issues the atomics.
 //   finalize    one thread per voxel: mean = centre + sum/count, colour = round-half-up
 //
 // Integer sums make the result independent of the order of points and of how they are split over
@@ -293,74 +293,89 @@ __device__ __forceinline__ void flush_run(uint64_t cell, const RunAcc& acc, cons
   atomicAdd(a + 4, ((unsigned long long)acc.b << 32) | acc.n);
 }
 
-constexpr int kAccPX = 8;  // consecutive points per thread
+// accumulate: one point per lane, aggregated ACROSS THE WARP before touching memory.  With a row length
+// (points are pixels of [rows, row_len] images) a warp covers an 8 x 4 pixel tile, otherwise 32
+// consecutive points.  Lanes whose points fall into the same cell are found with MATCH.ANY; every lane
+// walks its peer mask with shuffles (32-bit partial sums: at most 32 points of |offset| <= 2^19), and
+// the lowest lane of each group looks the slot up and issues the five 64-bit REDs.  The L2 atomic units
+// are the bound of this pass, so points per RED group is what matters: ~3 for 8 x 4 tiles at cfg 2.
+constexpr int kAccTilesPerWarp = 8;
 
-template <bool kVec>
+template <bool kTiled>
 __global__ void __launch_bounds__(256)
-accumulate_points_kernel(GridDev g, float rv, int64_t n, const float* __restrict__ xyz, const uint8_t* __restrict__ rgb,
-                         const uint8_t* __restrict__ votes, int thr, const uint4* __restrict__ units,
-                         unsigned long long* __restrict__ accum) {
-  const int64_t base = ((int64_t)blockIdx.x * 256 + threadIdx.x) * kAccPX;
-  if (base >= n) return;
-  float p[kAccPX * 3];
-  uint8_t c[kAccPX * 3];
-  uint8_t v[kAccPX];
-  const int m = (int)min((int64_t)kAccPX, n - base);
-  if (kVec && m == kAccPX) {
-    const float4* x4 = reinterpret_cast<const float4*>(xyz + base * 3);
-#pragma unroll
-    for (int q = 0; q < kAccPX * 3 / 4; ++q) {
-      const float4 t = __ldcs(x4 + q);
-      p[q * 4 + 0] = t.x, p[q * 4 + 1] = t.y, p[q * 4 + 2] = t.z, p[q * 4 + 3] = t.w;
-    }
-    const uint2* c2 = reinterpret_cast<const uint2*>(rgb + base * 3);
-#pragma unroll
-    for (int q = 0; q < kAccPX * 3 / 8; ++q) {
-      const uint2 t = __ldcs(c2 + q);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) c[q * 8 + e] = (uint8_t)(t.x >> (8 * e)), c[q * 8 + 4 + e] = (uint8_t)(t.y >> (8 * e));
-    }
-    if (votes != nullptr) {
-      const uint2 t = __ldcs(reinterpret_cast<const uint2*>(votes + base));
-#pragma unroll
-      for (int e = 0; e < 4; ++e) v[e] = (uint8_t)(t.x >> (8 * e)), v[4 + e] = (uint8_t)(t.y >> (8 * e));
-    }
+accumulate_points_kernel(GridDev g, float rv, int64_t n, int row_len, const float* __restrict__ xyz,
+                         const uint8_t* __restrict__ rgb, const uint8_t* __restrict__ votes, int thr,
+                         const uint4* __restrict__ units, unsigned long long* __restrict__ accum) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  int64_t tiles_x = 0, n_tiles;
+  if (kTiled) {
+    tiles_x = (row_len + 7) / 8;
+    const int64_t n_rows = (n + row_len - 1) / row_len;
+    n_tiles = tiles_x * ((n_rows + 3) / 4);
   } else {
-#pragma unroll
-    for (int j = 0; j < kAccPX; ++j) {
-      const bool in = j < m;
-#pragma unroll
-      for (int e = 0; e < 3; ++e) {
-        p[j * 3 + e] = in ? __ldg(xyz + (base + j) * 3 + e) : 0.f;
-        c[j * 3 + e] = in ? __ldg(rgb + (base + j) * 3 + e) : (uint8_t)0;
+    n_tiles = (n + 31) / 32;
+  }
+  const int dx = lane & 7, dy = lane >> 3;
+#pragma unroll 1
+  for (int q = 0; q < kAccTilesPerWarp; ++q) {
+    const int64_t t = warp * kAccTilesPerWarp + q;
+    if (t >= n_tiles) break;  // warp-uniform
+    int64_t i;
+    bool in;
+    if (kTiled) {
+      const int64_t ty = t / tiles_x;
+      const int x = (int)(t - ty * tiles_x) * 8 + dx;
+      i = (ty * 4 + dy) * (int64_t)row_len + x;
+      in = x < row_len && i < n;
+    } else {
+      i = t * 32 + lane;
+      in = i < n;
+    }
+    const bool take = in && (votes == nullptr || (int)__ldg(votes + i) < thr);
+    uint64_t cell = kNoCell;
+    int ox = 0, oy = 0, oz = 0;
+    uint32_t rg = 0, bb = 0;
+    if (take) {
+      const float x = __ldg(xyz + i * 3 + 0), y = __ldg(xyz + i * 3 + 1), z = __ldg(xyz + i * 3 + 2);
+      uint32_t kx, ky, kz;
+      cell = cell_of_point(g, rv, x, y, z, kx, ky, kz);
+      if (cell != kNoCell) {
+        // p - centre is exact in float32 for points inside the voxel
+        ox = (int)voxel_offset_fix(x, voxel_centre(g.ox, kx, g.voxel), g.voxel);
+        oy = (int)voxel_offset_fix(y, voxel_centre(g.oy, ky, g.voxel), g.voxel);
+        oz = (int)voxel_offset_fix(z, voxel_centre(g.oz, kz, g.voxel), g.voxel);
+        rg = ((uint32_t)__ldg(rgb + i * 3 + 0) << 16) | (uint32_t)__ldg(rgb + i * 3 + 1);
+        bb = (uint32_t)__ldg(rgb + i * 3 + 2);
       }
-      v[j] = (in && votes != nullptr) ? __ldg(votes + base + j) : (uint8_t)0;
+    }
+    const bool valid = cell != kNoCell;
+    uint32_t peers = __match_any_sync(0xffffffffu, cell);
+    if (!valid) peers = 0;
+    const bool leader = valid && (__ffs(peers) - 1) == lane;
+    const int iters = __reduce_max_sync(0xffffffffu, __popc(peers));
+    int sx = 0, sy = 0, sz = 0;
+    uint32_t srg = 0, sb = 0;
+    uint32_t rest = peers;
+#pragma unroll 1
+    for (int k = 0; k < iters; ++k) {
+      const bool has = rest != 0;
+      const int src = has ? __ffs(rest) - 1 : lane;
+      rest &= rest - 1;
+      const int ax = __shfl_sync(0xffffffffu, ox, src), ay = __shfl_sync(0xffffffffu, oy, src);
+      const int az = __shfl_sync(0xffffffffu, oz, src);
+      const uint32_t arg = __shfl_sync(0xffffffffu, rg, src), ab = __shfl_sync(0xffffffffu, bb, src);
+      if (has) sx += ax, sy += ay, sz += az, srg += arg, sb += ab;
+    }
+    if (leader) {
+      unsigned long long* a = accum + (size_t)slot_of_cell(cell, units) * kAccWords;
+      atomicAdd(a + 0, (unsigned long long)(long long)sx);
+      atomicAdd(a + 1, (unsigned long long)(long long)sy);
+      atomicAdd(a + 2, (unsigned long long)(long long)sz);
+      atomicAdd(a + 3, ((unsigned long long)(srg >> 16) << 32) | (srg & 0xffffu));
+      atomicAdd(a + 4, ((unsigned long long)sb << 32) | (unsigned)__popc(peers));
     }
   }
-  uint64_t cur = kNoCell;
-  RunAcc acc = {0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-  for (int j = 0; j < kAccPX; ++j) {
-    const bool take = j < m && (votes == nullptr || (int)v[j] < thr);
-    uint32_t kx = 0, ky = 0, kz = 0;
-    const uint64_t cell = take ? cell_of_point(g, rv, p[j * 3 + 0], p[j * 3 + 1], p[j * 3 + 2], kx, ky, kz) : kNoCell;
-    if (cell != cur) {
-      flush_run(cur, acc, units, accum);
-      acc = {0, 0, 0, 0, 0, 0, 0};
-      cur = cell;
-    }
-    if (cell != kNoCell) {
-      // p - centre is exact in float32 for points inside the voxel
-      acc.sx += voxel_offset_fix(p[j * 3 + 0], voxel_centre(g.ox, kx, g.voxel), g.voxel);
-      acc.sy += voxel_offset_fix(p[j * 3 + 1], voxel_centre(g.oy, ky, g.voxel), g.voxel);
-      acc.sz += voxel_offset_fix(p[j * 3 + 2], voxel_centre(g.oz, kz, g.voxel), g.voxel);
-      acc.r += c[j * 3 + 0];
-      acc.g += c[j * 3 + 1];
-      acc.b += c[j * 3 + 2];
-      acc.n += 1;
-    }
-  }
-  flush_run(cur, acc, units, accum);
 }
 
 __global__ void __launch_bounds__(256)
@@ -452,6 +467,7 @@ struct DenseSource {
   const uint8_t* rgb = nullptr;
   const uint8_t* votes = nullptr;
   int thr = 0;
+  int64_t row_len = 0;
   // records
   const uint64_t* rec_keys = nullptr;
   const long long* rec_sums = nullptr;
@@ -475,8 +491,7 @@ static int dense_fuse(const GridDev& g, int64_t n, const DenseSource& src, uint6
   const float rv = 1.0f / g.voxel;
   const unsigned blocks = (unsigned)((n + 255) / 256);
   const bool points = src.rec_keys == nullptr;
-  const bool vec = points && ((uintptr_t)src.xyz % 16 == 0) && ((uintptr_t)src.rgb % 8 == 0) &&
-                   (src.votes == nullptr || (uintptr_t)src.votes % 8 == 0);
+  const bool vec = points && ((uintptr_t)src.xyz % 16 == 0) && (src.votes == nullptr || (uintptr_t)src.votes % 4 == 0);
 
   DDN_TRY(check_cuda(cudaMemsetAsync(units, 0, L.units_bytes, st), "memset occupancy"));
   DDN_TRY(check_cuda(cudaMemsetAsync(counts_out, 0, 16, st), "memset counts"));
@@ -501,11 +516,13 @@ static int dense_fuse(const GridDev& g, int64_t n, const DenseSource& src, uint6
   zero_accum_kernel<<<kNumSMs * 8, 256, 0, st>>>((ulonglong2*)accum, counts_out);
   DDN_TRY(after_launch("zero_accum_kernel"));
   if (points) {
-    const unsigned ablocks = (unsigned)((n + 256 * kAccPX - 1) / (256 * kAccPX));
-    if (vec)
-      accumulate_points_kernel<true><<<ablocks, 256, 0, st>>>(g, rv, n, src.xyz, src.rgb, src.votes, src.thr, units, accum);
+    const bool tiled = src.row_len >= 8 && src.row_len < (1 << 30);
+    const int64_t n_tiles = tiled ? ((src.row_len + 7) / 8) * (((n + src.row_len - 1) / src.row_len + 3) / 4) : (n + 31) / 32;
+    const unsigned ablocks = (unsigned)((n_tiles + 8 * kAccTilesPerWarp - 1) / (8 * kAccTilesPerWarp));
+    if (tiled)
+      accumulate_points_kernel<true><<<ablocks, 256, 0, st>>>(g, rv, n, (int)src.row_len, src.xyz, src.rgb, src.votes, src.thr, units, accum);
     else
-      accumulate_points_kernel<false><<<ablocks, 256, 0, st>>>(g, rv, n, src.xyz, src.rgb, src.votes, src.thr, units, accum);
+      accumulate_points_kernel<false><<<ablocks, 256, 0, st>>>(g, rv, n, 0, src.xyz, src.rgb, src.votes, src.thr, units, accum);
   } else {
     accumulate_records_kernel<<<blocks, 256, 0, st>>>(g, n, src.rec_keys, src.rec_sums, src.rec_rgb, src.rec_count, units, accum);
   }
@@ -539,7 +556,7 @@ int ddn_fuse_workspace_bytes(const ddn_voxel_grid* grid_host, int64_t n_points, 
   return sort_fuse_workspace_bytes(n, bytes_out);
 }
 
-int ddn_voxel_fuse(const ddn_voxel_grid* grid_host, int64_t n_points, const float* xyz, const uint8_t* rgb,
+int ddn_voxel_fuse(const ddn_voxel_grid* grid_host, int64_t n_points, int64_t row_len, const float* xyz, const uint8_t* rgb,
                    const uint8_t* votes, int32_t vote_threshold, uint64_t* out_keys, float* out_xyz,
                    uint8_t* out_rgb, int32_t* out_count, int64_t* counts_out, void* workspace,
                    int64_t workspace_bytes, void* stream) {
@@ -547,6 +564,7 @@ int ddn_voxel_fuse(const ddn_voxel_grid* grid_host, int64_t n_points, const floa
   GridDev g;
   DDN_TRY(grid_from_host(grid_host, &g));
   DDN_REQUIRE(n_points >= 0 && n_points < (1ll << 31) - 1024, "n_points");
+  DDN_REQUIRE(row_len >= 0, "row_len");
   DDN_REQUIRE(counts_out != nullptr, "null counts_out");
   cudaStream_t st = (cudaStream_t)stream;
   if (n_points == 0) return check_cuda(cudaMemsetAsync(counts_out, 0, 16, st), "memset counts");
@@ -555,12 +573,12 @@ int ddn_voxel_fuse(const ddn_voxel_grid* grid_host, int64_t n_points, const floa
     return sort_fuse_points(g, n_points, xyz, rgb, votes, vote_threshold, out_keys, out_xyz, out_rgb, out_count, counts_out,
                             workspace, workspace_bytes, st, nullptr, nullptr);
   DenseSource src;
-  src.xyz = xyz, src.rgb = rgb, src.votes = votes, src.thr = vote_threshold;
+  src.xyz = xyz, src.rgb = rgb, src.votes = votes, src.thr = vote_threshold, src.row_len = row_len;
   return dense_fuse(g, n_points, src, out_keys, out_xyz, out_rgb, out_count, nullptr, nullptr, counts_out, workspace,
                     workspace_bytes, st);
 }
 
-int ddn_voxel_partials(const ddn_voxel_grid* grid_host, int64_t n_points, const float* xyz, const uint8_t* rgb,
+int ddn_voxel_partials(const ddn_voxel_grid* grid_host, int64_t n_points, int64_t row_len, const float* xyz, const uint8_t* rgb,
                        const uint8_t* votes, int32_t vote_threshold, uint64_t* part_keys, int64_t* part_sums,
                        uint32_t* part_rgb, int32_t* part_count, int64_t* counts_out, void* workspace,
                        int64_t workspace_bytes, void* stream) {
@@ -568,6 +586,7 @@ int ddn_voxel_partials(const ddn_voxel_grid* grid_host, int64_t n_points, const 
   GridDev g;
   DDN_TRY(grid_from_host(grid_host, &g));
   DDN_REQUIRE(n_points >= 0 && n_points < (1ll << 31) - 1024, "n_points");
+  DDN_REQUIRE(row_len >= 0, "row_len");
   DDN_REQUIRE(counts_out != nullptr, "null counts_out");
   cudaStream_t st = (cudaStream_t)stream;
   if (n_points == 0) return check_cuda(cudaMemsetAsync(counts_out, 0, 16, st), "memset counts");
@@ -576,7 +595,7 @@ int ddn_voxel_partials(const ddn_voxel_grid* grid_host, int64_t n_points, const 
     return sort_fuse_points(g, n_points, xyz, rgb, votes, vote_threshold, part_keys, nullptr, nullptr, part_count, counts_out,
                             workspace, workspace_bytes, st, (long long*)part_sums, part_rgb);
   DenseSource src;
-  src.xyz = xyz, src.rgb = rgb, src.votes = votes, src.thr = vote_threshold;
+  src.xyz = xyz, src.rgb = rgb, src.votes = votes, src.thr = vote_threshold, src.row_len = row_len;
   return dense_fuse(g, n_points, src, part_keys, nullptr, nullptr, part_count, (long long*)part_sums, part_rgb, counts_out,
                     workspace, workspace_bytes, st);
 }

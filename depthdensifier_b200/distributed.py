@@ -201,7 +201,7 @@ class ShardedDensifier:
         rgb_s = rgb if s == 1 else rgb[:, ::s, ::s].contiguous()
         if self.world == 1:
             k, x, c, n, counts = mark("voxel_fuse", lambda: self.ops.voxel_fuse(
-                xyz.view(-1, 3), rgb_s.view(-1, 3), votes.view(-1), self.thr, grid, trim=False))
+                xyz.view(-1, 3), rgb_s.view(-1, 3), votes.view(-1), self.thr, grid, trim=False, row_len=xyz.shape[2]))
         else:
             k, x, c, n, counts = mark("voxel_fuse", lambda: self._fuse_sharded(xyz, rgb_s, votes, grid))
         res.grid, res.voxel_keys, res.voxel_xyz, res.voxel_rgb, res.voxel_count, res.counts = grid, k, x, c, n, counts
@@ -217,7 +217,7 @@ class ShardedDensifier:
     def _fuse_sharded(self, xyz, rgb, votes, grid):
         import torch.distributed as dist
 
-        pk, psum, prgb, pcnt, counts = self.ops.voxel_fuse_partial(xyz.view(-1, 3), rgb.view(-1, 3), votes.view(-1), self.thr, grid)
+        pk, psum, prgb, pcnt, counts = self.ops.voxel_fuse_partial(xyz.view(-1, 3), rgb.view(-1, 3), votes.view(-1), self.thr, grid, row_len=xyz.shape[2])
         mv = int(counts[1].item())
         pk, psum, prgb, pcnt = pk[:mv], psum[:mv], prgb[:mv], pcnt[:mv]
         R = self.world

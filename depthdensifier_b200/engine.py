@@ -90,6 +90,6 @@ class DensifyEngine:
                 grid = ops.make_grid(bb[:3], bb[3:], cfg.voxel)
             s = cfg.filter.stride
             rgb_s = rgb if s == 1 else rgb[:, ::s, ::s].contiguous()
-            k, x, c, n, counts = ops.voxel_fuse(xyz.view(-1, 3), rgb_s.view(-1, 3), votes.view(-1), thr, grid)
+            k, x, c, n, counts = ops.voxel_fuse(xyz.view(-1, 3), rgb_s.view(-1, 3), votes.view(-1), thr, grid, row_len=xyz.shape[2])
             res.grid, res.voxel_keys, res.voxel_xyz, res.voxel_rgb, res.voxel_count, res.counts = grid, k, x, c, n, counts
         return res

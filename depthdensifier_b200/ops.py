@@ -232,10 +232,11 @@ def checked_voxel_count(counts: torch.Tensor) -> int:
     return mv
 
 
-def voxel_fuse(xyz, rgb, votes, vote_threshold: int, grid: _lib.VoxelGrid, trim: bool = True):
+def voxel_fuse(xyz, rgb, votes, vote_threshold: int, grid: _lib.VoxelGrid, trim: bool = True, row_len: int = 0):
     """Stage 4.  xyz [N,3] f32, rgb [N,3] u8, votes [N] u8 or None.  Returns keys, xyz, rgb, count
     (trimmed to the voxel count when ``trim``; that reads the counts back and synchronises) and the
-    device counts tensor [2] = (participating points, voxels)."""
+    device counts tensor [2] = (participating points, voxels).  ``row_len``: image width when the points
+    are the pixels of row-major depth maps (locality hint only)."""
     lib = _lib.load()
     dev = _require_cuda(xyz, rgb, votes)
     N = xyz.shape[0]
@@ -252,7 +253,7 @@ def voxel_fuse(xyz, rgb, votes, vote_threshold: int, grid: _lib.VoxelGrid, trim:
     with torch.cuda.device(dev):
         _lib.check(
             lib.ddn_voxel_fuse(
-                C.byref(grid), N, _p(xyz), _p(rgb), _p(votes), int(vote_threshold), _p(out_keys), _p(out_xyz),
+                C.byref(grid), N, int(row_len), _p(xyz), _p(rgb), _p(votes), int(vote_threshold), _p(out_keys), _p(out_xyz),
                 _p(out_rgb), _p(out_cnt), _p(counts), _p(ws), nbytes.value, _stream(),
             )
         )
@@ -262,7 +263,7 @@ def voxel_fuse(xyz, rgb, votes, vote_threshold: int, grid: _lib.VoxelGrid, trim:
     return out_keys, out_xyz, out_rgb, out_cnt, counts
 
 
-def voxel_fuse_partial(xyz, rgb, votes, vote_threshold: int, grid: _lib.VoxelGrid):
+def voxel_fuse_partial(xyz, rgb, votes, vote_threshold: int, grid: _lib.VoxelGrid, row_len: int = 0):
     """Rank-local stage 4: per-voxel partial sums (keys ascending).  Returns part_keys [N] i64,
     part_sums [N,3] i64, part_rgb [N,3] i32 (uint32 bits), part_count [N] i32 (all sized for the worst
     case N) and the device counts [2] = (participating points, local voxels)."""
@@ -281,7 +282,7 @@ def voxel_fuse_partial(xyz, rgb, votes, vote_threshold: int, grid: _lib.VoxelGri
     with torch.cuda.device(dev):
         _lib.check(
             lib.ddn_voxel_partials(
-                C.byref(grid), N, _p(xyz), _p(rgb), _p(votes), int(vote_threshold), _p(pk), _p(ps), _p(pr), _p(pc),
+                C.byref(grid), N, int(row_len), _p(xyz), _p(rgb), _p(votes), int(vote_threshold), _p(pk), _p(ps), _p(pr), _p(pc),
                 _p(counts), _p(ws), nbytes.value, _stream(),
             )
         )

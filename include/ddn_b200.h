@@ -160,11 +160,12 @@ typedef struct {
 DDN_API int ddn_fuse_workspace_bytes(const ddn_voxel_grid* grid_host, int64_t n_points, int64_t* bytes_out);
 
 /* xyz [N,3] f32, rgb [N,3] u8, votes [N] u8 (point i participates iff votes[i] < vote_threshold;
- * votes may be NULL => all).  Outputs sized for the worst case N: out_keys [N] u64 ascending,
+ * votes may be NULL => all).  row_len: 0, or the image width when the points are the pixels of
+ * [rows, row_len] depth maps in row-major order (a locality hint: the result does not depend on it).  Outputs sized for the worst case N: out_keys [N] u64 ascending,
  * out_xyz [N,3] f32, out_rgb [N,3] u8, out_count [N] i32; counts_out [2] i64 device:
  * {number of participating points, number of voxels}; the first is -1 if a voxel collected 2^24 or
  * more points (colour sums are 32-bit). */
-DDN_API int ddn_voxel_fuse(const ddn_voxel_grid* grid_host, int64_t n_points, const float* xyz,
+DDN_API int ddn_voxel_fuse(const ddn_voxel_grid* grid_host, int64_t n_points, int64_t row_len, const float* xyz,
                    const uint8_t* rgb, const uint8_t* votes, int32_t vote_threshold,
                    uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb, int32_t* out_count,
                    int64_t* counts_out, void* workspace, int64_t workspace_bytes, void* stream);
@@ -174,7 +175,7 @@ DDN_API int ddn_voxel_fuse(const ddn_voxel_grid* grid_host, int64_t n_points, co
  * part_rgb [N,3] u32 colour sums, part_count [N] i32.  Integer sums make the final means independent
  * of how points are split over ranks.  ddn_voxel_merge adds the records of equal key (any input
  * order, e.g. the concatenation of the sorted runs received from R ranks) and finalises them. */
-DDN_API int ddn_voxel_partials(const ddn_voxel_grid* grid_host, int64_t n_points, const float* xyz,
+DDN_API int ddn_voxel_partials(const ddn_voxel_grid* grid_host, int64_t n_points, int64_t row_len, const float* xyz,
                        const uint8_t* rgb, const uint8_t* votes, int32_t vote_threshold,
                        uint64_t* part_keys, int64_t* part_sums, uint32_t* part_rgb, int32_t* part_count,
                        int64_t* counts_out, void* workspace, int64_t workspace_bytes, void* stream);

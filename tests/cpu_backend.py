@@ -151,7 +151,7 @@ class OracleBackend:
         sel = sel & inside
         return x[sel], c[sel], voxel, origin
 
-    def voxel_fuse_partial(self, xyz, rgb, votes, thr, grid):
+    def voxel_fuse_partial(self, xyz, rgb, votes, thr, grid, row_len=0):
         x, c, voxel, origin = self._select(xyz, rgb, votes, thr, grid)
         uk, sums, csum, cnt = partial_sums_numpy(x, c, voxel, origin)
         counts = torch.tensor([len(x), len(uk)], dtype=torch.int64)
@@ -165,7 +165,7 @@ class OracleBackend:
         counts = torch.tensor([len(pk), len(uk)], dtype=torch.int64)
         return torch.from_numpy(uk.astype(np.int64)), torch.from_numpy(xyz), torch.from_numpy(col), torch.from_numpy(n), counts
 
-    def voxel_fuse(self, xyz, rgb, votes, thr, grid, trim=True):
+    def voxel_fuse(self, xyz, rgb, votes, thr, grid, trim=True, row_len=0):
         pk, ps, pr, pc, counts = self.voxel_fuse_partial(xyz, rgb, votes, thr, grid)
         k, x, c, n, _ = self.voxel_merge_partials(pk, ps, pr, pc, grid)
         return k, x, c, n, counts

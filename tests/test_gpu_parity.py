@@ -208,10 +208,12 @@ def test_depth_refiner_dropin(lib_built, golden_dir):
     assert res3["num_correspondences"] == 0 and res3["refined_depth"] is d_in
 
 
-@pytest.mark.parametrize("n,voxel,spread", [(20000, 0.05, 1.0), (200000, 0.01, 3.0), (1, 0.01, 1.0), (5000, 0.001, 40.0)])
-def test_voxel_fuse_vs_oracle(lib_built, n, voxel, spread):
-    """N4: keys and counts bit-exact, positions within 1e-5 relative, colours exact (the last case
-    needs > 31 key bits and takes the 64-bit sort path)."""
+@pytest.mark.parametrize("n,voxel,spread,row_len", [(20000, 0.05, 1.0, 0), (200000, 0.01, 3.0, 37), (1, 0.01, 1.0, 8),
+                                                    (5000, 0.001, 40.0, 0), (70001, 0.2, 2.0, 512), (33333, 0.02, 0.3, 33333)])
+def test_voxel_fuse_vs_oracle(lib_built, n, voxel, spread, row_len):
+    """N4: keys and counts bit-exact, positions within 1e-5 relative, colours exact.  The 0.001 / 40 case
+    has a grid of more than 2^35 cells and takes the sort path, the others the dense-rank path; row_len
+    (the image-width locality hint) must not change the result."""
     from depthdensifier_b200 import ops
 
     rng = np.random.default_rng(n)
@@ -228,7 +230,7 @@ def test_voxel_fuse_vs_oracle(lib_built, n, voxel, spread):
     k_ref, m_ref, c_ref, n_ref = R.voxel_fuse(xyz[sel], rgb[sel], voxel, origin)
     grid = ops.make_grid(xyz[sel].min(0), xyz[sel].max(0), voxel)
     assert np.array_equal(np.array(list(grid.origin), np.float32), origin)
-    k, m, c, cnt, counts = ops.voxel_fuse(_cuda(xyz), _cuda(rgb), _cuda(votes), thr, grid)
+    k, m, c, cnt, counts = ops.voxel_fuse(_cuda(xyz), _cuda(rgb), _cuda(votes), thr, grid, row_len=row_len)
     assert counts.cpu().tolist() == [int(sel.sum()), len(k_ref)]
     assert np.array_equal(k.cpu().numpy().view(np.uint64), k_ref)
     assert np.array_equal(cnt.cpu().numpy(), n_ref)
