@@ -7,7 +7,8 @@
 //          sorted by x (:148-150) or, in affine mode, the five-sum least squares in float64.
 //   K3     remap_median_kernel  fused per-pixel piecewise-linear remap (:157-176), 3x3 replicate
 //          median (:194-200) and mask (:203): depth+mask are read once, refined written once
-//          (9 B/pixel instead of the reference's 9x unfold blow-up).
+//          (9 B/pixel instead of the reference's 9x unfold blow-up).  The per-pixel searchsorted runs
+//          through a 1024-bucket index of the table built by K2, the median through sorted row triples.
 #include "common.cuh"
 
 namespace ddn {
@@ -22,8 +23,22 @@ struct AlignWorkspace {
   float* tx;     // [V,C] table x (sorted)
   float* ty;     // [V,C] table y
   unsigned long long* sortbuf;  // [V,Cp]
+  uint32_t* bucket;             // [V,kBuckets] search acceleration of the table: start | end << 16
   int64_t C, Cp;
 };
+
+// Uniform buckets over the table's x range.  bucket_of() is monotone non-decreasing in d (float
+// subtract, multiply by a positive constant and truncation all are), so every knot in a lower bucket
+// than d's is < d and every knot in a higher bucket is > d: searchsorted_left(xs, d) lies inside the
+// knot range of d's own bucket, exactly.
+constexpr int kBuckets = 1024;
+__device__ __forceinline__ float bucket_scale(float xmin, float xmax) {
+  const float w = __fadd_rn(xmax, -xmin);
+  return w > 0.f ? __fdiv_rn((float)kBuckets, w) : 0.f;
+}
+__device__ __forceinline__ int bucket_of(float d, float xmin, float scale) {
+  return min(max(__float2int_rz(__fmul_rn(__fadd_rn(d, -xmin), scale)), 0), kBuckets - 1);
+}
 
 static int64_t next_pow2(int64_t x) {
   int64_t p = 1;
@@ -33,7 +48,7 @@ static int64_t next_pow2(int64_t x) {
 
 static int64_t align_ws_bytes(int64_t V, int64_t C) {
   const int64_t Cp = next_pow2(C > 1 ? C : 2);
-  return align_up(V * C * 4, 256) * 5 + align_up(V * Cp * 8, 256) + 256;
+  return align_up(V * C * 4, 256) * 5 + align_up(V * Cp * 8, 256) + align_up(V * 1024 * 4, 256) + 256;
 }
 
 static AlignWorkspace carve(void* ws, int64_t V, int64_t C) {
@@ -47,7 +62,8 @@ static AlignWorkspace carve(void* ws, int64_t V, int64_t C) {
   w.ratio = (float*)p; p += fb;
   w.tx = (float*)p; p += fb;
   w.ty = (float*)p; p += fb;
-  w.sortbuf = (unsigned long long*)p;
+  w.sortbuf = (unsigned long long*)p; p += align_up(V * w.Cp * 8, 256);
+  w.bucket = (uint32_t*)p;
   return w;
 }
 
@@ -375,33 +391,49 @@ align_stats_kernel(ddn_align_config cfg, int H, int W, const float* __restrict__
     st.num_table = n3;
     stats[v] = st;
   }
+  if (n3 <= 0xffff) {  // bucket b -> [first knot with bucket >= b, first knot with bucket >= b + 1)
+    __syncthreads();
+    const float xmin = tx[0], scale = bucket_scale(xmin, tx[n3 - 1]);
+    for (int b = tid; b < kBuckets; b += kStatsThreads) {
+      int lo2[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        int lo_ = 0, len = n3;
+        while (len > 0) {
+          const int half = len >> 1;
+          const bool less = bucket_of(tx[lo_ + half], xmin, scale) < b + e;
+          lo_ = less ? lo_ + half + 1 : lo_;
+          len = less ? len - half - 1 : half;
+        }
+        lo2[e] = lo_;
+      }
+      ws.bucket[(size_t)v * kBuckets + b] = (uint32_t)lo2[0] | ((uint32_t)lo2[1] << 16);
+    }
+  }
 }
 
 // ---- K3 ---------------------------------------------------------------------------------------------
-constexpr int kTileW = 64, kTileH = 32, kRemapThreads = 256;
+// One CTA = a 128 x 32 pixel tile (+1 replicate halo) of one view.  Phase 1 remaps tile + halo into
+// shared memory (lookup table and its bucket index also in shared memory); phase 2 takes the 3x3 median
+// with a sliding window down each column: the three values of a row are sorted once and reused by the
+// three windows that contain them (median9 = med3(max of the minima, med3 of the middles, min of the
+// maxima)), 3 LDS and ~20 min/max per pixel instead of 9 LDS and 38.
+constexpr int kTileW = 128, kTileH = 32, kRemapThreads = 256;
 constexpr int kHaloW = kTileW + 2, kHaloH = kTileH + 2;
 constexpr int kLutSmemMax = 4096;  // knots kept in shared memory (32 KB); larger tables read global
 
-__device__ __forceinline__ void cswap(float& a, float& b) {
-  const float lo = fminf(a, b), hi = fmaxf(a, b);
-  a = lo;
-  b = hi;
-}
-// median of 9 (19 compare-exchanges), i.e. the 5th smallest as torch.median(dim) over 9 returns
-__device__ __forceinline__ float median9(float p0, float p1, float p2, float p3, float p4, float p5, float p6,
-                                         float p7, float p8) {
-  cswap(p1, p2); cswap(p4, p5); cswap(p7, p8);
-  cswap(p0, p1); cswap(p3, p4); cswap(p6, p7);
-  cswap(p1, p2); cswap(p4, p5); cswap(p7, p8);
-  cswap(p0, p3); cswap(p5, p8); cswap(p4, p7);
-  cswap(p3, p6); cswap(p1, p4); cswap(p2, p5);
-  cswap(p4, p7); cswap(p4, p2); cswap(p6, p4);
-  cswap(p4, p2);
-  return p4;
+__device__ __forceinline__ float med3(float a, float b, float c) { return fmaxf(fminf(a, b), fminf(fmaxf(a, b), c)); }
+
+__device__ __forceinline__ float pwl_interp(float d, float x0, float x1, float y0, float y1) {
+  float dx = __fadd_rn(x1, -x0);
+  dx = dx == 0.f ? 1e-6f : dx;
+  float t = __fdiv_rn(__fadd_rn(d, -x0), dx);
+  t = fminf(fmaxf(t, 0.f), 1.f);
+  return fmaxf(__fadd_rn(y0, __fmul_rn(t, __fadd_rn(y1, -y0))), 1e-3f);
 }
 
+// i = clamp(searchsorted_left(xs, d), 1, n-1)  (depth_refiner.py:157-158), binary search
 __device__ __forceinline__ float pwl_eval(float d, const float* __restrict__ xs, const float* __restrict__ ys, int n) {
-  // i = clamp(searchsorted_left(xs, d), 1, n-1)  (depth_refiner.py:157-158)
   int lo = 0, len = n;
   while (len > 0) {
     const int half = len >> 1;
@@ -410,19 +442,25 @@ __device__ __forceinline__ float pwl_eval(float d, const float* __restrict__ xs,
     len = less ? len - half - 1 : half;
   }
   const int i = min(max(lo, 1), n - 1);
-  const float x0 = xs[i - 1], x1 = xs[i], y0 = ys[i - 1], y1 = ys[i];
-  float dx = __fadd_rn(x1, -x0);
-  dx = dx == 0.f ? 1e-6f : dx;
-  float t = __fdiv_rn(__fadd_rn(d, -x0), dx);
-  t = fminf(fmaxf(t, 0.f), 1.f);
-  return fmaxf(__fadd_rn(y0, __fmul_rn(t, __fadd_rn(y1, -y0))), 1e-3f);
+  return pwl_interp(d, xs[i - 1], xs[i], ys[i - 1], ys[i]);
+}
+
+// same result through the bucket index: a short linear scan inside d's bucket
+__device__ __forceinline__ float pwl_eval_bucketed(float d, const float* __restrict__ xs, const float* __restrict__ ys,
+                                                   int n, const uint32_t* __restrict__ bucket, float xmin, float scale) {
+  const uint32_t se = bucket[bucket_of(d, xmin, scale)];
+  int i = (int)(se & 0xffffu);
+  const int end = (int)(se >> 16);
+  while (i < end && xs[i] < d) ++i;
+  i = min(max(i, 1), n - 1);
+  return pwl_interp(d, xs[i - 1], xs[i], ys[i - 1], ys[i]);
 }
 
 __global__ void __launch_bounds__(kRemapThreads)
 remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y, const float* __restrict__ depth,
                     const uint8_t* __restrict__ mask, const ddn_view_stats* __restrict__ stats, AlignWorkspace ws,
                     float* __restrict__ refined, int lut_cap) {
-  extern __shared__ __align__(16) float s_dyn[];  // LUT xs | ys (when it fits)
+  extern __shared__ __align__(16) float s_dyn[];  // LUT xs | ys | bucket index (when the table fits)
   __shared__ float s_val[kHaloH][kHaloW];
   __shared__ uint8_t s_msk[kHaloH][kHaloW + 2];
 
@@ -454,20 +492,28 @@ remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y
   const int n = st.num_table;
   const float* xs = ws.tx + (size_t)v * ws.C;
   const float* ys = ws.ty + (size_t)v * ws.C;
-  if (cfg.mode == 0 && n <= lut_cap) {
+  const bool bucketed = cfg.mode == 0 && n >= 2 && n <= lut_cap;
+  const uint32_t* bkt = nullptr;
+  float xmin = 0.f, bscale = 0.f;
+  if (bucketed) {
     float* sx = s_dyn;
-    float* sy = s_dyn + n;
+    float* sy = s_dyn + lut_cap;
+    uint32_t* sb = reinterpret_cast<uint32_t*>(s_dyn + 2 * lut_cap);
     for (int i = tid; i < n; i += kRemapThreads) {
       sx[i] = xs[i];
       sy[i] = ys[i];
     }
+    for (int i = tid; i < kBuckets; i += kRemapThreads) sb[i] = ws.bucket[(size_t)v * kBuckets + i];
+    xmin = xs[0];
+    bscale = bucket_scale(xmin, xs[n - 1]);
     xs = sx;
     ys = sy;
+    bkt = sb;
     __syncthreads();
   }
   const float a_s = st.affine_scale, a_t = st.affine_shift;
 
-  // remap tile + 1-pixel replicate halo into shared memory
+  // phase 1: remap tile + 1-pixel replicate halo into shared memory
   for (int i = tid; i < kHaloW * kHaloH; i += kRemapThreads) {
     const int hy = i / kHaloW, hx = i - hy * kHaloW;
     const int y = min(max(ty0 + hy - 1, 0), H - 1), x = min(max(tx0 + hx - 1, 0), W - 1);
@@ -476,33 +522,47 @@ remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y
     const bool mk = mmap ? (__ldg(mmap + g) != 0) : (d > 0.f);
     float val = 0.f;
     if (mk) {
-      if (cfg.mode == 0) {
-        val = (n >= 2) ? pwl_eval(d, xs, ys, n) : __fmul_rn(d, __fdiv_rn(ys[0], __fadd_rn(xs[0], 1e-6f)));
-      } else {
-        val = fmaxf(__fadd_rn(__fmul_rn(d, a_s), a_t), 1e-3f);
-      }
+      if (bucketed) val = pwl_eval_bucketed(d, xs, ys, n, bkt, xmin, bscale);
+      else if (cfg.mode == 0) val = (n >= 2) ? pwl_eval(d, xs, ys, n) : __fmul_rn(d, __fdiv_rn(ys[0], __fadd_rn(xs[0], 1e-6f)));
+      else val = fmaxf(__fadd_rn(__fmul_rn(d, a_s), a_t), 1e-3f);
     }
     s_val[hy][hx] = val;
     s_msk[hy][hx] = mk ? 1 : 0;
   }
   __syncthreads();
 
+  // phase 2: column lx, rows [ly0, ly0 + 16)
   const int lx = tid & (kTileW - 1);
   const int x = tx0 + lx;
   if (x >= W) return;
-#pragma unroll
-  for (int r = 0; r < kTileH / (kRemapThreads / kTileW); ++r) {
-    const int ly = (tid / kTileW) + r * (kRemapThreads / kTileW);
-    const int y = ty0 + ly;
-    if (y >= H) break;
-    float o;
-    if (cfg.skip_smoothing) {
-      o = s_val[ly + 1][lx + 1];
-    } else {
-      o = median9(s_val[ly][lx], s_val[ly][lx + 1], s_val[ly][lx + 2], s_val[ly + 1][lx], s_val[ly + 1][lx + 1],
-                  s_val[ly + 1][lx + 2], s_val[ly + 2][lx], s_val[ly + 2][lx + 1], s_val[ly + 2][lx + 2]);
+  constexpr int kRowsPerThread = kTileH / (kRemapThreads / kTileW);
+  const int ly0 = (tid / kTileW) * kRowsPerThread;
+  if (cfg.skip_smoothing) {
+#pragma unroll 4
+    for (int r = 0; r < kRowsPerThread; ++r) {
+      const int y = ty0 + ly0 + r;
+      if (y >= H) break;
+      out[(size_t)y * W + x] = s_msk[ly0 + r + 1][lx + 1] ? s_val[ly0 + r + 1][lx + 1] : 0.f;
     }
-    out[(size_t)y * W + x] = s_msk[ly + 1][lx + 1] ? o : 0.f;
+    return;
+  }
+  float lo[3], mi[3], hi[3];
+  auto load_row = [&](int hy, int slot) {
+    float a = s_val[hy][lx], b = s_val[hy][lx + 1], c = s_val[hy][lx + 2];
+    const float ab_lo = fminf(a, b), ab_hi = fmaxf(a, b);
+    lo[slot] = fminf(ab_lo, c);
+    hi[slot] = fmaxf(ab_hi, c);
+    mi[slot] = fmaxf(ab_lo, fminf(ab_hi, c));
+  };
+  load_row(ly0, 0);
+  load_row(ly0 + 1, 1);
+#pragma unroll
+  for (int r = 0; r < kRowsPerThread; ++r) {
+    const int y = ty0 + ly0 + r;
+    if (y >= H) break;
+    load_row(ly0 + r + 2, (r + 2) % 3);
+    const float o = med3(fmaxf(fmaxf(lo[0], lo[1]), lo[2]), med3(mi[0], mi[1], mi[2]), fminf(fminf(hi[0], hi[1]), hi[2]));
+    out[(size_t)y * W + x] = s_msk[ly0 + r + 1][lx + 1] ? o : 0.f;
   }
 }
 
@@ -552,7 +612,7 @@ int ddn_align_views(const ddn_align_config* cfg, int64_t n_views, int64_t height
   // largest table any view can have: max_pairs when subsampling, else every surviving pair
   int64_t lut = (cfg->adaptive_correspondences && cfg->max_pairs < C) ? cfg->max_pairs : C;
   if (cfg->mode != 0 || lut > kLutSmemMax) lut = 0;  // affine mode has no table; huge tables stay in global
-  const size_t smem_lut = (size_t)lut * 8;
+  const size_t smem_lut = lut > 0 ? (size_t)lut * 8 + (size_t)kBuckets * 4 : 0;
   DDN_TRY(check_cuda(cudaFuncSetAttribute(remap_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lut),
                      "cudaFuncSetAttribute(remap_median)"));
   dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)n_views);

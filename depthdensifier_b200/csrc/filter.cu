@@ -7,9 +7,11 @@
 // HBM-bound design (no dense contraction anywhere on this path, so no tensor cores):
 //   * one CTA owns 256*PX consecutive pixels of ONE source view, so the K neighbour tables are
 //     CTA-uniform and live in shared memory;
-//   * normals in / xyz out are AoS float3: they move through a shared staging buffer as float4
-//     vectors (fully coalesced 16 B per lane) and are read/written per pixel with stride-3 LDS/STS
-//     (conflict free);
+//   * xyz out is AoS float3: it moves through a shared staging buffer as float4 vectors (fully
+//     coalesced 16 B per lane) and is written per pixel with stride-3 STS (conflict free); the
+//     normal map is only read for vote candidates (rare), not streamed;
+//   * pixel groups without any point (sky, masked regions - contiguous in practice) are skipped per
+//     warp;
 //   * neighbour depth gathers go through the read-only path; consecutive lanes hit consecutive
 //     pixels of the neighbour map, and CTAs are scheduled view by view so the K neighbour maps of
 //     the views in flight stay L2 resident;
@@ -28,7 +30,8 @@ constexpr int kFilterChunk = kFilterThreads * kFilterPX;
 
 // ------------------------------------------------------------------------------------------------
 // Table set-up (float64, one thread per (source view, neighbour))
-// pair_table[s][k][24]: rows 0..2 of M = R_t R_s^T Kinv_s with t_ts appended (12 floats),
+// pair_table[s][k][24]: rows 0..2 of K_t [M | t_ts], M = R_t R_s^T Kinv_s (12 floats) - i.e. the pixel
+//   (x, y) at depth d maps to (U, V, Z) = rows * (d x, d y, d, 1) and lands at u = U/Z, v = V/Z;
 //   camera centre of t (3), target view index (int bits), fx_t fy_t cx_t cy_t, own-view flag, pad.
 // src_table[s][16]: rows of R_s^T Kinv_s with c_s appended (12 floats), cx_s, cy_s, pad.
 // ------------------------------------------------------------------------------------------------
@@ -81,13 +84,20 @@ __global__ void build_pair_tables_kernel(int n_total, int src_begin, int n_src, 
     for (int j = 0; j < 3; ++j) Rt[i][j] = Pt[i * 4 + j];
     tt[i] = Pt[i * 4 + 3];
   }
+  double rows[3][4];
   for (int i = 0; i < 3; ++i) {
     double r[3];  // row i of R_t R_s^T
     for (int j = 0; j < 3; ++j) r[j] = Rt[i][0] * Rs[j][0] + Rt[i][1] * Rs[j][1] + Rt[i][2] * Rs[j][2];
-    o[i * 4 + 0] = (float)(r[0] / fx);
-    o[i * 4 + 1] = (float)(r[1] / fy);
-    o[i * 4 + 2] = (float)(-r[0] * cx / fx - r[1] * cy / fy + r[2]);
-    o[i * 4 + 3] = (float)(tt[i] - (r[0] * ts[0] + r[1] * ts[1] + r[2] * ts[2]));
+    rows[i][0] = r[0] / fx;
+    rows[i][1] = r[1] / fy;
+    rows[i][2] = -r[0] * cx / fx - r[1] * cy / fy + r[2];
+    rows[i][3] = tt[i] - (r[0] * ts[0] + r[1] * ts[1] + r[2] * ts[2]);
+  }
+  const double fxt = intr[t * 4 + 0], fyt = intr[t * 4 + 1], cxt = intr[t * 4 + 2], cyt = intr[t * 4 + 3];
+  for (int j = 0; j < 4; ++j) {
+    o[0 * 4 + j] = (float)(fxt * rows[0][j] + cxt * rows[2][j]);
+    o[1 * 4 + j] = (float)(fyt * rows[1][j] + cyt * rows[2][j]);
+    o[2 * 4 + j] = (float)rows[2][j];
   }
   for (int i = 0; i < 3; ++i)  // c_t = -R_t^T t_t
     o[12 + i] = (float)(-(Rt[0][i] * tt[0] + Rt[1][i] * tt[1] + Rt[2][i] * tt[2]));
@@ -171,19 +181,18 @@ __device__ __forceinline__ void stage_floats(float* smem, float* gptr, int n) {
 }
 
 // One (pixel, neighbour) evaluation up to the depth lookup: returns the candidate flag ("would vote if
-// the grazing gate passes") and leaves the target-frame point in X, Y, Z.
+// the grazing gate passes").
 template <bool kBilinear, bool kTwoSided>
-__device__ __forceinline__ bool pair_candidate(const float4& r0, const float4& r1, const float4& r2, const float4& kk,
-                                               float P, float Q, float d, const float* __restrict__ depth_all,
-                                               unsigned map_off, unsigned W, int H, unsigned wbits, unsigned hbits,
-                                               unsigned idx_bias, float thr, float tau, float& X, float& Y,
-                                               float& Z) {
-  X = fmaf(r0.x, P, fmaf(r0.y, Q, fmaf(r0.z, d, r0.w)));
-  Y = fmaf(r1.x, P, fmaf(r1.y, Q, fmaf(r1.z, d, r1.w)));
-  Z = fmaf(r2.x, P, fmaf(r2.y, Q, fmaf(r2.z, d, r2.w)));
+__device__ __forceinline__ bool pair_candidate(const float4& r0, const float4& r1, const float4& r2, float P, float Q,
+                                               float d, const float* __restrict__ depth_all, unsigned map_off,
+                                               unsigned W, int H, unsigned wbits, unsigned hbits, unsigned idx_bias,
+                                               float thr, float tau) {
+  const float U = fmaf(r0.x, P, fmaf(r0.y, Q, fmaf(r0.z, d, r0.w)));
+  const float V = fmaf(r1.x, P, fmaf(r1.y, Q, fmaf(r1.z, d, r1.w)));
+  const float Z = fmaf(r2.x, P, fmaf(r2.y, Q, fmaf(r2.z, d, r2.w)));
   const float inv = rcp_approx(Z);
-  const float u = fmaf(kk.x, X * inv, kk.z);
-  const float v = fmaf(kk.y, Y * inv, kk.w);
+  const float u = U * inv;
+  const float v = V * inv;
   // 0 <= u < W and 0 <= v < H on the raw bits (negative floats and NaN compare as huge unsigned);
   // invalid pixels carry NaN depth, so Z > 0 rejects them too.
   const bool inb = (__float_as_uint(u) < wbits) & (__float_as_uint(v) < hbits) & (Z > 0.f);
@@ -214,13 +223,34 @@ __device__ __forceinline__ bool pair_candidate(const float4& r0, const float4& r
   return inb & (Z < __fmul_rn(thr, D));
 }
 
+// Normal of one source pixel for the grazing gate (scripts/test.py:291), read on demand: only vote
+// candidates need it, and they are rare (floaters), so the 12 B/pixel normal map is not streamed.
+// normals_in_world rotates it by R_s^T (rows recovered from the source table).
+__device__ __forceinline__ void load_normal(const float* __restrict__ normal_view, size_t pixel, bool in_world,
+                                            const float* __restrict__ s_src, float& n0, float& n1, float& n2) {
+  const float* np_ = normal_view + pixel * 3;
+  n0 = __ldg(np_ + 0);
+  n1 = __ldg(np_ + 1);
+  n2 = __ldg(np_ + 2);
+  if (in_world) {
+    const float fx = s_src[14], fy = s_src[15], cx = s_src[12], cy = s_src[13];
+    float w[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const float ra = s_src[i * 4 + 0] * fx, rb = s_src[i * 4 + 1] * fy;
+      const float rc = s_src[i * 4 + 2] + s_src[i * 4 + 0] * cx + s_src[i * 4 + 1] * cy;
+      w[i] = ra * n0 + rb * n1 + rc * n2;
+    }
+    n0 = w[0], n1 = w[1], n2 = w[2];
+  }
+}
+
 template <bool kBilinear, bool kStride1, bool kTwoSided>
 __global__ void __launch_bounds__(kFilterThreads, kBilinear ? 3 : DDN_K4_MINBLOCKS) backproject_filter_kernel(const FilterParams p) {
   extern __shared__ __align__(16) float smem[];
-  float* s_nrm = smem;                            // kFilterChunk*3 floats: normals (staged in)
-  float* s_xyz = smem + kFilterChunk * 3;         // kFilterChunk*3 floats: world xyz (staged out)
-  float* s_src = s_xyz + kFilterChunk * 3;        // 16 floats
-  float* s_pair = s_src + 16;                     // K*24 floats
+  float* s_xyz = smem;                      // kFilterChunk*3 floats: world xyz (staged out)
+  float* s_src = s_xyz + kFilterChunk * 3;  // 16 floats
+  float* s_pair = s_src + 16;               // K*24 floats
   __shared__ int s_bbox[6];
 
   const int tid = threadIdx.x;
@@ -231,117 +261,129 @@ __global__ void __launch_bounds__(kFilterThreads, kBilinear ? 3 : DDN_K4_MINBLOC
   const int n_here = min(kFilterChunk, Ps - chunk0);
   const size_t HW = (size_t)p.H * p.W;
   const float* __restrict__ depth_s = p.refined_all + (size_t)s * HW;
+  const float* __restrict__ normal_s = p.normal + (size_t)sl * HW * 3;
 
   for (int i = tid; i < p.K * DDN_PAIR_TABLE_FLOATS; i += kFilterThreads)
     s_pair[i] = __ldg(p.pair_table + (size_t)sl * p.K * DDN_PAIR_TABLE_FLOATS + i);
   if (tid < 16) s_src[tid] = __ldg(p.src_table + (size_t)sl * 16 + tid);
   if (tid < 6) s_bbox[tid] = tid < 3 ? 0x7fffffff : (int)0x80000000;
-  if (kStride1) {
-    stage_floats<true>(s_nrm, const_cast<float*>(p.normal) + ((size_t)sl * HW + chunk0) * 3, n_here * 3);
-  } else {
-    for (int l = tid; l < n_here; l += kFilterThreads) {
-      const int pix = chunk0 + l;
-      const int ys = pix / p.Ws, xs = pix - ys * p.Ws;
-      const float* np_ = p.normal + ((size_t)sl * HW + (size_t)ys * p.stride * p.W + xs * p.stride) * 3;
-      s_nrm[l * 3 + 0] = __ldg(np_ + 0);
-      s_nrm[l * 3 + 1] = __ldg(np_ + 1);
-      s_nrm[l * 3 + 2] = __ldg(np_ + 2);
-    }
-  }
-  __syncthreads();
 
   // Per-pixel state kept in registers: depth d (NaN = no point), P = d*x, Q = d*y, vote count.
   float d[kFilterPX], P[kFilterPX], Q[kFilterPX];
   int nvotes[kFilterPX];
+  unsigned src_pix[kFilterPX];  // element index of the pixel in its own full-resolution map
   const float qnan = __int_as_float(0x7fc00000);
 
   // (row, column) of the thread's first pixel: one integer division per thread, then +256 steps
   int ys_run = (chunk0 + tid) / p.Ws;
   int xs_run = (chunk0 + tid) - ys_run * p.Ws;
+  float dd[kFilterPX];
+  {
+    int px[kFilterPX], py[kFilterPX];
 #pragma unroll
-  for (int j = 0; j < kFilterPX; ++j) {
-    const int l = j * kFilterThreads + tid;
-    const int pix = chunk0 + l;
-    const bool in = l < n_here;
-    const int x = kStride1 ? xs_run : xs_run * p.stride;
-    const int y = kStride1 ? ys_run : ys_run * p.stride;
-    float dd = 0.f;
-    if (in) dd = __ldg(depth_s + (kStride1 ? (size_t)pix : (size_t)y * p.W + x));
-    xs_run += kFilterThreads;
-    while (xs_run >= p.Ws) {
-      xs_run -= p.Ws;
-      ++ys_run;
-    }
-    const bool valid = in && dd > 0.f;
-    const float dv = valid ? dd : 0.f;
-    const float Pv = dv * (float)x, Qv = dv * (float)y;
-    // world position (scripts/test.py:79-90 then :233), fp32 with float64-precomputed rows
-    const float X = fmaf(s_src[0], Pv, fmaf(s_src[1], Qv, fmaf(s_src[2], dv, s_src[3])));
-    const float Y = fmaf(s_src[4], Pv, fmaf(s_src[5], Qv, fmaf(s_src[6], dv, s_src[7])));
-    const float Z = fmaf(s_src[8], Pv, fmaf(s_src[9], Qv, fmaf(s_src[10], dv, s_src[11])));
-    if (in) {
-      s_xyz[l * 3 + 0] = valid ? X : 0.f;
-      s_xyz[l * 3 + 1] = valid ? Y : 0.f;
-      s_xyz[l * 3 + 2] = valid ? Z : 0.f;
-      if (p.normals_in_world) {
-        // n_w = R_s^T n_c; recover the rows of R_s^T from the source table
-        const float fx = s_src[14], fy = s_src[15], cx = s_src[12], cy = s_src[13];
-        const float n0 = s_nrm[l * 3 + 0], n1 = s_nrm[l * 3 + 1], n2 = s_nrm[l * 3 + 2];
-        float w[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          const float ra = s_src[i * 4 + 0] * fx, rb = s_src[i * 4 + 1] * fy;
-          const float rc = s_src[i * 4 + 2] + s_src[i * 4 + 0] * cx + s_src[i * 4 + 1] * cy;
-          w[i] = ra * n0 + rb * n1 + rc * n2;
-        }
-        s_nrm[l * 3 + 0] = w[0];
-        s_nrm[l * 3 + 1] = w[1];
-        s_nrm[l * 3 + 2] = w[2];
+    for (int j = 0; j < kFilterPX; ++j) {
+      const int l = j * kFilterThreads + tid;
+      px[j] = kStride1 ? xs_run : xs_run * p.stride;
+      py[j] = kStride1 ? ys_run : ys_run * p.stride;
+      src_pix[j] = kStride1 ? (unsigned)(chunk0 + l) : (unsigned)py[j] * (unsigned)p.W + (unsigned)px[j];
+      dd[j] = l < n_here ? __ldg(depth_s + src_pix[j]) : 0.f;
+      xs_run += kFilterThreads;
+      while (xs_run >= p.Ws) {
+        xs_run -= p.Ws;
+        ++ys_run;
       }
     }
-    d[j] = valid ? dd : qnan;
-    P[j] = d[j] * (float)x;
-    Q[j] = d[j] * (float)y;
-    nvotes[j] = 0;
+    __syncthreads();  // tables visible
+#pragma unroll
+    for (int j = 0; j < kFilterPX; ++j) {
+      const int l = j * kFilterThreads + tid;
+      const bool valid = dd[j] > 0.f;
+      const float dv = valid ? dd[j] : 0.f;
+      const float Pv = dv * (float)px[j], Qv = dv * (float)py[j];
+      // world position (scripts/test.py:79-90 then :233), fp32 with float64-precomputed rows
+      const float X = fmaf(s_src[0], Pv, fmaf(s_src[1], Qv, fmaf(s_src[2], dv, s_src[3])));
+      const float Y = fmaf(s_src[4], Pv, fmaf(s_src[5], Qv, fmaf(s_src[6], dv, s_src[7])));
+      const float Z = fmaf(s_src[8], Pv, fmaf(s_src[9], Qv, fmaf(s_src[10], dv, s_src[11])));
+      if (l < n_here) {
+        s_xyz[l * 3 + 0] = valid ? X : 0.f;
+        s_xyz[l * 3 + 1] = valid ? Y : 0.f;
+        s_xyz[l * 3 + 2] = valid ? Z : 0.f;
+      }
+      d[j] = valid ? dd[j] : qnan;
+      P[j] = d[j] * (float)px[j];
+      Q[j] = d[j] * (float)py[j];
+      nvotes[j] = 0;
+    }
+  }
+  // warp-uniform flags: pixel group j of this warp has at least one point (sky / masked regions are
+  // contiguous, so whole groups drop out of the pair loop)
+  bool live[kFilterPX];
+  bool any_live = false;
+#pragma unroll
+  for (int j = 0; j < kFilterPX; ++j) {
+    live[j] = __any_sync(0xffffffffu, d[j] > 0.f);
+    any_live |= live[j];
   }
 
   const unsigned wbits = __float_as_uint((float)p.W), hbits = __float_as_uint((float)p.H);
   const unsigned idx_bias = (unsigned)kTruncBias * (unsigned)(p.W + 1);
   const float thr = p.depth_threshold, gcos = p.grazing_cos, tau = p.two_sided_tau;
+  const bool in_world = p.normals_in_world != 0;
   bool any_own = false;
 
-  for (int k = 0; k < p.K; ++k) {
-    const float4* t4 = reinterpret_cast<const float4*>(s_pair + k * DDN_PAIR_TABLE_FLOATS);
-    const int t = __float_as_int(t4[3].w);
-    if (t < 0) continue;
-    if (t4[5].x != 0.f) {  // own view: handled after the main loop
-      any_own = true;
-      continue;
-    }
-    const float4 r0 = t4[0], r1 = t4[1], r2 = t4[2], kk = t4[4];
-    const unsigned map_off = (unsigned)t * (unsigned)HW;
-    float X[kFilterPX], Y[kFilterPX], Z[kFilterPX];
-    bool cand[kFilterPX];
-    bool any = false;
+  // Hot loop: branch-free candidate test for every (pixel, neighbour); the four gathers of a thread
+  // issue back to back.  Candidates ("would vote if the grazing gate passes") are only recorded as a
+  // bit per neighbour; the gate itself (scripts/test.py:284-295) needs the pixel's normal and is
+  // resolved after each block of 32 neighbours, once per pixel that has a candidate at all.
+  if (any_live) {
+    const bool all_live = live[0] & live[1] & live[2] & live[3];
+    for (int k0 = 0; k0 < p.K; k0 += 32) {
+      const int k1 = min(k0 + 32, p.K);
+      unsigned cm[kFilterPX];
 #pragma unroll
-    for (int j = 0; j < kFilterPX; ++j) {
-      cand[j] = pair_candidate<kBilinear, kTwoSided>(r0, r1, r2, kk, P[j], Q[j], d[j], p.refined_all, map_off,
-                                                     (unsigned)p.W, p.H, wbits, hbits, idx_bias, thr, tau, X[j], Y[j],
-                                                     Z[j]);
-      any |= cand[j];
-    }
-    // Candidates are rare (floaters): evaluate the grazing gate (scripts/test.py:284-295) only in warps
-    // that have one.  dot(n, -(Xw - c_t)/|Xw - c_t|) > cos with |Xw - c_t| = |X_t|.
-    if (__any_sync(0xffffffffu, any)) {
-      const float4 cc = t4[3];
+      for (int j = 0; j < kFilterPX; ++j) cm[j] = 0u;
+      for (int k = k0; k < k1; ++k) {
+        const float4* t4 = reinterpret_cast<const float4*>(s_pair + k * DDN_PAIR_TABLE_FLOATS);
+        const int t = __float_as_int(t4[3].w);
+        if (t < 0) continue;
+        if (t4[5].x != 0.f) {  // own view: handled after the main loop
+          any_own = true;
+          continue;
+        }
+        const float4 r0 = t4[0], r1 = t4[1], r2 = t4[2];
+        const unsigned map_off = (unsigned)t * (unsigned)HW;
+        const unsigned bit = 1u << (k - k0);
+        if (all_live) {
+#pragma unroll
+          for (int j = 0; j < kFilterPX; ++j)
+            cm[j] |= pair_candidate<kBilinear, kTwoSided>(r0, r1, r2, P[j], Q[j], d[j], p.refined_all, map_off, (unsigned)p.W,
+                                                          p.H, wbits, hbits, idx_bias, thr, tau) ? bit : 0u;
+        } else {
+#pragma unroll
+          for (int j = 0; j < kFilterPX; ++j)
+            if (live[j])
+              cm[j] |= pair_candidate<kBilinear, kTwoSided>(r0, r1, r2, P[j], Q[j], d[j], p.refined_all, map_off,
+                                                            (unsigned)p.W, p.H, wbits, hbits, idx_bias, thr, tau) ? bit : 0u;
+        }
+      }
+      // dot(n, -(Xw - c_t)/|Xw - c_t|) > cos  <=>  dot(n, c_t - Xw) > cos * |c_t - Xw|
 #pragma unroll
       for (int j = 0; j < kFilterPX; ++j) {
-        if (cand[j]) {
+        if (cm[j]) {
           const int l = j * kFilterThreads + tid;
-          const float n0 = s_nrm[l * 3 + 0], n1 = s_nrm[l * 3 + 1], n2 = s_nrm[l * 3 + 2];
-          const float dn = fmaf(n0, cc.x - s_xyz[l * 3 + 0], fmaf(n1, cc.y - s_xyz[l * 3 + 1], n2 * (cc.z - s_xyz[l * 3 + 2])));
-          const float len = sqrt_approx(fmaf(X[j], X[j], fmaf(Y[j], Y[j], Z[j] * Z[j])));
-          nvotes[j] += (dn > gcos * len) ? 1 : 0;
+          float n0, n1, n2;
+          load_normal(normal_s, src_pix[j], in_world, s_src, n0, n1, n2);
+          const float wx = s_xyz[l * 3 + 0], wy = s_xyz[l * 3 + 1], wz = s_xyz[l * 3 + 2];
+          unsigned m = cm[j];
+          while (m) {
+            const int k = k0 + __ffs(m) - 1;
+            m &= m - 1;
+            const float4 cc = reinterpret_cast<const float4*>(s_pair + k * DDN_PAIR_TABLE_FLOATS)[3];
+            const float ex = cc.x - wx, ey = cc.y - wy, ez = cc.z - wz;
+            const float dn = fmaf(n0, ex, fmaf(n1, ey, n2 * ez));
+            const float len = sqrt_approx(fmaf(ex, ex, fmaf(ey, ey, ez * ez)));
+            nvotes[j] += (dn > gcos * len) ? 1 : 0;
+          }
         }
       }
     }
@@ -361,16 +403,18 @@ __global__ void __launch_bounds__(kFilterThreads, kBilinear ? 3 : DDN_K4_MINBLOC
       for (int j = 0; j < kFilterPX; ++j) {
         const int l = j * kFilterThreads + tid;
         if (l < n_here && d[j] > 0.f) {
-          const int pix = chunk0 + l;
-          const int ys = pix / p.Ws, xs = pix - ys * p.Ws;
-          const int ux = max(xs * p.stride - 1, 0), vy = max(ys * p.stride - 1, 0);
+          const int py = (int)(src_pix[j] / (unsigned)p.W), px = (int)(src_pix[j] - (unsigned)py * (unsigned)p.W);
+          const int ux = max(px - 1, 0), vy = max(py - 1, 0);
           const float D = __ldg(depth_s + (size_t)vy * p.W + ux);
-          const float n0 = s_nrm[l * 3 + 0], n1 = s_nrm[l * 3 + 1], n2 = s_nrm[l * 3 + 2];
-          const float ex = cc.x - s_xyz[l * 3 + 0], ey = cc.y - s_xyz[l * 3 + 1], ez = cc.z - s_xyz[l * 3 + 2];
-          const float dn = fmaf(n0, ex, fmaf(n1, ey, n2 * ez));
-          const float len = sqrt_approx(fmaf(ex, ex, fmaf(ey, ey, ez * ez)));
           const bool bad = kTwoSided ? (fabsf(d[j] - D) > tau * D) : (d[j] < __fmul_rn(thr, D));
-          nvotes[j] += (D > 0.f && bad && dn > gcos * len) ? 1 : 0;
+          if (D > 0.f && bad) {
+            float n0, n1, n2;
+            load_normal(normal_s, src_pix[j], in_world, s_src, n0, n1, n2);
+            const float ex = cc.x - s_xyz[l * 3 + 0], ey = cc.y - s_xyz[l * 3 + 1], ez = cc.z - s_xyz[l * 3 + 2];
+            const float dn = fmaf(n0, ex, fmaf(n1, ey, n2 * ez));
+            const float len = sqrt_approx(fmaf(ex, ex, fmaf(ey, ey, ez * ez)));
+            nvotes[j] += (dn > gcos * len) ? 1 : 0;
+          }
         }
       }
     }
@@ -393,7 +437,7 @@ __global__ void __launch_bounds__(kFilterThreads, kBilinear ? 3 : DDN_K4_MINBLOC
       }
     }
   }
-  if (p.bbox != nullptr) {
+  if (p.bbox != nullptr && any_live) {
     // warp reduction with REDUX on the order-preserving int encoding, then one shared atomic per warp
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -491,7 +535,7 @@ int ddn_backproject_filter(const ddn_filter_config* cfg, int64_t n_views_total, 
   const int Ps = p.Hs * p.Ws;
   dim3 grid((Ps + kFilterChunk - 1) / kFilterChunk, (unsigned)n_src);
   DDN_REQUIRE(n_src <= 65535, "too many source views per call");
-  const size_t smem = (size_t)(kFilterChunk * 6 + 16 + p.K * DDN_PAIR_TABLE_FLOATS) * sizeof(float);
+  const size_t smem = (size_t)(kFilterChunk * 3 + 16 + p.K * DDN_PAIR_TABLE_FLOATS) * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
   const bool bil = cfg->sample_mode == 1;
   const bool s1 = cfg->stride == 1;

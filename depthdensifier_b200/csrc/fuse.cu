@@ -307,29 +307,36 @@ accumulate_points_kernel(GridDev g, float rv, int64_t n, int row_len, const floa
                          const uint8_t* __restrict__ rgb, const uint8_t* __restrict__ votes, int thr,
                          const uint4* __restrict__ units, unsigned long long* __restrict__ accum) {
   const int lane = threadIdx.x & 31;
-  const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  int64_t tiles_x = 0, n_tiles;
+  const float fix_scale = voxel_fix_scale(g.voxel);
+  // n < 2^31, so tile indices fit 32 bits
+  const uint32_t warp = blockIdx.x * 8u + (threadIdx.x >> 5);
+  uint32_t tiles_x = 0, n_tiles;
   if (kTiled) {
-    tiles_x = (row_len + 7) / 8;
-    const int64_t n_rows = (n + row_len - 1) / row_len;
-    n_tiles = tiles_x * ((n_rows + 3) / 4);
+    tiles_x = ((uint32_t)row_len + 7u) / 8u;
+    const uint32_t n_rows = (uint32_t)((n + row_len - 1) / row_len);
+    n_tiles = tiles_x * ((n_rows + 3u) / 4u);
   } else {
-    n_tiles = (n + 31) / 32;
+    n_tiles = (uint32_t)((n + 31) / 32);
   }
   const int dx = lane & 7, dy = lane >> 3;
+  uint32_t ty = 0, tx = 0;
+  if (kTiled) {
+    ty = (warp * kAccTilesPerWarp) / tiles_x;
+    tx = (warp * kAccTilesPerWarp) - ty * tiles_x;
+  }
 #pragma unroll 1
   for (int q = 0; q < kAccTilesPerWarp; ++q) {
-    const int64_t t = warp * kAccTilesPerWarp + q;
+    const uint32_t t = warp * kAccTilesPerWarp + q;
     if (t >= n_tiles) break;  // warp-uniform
     int64_t i;
     bool in;
     if (kTiled) {
-      const int64_t ty = t / tiles_x;
-      const int x = (int)(t - ty * tiles_x) * 8 + dx;
-      i = (ty * 4 + dy) * (int64_t)row_len + x;
+      const int x = (int)tx * 8 + dx;
+      i = (int64_t)(ty * 4u + dy) * row_len + x;
       in = x < row_len && i < n;
+      if (++tx == tiles_x) tx = 0, ++ty;
     } else {
-      i = t * 32 + lane;
+      i = (int64_t)t * 32 + lane;
       in = i < n;
     }
     const bool take = in && (votes == nullptr || (int)__ldg(votes + i) < thr);
@@ -342,9 +349,9 @@ accumulate_points_kernel(GridDev g, float rv, int64_t n, int row_len, const floa
       cell = cell_of_point(g, rv, x, y, z, kx, ky, kz);
       if (cell != kNoCell) {
         // p - centre is exact in float32 for points inside the voxel
-        ox = (int)voxel_offset_fix(x, voxel_centre(g.ox, kx, g.voxel), g.voxel);
-        oy = (int)voxel_offset_fix(y, voxel_centre(g.oy, ky, g.voxel), g.voxel);
-        oz = (int)voxel_offset_fix(z, voxel_centre(g.oz, kz, g.voxel), g.voxel);
+        ox = voxel_offset_fix(x, voxel_centre(g.ox, kx, g.voxel), fix_scale);
+        oy = voxel_offset_fix(y, voxel_centre(g.oy, ky, g.voxel), fix_scale);
+        oz = voxel_offset_fix(z, voxel_centre(g.oz, kz, g.voxel), fix_scale);
         rg = ((uint32_t)__ldg(rgb + i * 3 + 0) << 16) | (uint32_t)__ldg(rgb + i * 3 + 1);
         bb = (uint32_t)__ldg(rgb + i * 3 + 2);
       }

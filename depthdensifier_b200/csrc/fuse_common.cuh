@@ -52,9 +52,12 @@ __device__ __forceinline__ float voxel_centre(float o, uint32_t k, float voxel) 
   return __fadd_rn(o, __fmul_rn((float)k + 0.5f, voxel));
 }
 
-// (p - voxel centre) / voxel * 2^20, rounded to nearest: the integer a point adds to its voxel's sum
-__device__ __forceinline__ long long voxel_offset_fix(float p, float centre, float voxel) {
-  return __float2ll_rn(__fmul_rn(__fdiv_rn(__fsub_rn(p, centre), voxel), (float)(1 << kFixShift)));
+// (p - voxel centre) * fix_scale rounded to nearest, fix_scale = fl(1/voxel) * 2^20: the integer a point
+// adds to its voxel's sum (|result| <= 2^19 for a point inside the voxel).  One multiply, no division:
+// the value only has to be the SAME everywhere (kernels, ranks, the numpy statement), not a quotient.
+__host__ __device__ __forceinline__ float voxel_fix_scale(float voxel) { return (1.0f / voxel) * (float)(1 << kFixShift); }
+__device__ __forceinline__ int voxel_offset_fix(float p, float centre, float fix_scale) {
+  return __float2int_rn(__fmul_rn(__fsub_rn(p, centre), fix_scale));
 }
 
 // mean position = centre + (sum / count) * voxel * 2^-20 (float64, once per voxel); colour = round-half-up

@@ -68,7 +68,7 @@ segment_mean_kernel(GridDev g, const KeyT* __restrict__ unique_keys, const int* 
                     uint8_t* __restrict__ out_rgb, int32_t* __restrict__ out_count, long long* __restrict__ part_sums,
                     uint32_t* __restrict__ part_rgb) {
   const int64_t mv = counts[1];
-  const float scale = (float)(1 << kFixShift);
+  const float scale = voxel_fix_scale(g.voxel);
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < mv; r += (int64_t)gridDim.x * blockDim.x) {
     const KeyT key = unique_keys[r];
     const uint32_t kx = (uint32_t)(key & (((KeyT)1 << g.bx) - 1));
@@ -82,9 +82,9 @@ segment_mean_kernel(GridDev g, const KeyT* __restrict__ unique_keys, const int* 
     for (int j = 0; j < cnt; ++j) {
       const size_t i = sorted_idx[start + j];
       const float x = __ldg(xyz + i * 3 + 0), y = __ldg(xyz + i * 3 + 1), z = __ldg(xyz + i * 3 + 2);
-      sx += __float2ll_rn(__fmul_rn(__fdiv_rn(__fsub_rn(x, cx), g.voxel), scale));
-      sy += __float2ll_rn(__fmul_rn(__fdiv_rn(__fsub_rn(y, cy), g.voxel), scale));
-      sz += __float2ll_rn(__fmul_rn(__fdiv_rn(__fsub_rn(z, cz), g.voxel), scale));
+      sx += voxel_offset_fix(x, cx, scale);
+      sy += voxel_offset_fix(y, cy, scale);
+      sz += voxel_offset_fix(z, cz, scale);
       sr += __ldg(rgb + i * 3 + 0);
       sg += __ldg(rgb + i * 3 + 1);
       sb += __ldg(rgb + i * 3 + 2);

@@ -33,7 +33,8 @@ def partial_sums_numpy(xyz32, rgb, voxel, origin):
         return z(0, np.int64), z((0, 3), np.int64), z((0, 3), np.int64), z(0, np.int32)
     k, keys = canonical_keys(xyz32.astype(np.float32), voxel, origin)
     centre = (origin[None] + (k.astype(np.float32) + np.float32(0.5)) * voxel).astype(np.float32)
-    off = np.rint(((xyz32 - centre) / voxel).astype(np.float32) * FIX).astype(np.int64)
+    fix_scale = np.float32((np.float32(1.0) / np.float32(voxel)) * FIX)  # voxel_fix_scale (csrc/fuse_common.cuh)
+    off = np.rint(((xyz32.astype(np.float32) - centre) * fix_scale).astype(np.float32)).astype(np.int64)
     uk, inv, cnt = np.unique(keys, return_inverse=True, return_counts=True)
     sums = np.zeros((len(uk), 3), np.int64)
     np.add.at(sums, inv, off)
