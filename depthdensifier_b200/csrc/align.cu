@@ -456,7 +456,10 @@ __device__ __forceinline__ float pwl_eval_bucketed(float d, const float* __restr
   return pwl_interp(d, xs[i - 1], xs[i], ys[i - 1], ys[i]);
 }
 
-__global__ void __launch_bounds__(kRemapThreads)
+#ifndef DDN_K3_MINB
+#define DDN_K3_MINB 8
+#endif
+__global__ void __launch_bounds__(kRemapThreads, DDN_K3_MINB)
 remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y, const float* __restrict__ depth,
                     const uint8_t* __restrict__ mask, const ddn_view_stats* __restrict__ stats, AlignWorkspace ws,
                     float* __restrict__ refined, int lut_cap) {
@@ -490,25 +493,21 @@ remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y
   }
 
   const int n = st.num_table;
-  const float* xs = ws.tx + (size_t)v * ws.C;
-  const float* ys = ws.ty + (size_t)v * ws.C;
+  const float* gxs = ws.tx + (size_t)v * ws.C;
+  const float* gys = ws.ty + (size_t)v * ws.C;
   const bool bucketed = cfg.mode == 0 && n >= 2 && n <= lut_cap;
-  const uint32_t* bkt = nullptr;
+  float* const sx = s_dyn;  // shared-memory copies (only valid when `bucketed`)
+  float* const sy = s_dyn + lut_cap;
+  uint32_t* const sb = reinterpret_cast<uint32_t*>(s_dyn + 2 * lut_cap);
   float xmin = 0.f, bscale = 0.f;
   if (bucketed) {
-    float* sx = s_dyn;
-    float* sy = s_dyn + lut_cap;
-    uint32_t* sb = reinterpret_cast<uint32_t*>(s_dyn + 2 * lut_cap);
     for (int i = tid; i < n; i += kRemapThreads) {
-      sx[i] = xs[i];
-      sy[i] = ys[i];
+      sx[i] = gxs[i];
+      sy[i] = gys[i];
     }
     for (int i = tid; i < kBuckets; i += kRemapThreads) sb[i] = ws.bucket[(size_t)v * kBuckets + i];
-    xmin = xs[0];
-    bscale = bucket_scale(xmin, xs[n - 1]);
-    xs = sx;
-    ys = sy;
-    bkt = sb;
+    xmin = gxs[0];
+    bscale = bucket_scale(xmin, gxs[n - 1]);
     __syncthreads();
   }
   const float a_s = st.affine_scale, a_t = st.affine_shift;
@@ -517,13 +516,13 @@ remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y
   for (int i = tid; i < kHaloW * kHaloH; i += kRemapThreads) {
     const int hy = i / kHaloW, hx = i - hy * kHaloW;
     const int y = min(max(ty0 + hy - 1, 0), H - 1), x = min(max(tx0 + hx - 1, 0), W - 1);
-    const size_t g = (size_t)y * W + x;
+    const int g = y * W + x;
     const float d = __ldg(dmap + g);
     const bool mk = mmap ? (__ldg(mmap + g) != 0) : (d > 0.f);
     float val = 0.f;
     if (mk) {
-      if (bucketed) val = pwl_eval_bucketed(d, xs, ys, n, bkt, xmin, bscale);
-      else if (cfg.mode == 0) val = (n >= 2) ? pwl_eval(d, xs, ys, n) : __fmul_rn(d, __fdiv_rn(ys[0], __fadd_rn(xs[0], 1e-6f)));
+      if (bucketed) val = pwl_eval_bucketed(d, sx, sy, n, sb, xmin, bscale);
+      else if (cfg.mode == 0) val = (n >= 2) ? pwl_eval(d, gxs, gys, n) : __fmul_rn(d, __fdiv_rn(gys[0], __fadd_rn(gxs[0], 1e-6f)));
       else val = fmaxf(__fadd_rn(__fmul_rn(d, a_s), a_t), 1e-3f);
     }
     s_val[hy][hx] = val;
