@@ -180,9 +180,14 @@ def decode_bbox(bbox: torch.Tensor) -> np.ndarray:
 
 def backproject_filter(refined_all, normal, nbr, pair_table, src_table, src_begin: int, vote_threshold: int,
                        opts: FilterOptions, bbox=None, xyz_out=None, votes_out=None):
-    """Stages 2+3 for the source views src_begin..src_begin+n_src (n_src = normal.shape[0])."""
+    """Stages 2+3 for the source views src_begin..src_begin+n_src (n_src = normal.shape[0]).  ``normal`` may
+    be a PINNED HOST tensor: the kernel then reads the normals of its vote candidates in place over PCIe
+    (unified addressing) and the 12 B/pixel normal map never moves to the device."""
     lib = _lib.load()
-    dev = _require_cuda(refined_all, normal, nbr, pair_table, src_table, bbox, xyz_out, votes_out)
+    normal_on_host = not normal.is_cuda
+    if normal_on_host and not (normal.is_pinned() and normal.is_contiguous()):
+        raise DDNError("a host normal map must be pinned and contiguous")
+    dev = _require_cuda(refined_all, None if normal_on_host else normal, nbr, pair_table, src_table, bbox, xyz_out, votes_out)
     V, H, W = refined_all.shape
     n_src = normal.shape[0]
     K = nbr.shape[1]

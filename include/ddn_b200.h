@@ -129,7 +129,8 @@ DDN_API int ddn_build_pair_tables(int64_t n_views_total, int64_t src_begin, int6
                           float* pair_table, float* src_table, void* stream);
 
 /* refined_all [V,H,W] f32 (zero outside the mask); normal [n_src,H,W,3] f32 for the source views
- * src_begin..src_begin+n_src; outputs on the strided grid Hs=ceil(H/stride), Ws=ceil(W/stride):
+ * src_begin..src_begin+n_src - only the normals of vote candidates are read, so this one pointer may
+ * also be PINNED HOST memory (unified addressing): the map then never moves to the device; outputs on the strided grid Hs=ceil(H/stride), Ws=ceil(W/stride):
  * xyz [n_src,Hs,Ws,3] f32 world, votes [n_src,Hs,Ws] u8 (255 = pixel has no point, i.e. depth<=0).
  * bbox [6] f32 (optional, may be NULL): running min xyz / max xyz over points with
  * votes < vote_threshold; must be initialised to +inf/-inf by ddn_bbox_init. */

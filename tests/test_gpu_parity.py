@@ -314,3 +314,30 @@ def test_voxel_partials_and_merge_bit_exact(lib_built):
     assert np.array_equal(x.cpu().numpy(), ref_xyz) and np.array_equal(c.cpu().numpy(), ref_rgb)
     mk, ms, mcs, mn = merge_numpy(uk, sums, csum, cnt)
     assert np.array_equal(mk, uk) and np.array_equal(mn, cnt)
+
+
+@pytest.mark.parametrize("in_place", [True, False])
+def test_run_host_matches_device_pipeline(lib_built, in_place):
+    """The pipelined host entry point (chunked uploads overlapped with alignment, normals read in place from
+    pinned host memory or copied) returns exactly what the device-resident pipeline computes."""
+    from depthdensifier_b200.distributed import ShardedDensifier
+    from depthdensifier_b200.engine import DensifyConfig
+
+    sc = make_scene(SceneConfig(n_views=7, width=150, height=96, n_sparse=700, seed=3))
+    K = 4
+    nbr = nearest_views_table(sc.cam_from_world.numpy(), K)
+    sd = ShardedDensifier(DensifyConfig(voxel=0.02), torch.device("cuda", 0), 0, 1, 7, 0, 7, sc.cam_from_world, sc.intrinsics,
+                          nbr, 96, 150)
+    host = (sc.mono_depth, sc.normal, sc.mask, sc.rgb, sc.sparse_xyz, sc.sparse_offsets)
+    res = sd.run(*[t.cuda() for t in host])
+    mv = int(res.counts[1])
+    pinned = sd.pin_host_inputs(*host)
+    for _ in range(2):  # second call reuses the staging buffers
+        out = sd.run_host(*pinned, normals_in_place=in_place, chunk_views=3)
+    assert out["num_points"] == int(res.counts[0]) and len(out["keys"]) == mv
+    assert np.array_equal(out["keys"].numpy(), res.voxel_keys[:mv].cpu().numpy())
+    assert np.array_equal(out["xyz"].numpy(), res.voxel_xyz[:mv].cpu().numpy())
+    assert np.array_equal(out["rgb"].numpy(), res.voxel_rgb[:mv].cpu().numpy())
+    assert np.array_equal(out["count"].numpy(), res.voxel_count[:mv].cpu().numpy())
+    expected_h2d = sum(t.numel() * t.element_size() for i, t in enumerate(host) if not (in_place and i == 1))
+    assert out["h2d_bytes"] == expected_h2d
