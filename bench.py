@@ -193,6 +193,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+
         dist.init_process_group("nccl", device_id=dev)
         dist.barrier()
     _lib.load()

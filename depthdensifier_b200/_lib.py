@@ -61,6 +61,7 @@ class VoxelGrid(C.Structure):
 
 
 PAIR_TABLE_FLOATS = 24
+RECORD_WORDS = 6  # DDN_RECORD_WORDS
 
 # every symbol include/ddn_b200.h declares: name -> (restype, argtypes)
 _vp, _i64, _i32 = C.c_void_p, C.c_int64, C.c_int32
@@ -88,11 +89,11 @@ SYMBOLS = {
     ),
     "ddn_voxel_partials": (
         C.c_int,
-        [C.POINTER(VoxelGrid), _i64, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
+        [C.POINTER(VoxelGrid), _i64, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _vp],
     ),
     "ddn_voxel_merge": (
         C.c_int,
-        [C.POINTER(VoxelGrid), _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
+        [C.POINTER(VoxelGrid), _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     ),
     "ddn_voxel_keys": (C.c_int, [C.POINTER(VoxelGrid), _i64, _vp, _vp, _vp]),
 }

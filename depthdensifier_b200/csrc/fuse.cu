@@ -30,6 +30,11 @@ constexpr int kUnitsPerThread = 8;
 constexpr int kScanThreads = 256;
 constexpr int kTileUnits = kScanThreads * kUnitsPerThread;  // units per CTA in the rank passes (32 KB)
 constexpr int kAccWords = 5;                                // sx, sy, sz, r:g, b:count (u64 each)
+// Partial-sum RECORD exchanged between ranks: {key, sx, sy, sz, r:g, b:count} = DDN_RECORD_WORDS u64.  In
+// partial mode the accumulators ARE words 1..5 of the output records (stride 6), so there is no
+// finalisation pass and a destination's share of the sorted records is one contiguous slice.
+constexpr int kRecWords = DDN_RECORD_WORDS;
+static_assert(kRecWords == kAccWords + 1, "record = key + accumulators");
 constexpr uint64_t kDenseMaxCells = 1ull << 35;             // 5.7 GB of units
 constexpr uint64_t kNoCell = ~0ull;
 
@@ -119,13 +124,13 @@ mark_points_kernel(GridDev g, float rv, int64_t n, const float* __restrict__ xyz
 }
 
 __global__ void __launch_bounds__(256)
-mark_records_kernel(GridDev g, int64_t n, const uint64_t* __restrict__ keys, uint32_t* __restrict__ units,
+mark_records_kernel(GridDev g, int64_t n, const uint64_t* __restrict__ records, uint32_t* __restrict__ units,
                     unsigned long long* __restrict__ n_in) {
   __shared__ int s_count;
   if (threadIdx.x == 0) s_count = 0;
   __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  const uint64_t cell = i < n ? cell_of_key(g, __ldg(keys + i)) : kNoCell;
+  const uint64_t cell = i < n ? cell_of_key(g, __ldg(records + i * kRecWords)) : kNoCell;
   if (cell != kNoCell) set_cell_bit(units, cell);
   const int c = __popc(__ballot_sync(0xffffffffu, cell != kNoCell));
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_count, c);
@@ -199,7 +204,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t* __restrict__ 
 // keys[slot].  The cell coordinates are decoded once per non-empty unit and then stepped along x.
 __global__ void __launch_bounds__(kScanThreads)
 unit_prefix_kernel(GridDev g, uint4* __restrict__ units, uint32_t n_units, const uint32_t* __restrict__ tile_excl,
-                   uint64_t* __restrict__ keys) {
+                   uint64_t* __restrict__ keys, int key_stride) {
   __shared__ uint32_t s_warp[kScanThreads / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t base = blockIdx.x * kTileUnits;
@@ -250,7 +255,7 @@ unit_prefix_kernel(GridDev g, uint4* __restrict__ units, uint32_t n_units, const
             row_off += (uint32_t)g.nx;
             if (++ky >= (uint32_t)g.ny) ky = 0, ++kz;
           }
-          keys[slot++] = (uint64_t)kx | ((uint64_t)ky << 21) | ((uint64_t)kz << 42);
+          keys[(size_t)(slot++) * key_stride] = (uint64_t)kx | ((uint64_t)ky << 21) | ((uint64_t)kz << 42);
         }
       }
     }
@@ -258,8 +263,9 @@ unit_prefix_kernel(GridDev g, uint4* __restrict__ units, uint32_t n_units, const
 }
 
 // accumulators of the counts[1] voxels -> 0 (device-side count, no host round trip)
-__global__ void __launch_bounds__(256) zero_accum_kernel(ulonglong2* __restrict__ accum2, const int64_t* __restrict__ counts) {
-  const int64_t n2 = (counts[1] * kAccWords + 1) / 2;
+__global__ void __launch_bounds__(256)
+zero_accum_kernel(ulonglong2* __restrict__ accum2, const int64_t* __restrict__ counts, int words_per_voxel) {
+  const int64_t n2 = (counts[1] * words_per_voxel + 1) / 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x)
     accum2[i] = make_ulonglong2(0ull, 0ull);
 }
@@ -283,9 +289,9 @@ struct RunAcc {
 };
 
 __device__ __forceinline__ void flush_run(uint64_t cell, const RunAcc& acc, const uint4* __restrict__ units,
-                                          unsigned long long* __restrict__ accum) {
+                                          unsigned long long* __restrict__ accum, int stride) {
   if (cell == kNoCell || acc.n == 0) return;
-  unsigned long long* a = accum + (size_t)slot_of_cell(cell, units) * kAccWords;
+  unsigned long long* a = accum + (size_t)slot_of_cell(cell, units) * stride;
   atomicAdd(a + 0, (unsigned long long)acc.sx);
   atomicAdd(a + 1, (unsigned long long)acc.sy);
   atomicAdd(a + 2, (unsigned long long)acc.sz);
@@ -305,7 +311,7 @@ template <bool kTiled>
 __global__ void __launch_bounds__(256)
 accumulate_points_kernel(GridDev g, float rv, int64_t n, int row_len, const float* __restrict__ xyz,
                          const uint8_t* __restrict__ rgb, const uint8_t* __restrict__ votes, int thr,
-                         const uint4* __restrict__ units, unsigned long long* __restrict__ accum) {
+                         const uint4* __restrict__ units, unsigned long long* __restrict__ accum, int stride) {
   const int lane = threadIdx.x & 31;
   const float fix_scale = voxel_fix_scale(g.voxel);
   // n < 2^31, so tile indices fit 32 bits
@@ -375,7 +381,7 @@ accumulate_points_kernel(GridDev g, float rv, int64_t n, int row_len, const floa
       if (has) sx += ax, sy += ay, sz += az, srg += arg, sb += ab;
     }
     if (leader) {
-      unsigned long long* a = accum + (size_t)slot_of_cell(cell, units) * kAccWords;
+      unsigned long long* a = accum + (size_t)slot_of_cell(cell, units) * stride;
       atomicAdd(a + 0, (unsigned long long)(long long)sx);
       atomicAdd(a + 1, (unsigned long long)(long long)sy);
       atomicAdd(a + 2, (unsigned long long)(long long)sz);
@@ -386,26 +392,24 @@ accumulate_points_kernel(GridDev g, float rv, int64_t n, int row_len, const floa
 }
 
 __global__ void __launch_bounds__(256)
-accumulate_records_kernel(GridDev g, int64_t n, const uint64_t* __restrict__ keys, const long long* __restrict__ in_sums,
-                          const uint32_t* __restrict__ in_rgb, const int32_t* __restrict__ in_count,
-                          const uint4* __restrict__ units, unsigned long long* __restrict__ accum) {
+accumulate_records_kernel(GridDev g, int64_t n, const unsigned long long* __restrict__ records, const uint4* __restrict__ units,
+                          unsigned long long* __restrict__ accum) {
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
-  const uint64_t cell = cell_of_key(g, __ldg(keys + i));
-  RunAcc acc;
-  acc.sx = in_sums[i * 3 + 0], acc.sy = in_sums[i * 3 + 1], acc.sz = in_sums[i * 3 + 2];
-  acc.r = in_rgb[i * 3 + 0], acc.g = in_rgb[i * 3 + 1], acc.b = in_rgb[i * 3 + 2];
-  acc.n = (uint32_t)in_count[i];
-  flush_run(cell, acc, units, accum);
+  const unsigned long long* r = records + i * kRecWords;
+  const uint64_t cell = cell_of_key(g, __ldg(r));
+  if (cell == kNoCell) return;
+  unsigned long long* a = accum + (size_t)slot_of_cell(cell, units) * kAccWords;
+#pragma unroll
+  for (int q = 0; q < kAccWords; ++q) atomicAdd(a + q, __ldg(r + 1 + q));
 }
 
 // One thread per voxel.  The colour fields are 32 bits wide: a voxel with 2^24 or more points could
 // have overflowed them, which is reported (counts_out[0] = -1) instead of returned as a wrong colour.
-template <bool kPartialOut>
 __global__ void __launch_bounds__(256)
 finalize_kernel(GridDev g, const unsigned long long* __restrict__ accum, const uint64_t* __restrict__ keys,
                 int64_t* __restrict__ counts, float* __restrict__ out_xyz, uint8_t* __restrict__ out_rgb,
-                int32_t* __restrict__ out_count, long long* __restrict__ part_sums, uint32_t* __restrict__ part_rgb) {
+                int32_t* __restrict__ out_count) {
   const int64_t mv = counts[1];
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < mv; r += (int64_t)gridDim.x * blockDim.x) {
     const unsigned long long* a = accum + (size_t)r * kAccWords;
@@ -414,19 +418,10 @@ finalize_kernel(GridDev g, const unsigned long long* __restrict__ accum, const u
     const uint32_t cnt = (uint32_t)bn;
     if (cnt >= (1u << 24)) counts[0] = -1;
     out_count[r] = (int32_t)cnt;
-    if (kPartialOut) {
-      part_sums[r * 3 + 0] = sx;
-      part_sums[r * 3 + 1] = sy;
-      part_sums[r * 3 + 2] = sz;
-      part_rgb[r * 3 + 0] = (uint32_t)(rg >> 32);
-      part_rgb[r * 3 + 1] = (uint32_t)rg;
-      part_rgb[r * 3 + 2] = (uint32_t)(bn >> 32);
-    } else {
-      const uint64_t key = keys[r];
-      const uint32_t kx = (uint32_t)(key & 0x1fffff), ky = (uint32_t)((key >> 21) & 0x1fffff), kz = (uint32_t)((key >> 42) & 0x1fffff);
-      finalize_voxel(g, voxel_centre(g.ox, kx, g.voxel), voxel_centre(g.oy, ky, g.voxel), voxel_centre(g.oz, kz, g.voxel), sx, sy,
-                     sz, rg >> 32, rg & 0xffffffffull, bn >> 32, (long long)cnt, out_xyz + r * 3, out_rgb + r * 3);
-    }
+    const uint64_t key = keys[r];
+    const uint32_t kx = (uint32_t)(key & 0x1fffff), ky = (uint32_t)((key >> 21) & 0x1fffff), kz = (uint32_t)((key >> 42) & 0x1fffff);
+    finalize_voxel(g, voxel_centre(g.ox, kx, g.voxel), voxel_centre(g.oy, ky, g.voxel), voxel_centre(g.oz, kz, g.voxel), sx, sy, sz,
+                   rg >> 32, rg & 0xffffffffull, bn >> 32, (long long)cnt, out_xyz + r * 3, out_rgb + r * 3);
   }
 }
 
@@ -450,7 +445,7 @@ struct DenseLayout {
 static uint64_t grid_cells(const GridDev& g) { return (uint64_t)g.nx * (uint64_t)g.ny * (uint64_t)g.nz; }
 static bool use_dense(const GridDev& g) { return grid_cells(g) <= kDenseMaxCells; }
 
-static void dense_layout(const GridDev& g, int64_t n, DenseLayout* L) {
+static void dense_layout(const GridDev& g, int64_t n, DenseLayout* L) {  // sized for the non-partial form
   L->cells = grid_cells(g);
   L->n_units = (L->cells + kUnitBits - 1) / kUnitBits;
   L->tiles = (L->n_units + kTileUnits - 1) / kTileUnits;
@@ -476,14 +471,12 @@ struct DenseSource {
   int thr = 0;
   int64_t row_len = 0;
   // records
-  const uint64_t* rec_keys = nullptr;
-  const long long* rec_sums = nullptr;
-  const uint32_t* rec_rgb = nullptr;
-  const int32_t* rec_count = nullptr;
+  const unsigned long long* records = nullptr;
 };
 
+// records_out != nullptr: partial mode (output = records, no finalisation); else final voxels.
 static int dense_fuse(const GridDev& g, int64_t n, const DenseSource& src, uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb,
-                      int32_t* out_count, long long* part_sums, uint32_t* part_rgb, int64_t* counts_out, void* workspace,
+                      int32_t* out_count, unsigned long long* records_out, int64_t* counts_out, void* workspace,
                       int64_t workspace_bytes, cudaStream_t st) {
   DenseLayout L;
   dense_layout(g, n, &L);
@@ -494,11 +487,17 @@ static int dense_fuse(const GridDev& g, int64_t n, const DenseSource& src, uint6
   char* base = reinterpret_cast<char*>(align_up((int64_t)(uintptr_t)workspace, 256));
   uint4* units = (uint4*)(base + L.units);
   uint32_t* tile_sums = (uint32_t*)(base + L.tile_sums);
-  unsigned long long* accum = (unsigned long long*)(base + L.accum);
+  const bool partial = records_out != nullptr;
+  // accumulators: words 1..5 of the output records (partial mode) or a workspace array
+  unsigned long long* accum = partial ? records_out + 1 : (unsigned long long*)(base + L.accum);
+  const int stride = partial ? kRecWords : kAccWords;
+  unsigned long long* zero_base = partial ? records_out : accum;
+  uint64_t* keys = partial ? (uint64_t*)records_out : out_keys;
   const float rv = 1.0f / g.voxel;
   const unsigned blocks = (unsigned)((n + 255) / 256);
-  const bool points = src.rec_keys == nullptr;
+  const bool points = src.records == nullptr;
   const bool vec = points && ((uintptr_t)src.xyz % 16 == 0) && (src.votes == nullptr || (uintptr_t)src.votes % 4 == 0);
+  DDN_REQUIRE((uintptr_t)zero_base % 16 == 0, "record / accumulator buffer must be 16-byte aligned");
 
   DDN_TRY(check_cuda(cudaMemsetAsync(units, 0, L.units_bytes, st), "memset occupancy"));
   DDN_TRY(check_cuda(cudaMemsetAsync(counts_out, 0, 16, st), "memset counts"));
@@ -511,33 +510,32 @@ static int dense_fuse(const GridDev& g, int64_t n, const DenseSource& src, uint6
       mark_points_kernel<false><<<mblocks, 256, 0, st>>>(g, rv, n, src.xyz, src.votes, src.thr, (uint32_t*)units,
                                                          (unsigned long long*)counts_out);
   } else {
-    mark_records_kernel<<<blocks, 256, 0, st>>>(g, n, src.rec_keys, (uint32_t*)units, (unsigned long long*)counts_out);
+    mark_records_kernel<<<blocks, 256, 0, st>>>(g, n, (const uint64_t*)src.records, (uint32_t*)units, (unsigned long long*)counts_out);
   }
   DDN_TRY(after_launch("mark_kernel"));
   tile_count_kernel<<<(unsigned)L.tiles, kScanThreads, 0, st>>>(units, (uint32_t)L.n_units, tile_sums);
   DDN_TRY(after_launch("tile_count_kernel"));
   tile_scan_kernel<<<1, 1024, 0, st>>>(tile_sums, (int)L.tiles, counts_out);
   DDN_TRY(after_launch("tile_scan_kernel"));
-  unit_prefix_kernel<<<(unsigned)L.tiles, kScanThreads, 0, st>>>(g, units, (uint32_t)L.n_units, tile_sums, out_keys);
-  DDN_TRY(after_launch("unit_prefix_kernel"));
-  zero_accum_kernel<<<kNumSMs * 8, 256, 0, st>>>((ulonglong2*)accum, counts_out);
+  zero_accum_kernel<<<kNumSMs * 8, 256, 0, st>>>((ulonglong2*)zero_base, counts_out, stride);
   DDN_TRY(after_launch("zero_accum_kernel"));
+  unit_prefix_kernel<<<(unsigned)L.tiles, kScanThreads, 0, st>>>(g, units, (uint32_t)L.n_units, tile_sums, keys, partial ? kRecWords : 1);
+  DDN_TRY(after_launch("unit_prefix_kernel"));
   if (points) {
     const bool tiled = src.row_len >= 8 && src.row_len < (1 << 30);
     const int64_t n_tiles = tiled ? ((src.row_len + 7) / 8) * (((n + src.row_len - 1) / src.row_len + 3) / 4) : (n + 31) / 32;
     const unsigned ablocks = (unsigned)((n_tiles + 8 * kAccTilesPerWarp - 1) / (8 * kAccTilesPerWarp));
     if (tiled)
-      accumulate_points_kernel<true><<<ablocks, 256, 0, st>>>(g, rv, n, (int)src.row_len, src.xyz, src.rgb, src.votes, src.thr, units, accum);
+      accumulate_points_kernel<true><<<ablocks, 256, 0, st>>>(g, rv, n, (int)src.row_len, src.xyz, src.rgb, src.votes, src.thr, units,
+                                                              accum, stride);
     else
-      accumulate_points_kernel<false><<<ablocks, 256, 0, st>>>(g, rv, n, 0, src.xyz, src.rgb, src.votes, src.thr, units, accum);
+      accumulate_points_kernel<false><<<ablocks, 256, 0, st>>>(g, rv, n, 0, src.xyz, src.rgb, src.votes, src.thr, units, accum, stride);
   } else {
-    accumulate_records_kernel<<<blocks, 256, 0, st>>>(g, n, src.rec_keys, src.rec_sums, src.rec_rgb, src.rec_count, units, accum);
+    accumulate_records_kernel<<<blocks, 256, 0, st>>>(g, n, src.records, units, accum);
   }
   DDN_TRY(after_launch("accumulate_kernel"));
-  if (part_sums != nullptr)
-    finalize_kernel<true><<<kNumSMs * 8, 256, 0, st>>>(g, accum, out_keys, counts_out, out_xyz, out_rgb, out_count, part_sums, part_rgb);
-  else
-    finalize_kernel<false><<<kNumSMs * 8, 256, 0, st>>>(g, accum, out_keys, counts_out, out_xyz, out_rgb, out_count, nullptr, nullptr);
+  if (partial) return DDN_OK;
+  finalize_kernel<<<kNumSMs * 8, 256, 0, st>>>(g, accum, out_keys, counts_out, out_xyz, out_rgb, out_count);
   return after_launch("finalize_kernel");
 }
 
@@ -578,17 +576,15 @@ int ddn_voxel_fuse(const ddn_voxel_grid* grid_host, int64_t n_points, int64_t ro
   DDN_REQUIRE(xyz && rgb && out_keys && out_xyz && out_rgb && out_count && workspace, "null pointer");
   if (!use_dense(g))
     return sort_fuse_points(g, n_points, xyz, rgb, votes, vote_threshold, out_keys, out_xyz, out_rgb, out_count, counts_out,
-                            workspace, workspace_bytes, st, nullptr, nullptr);
+                            workspace, workspace_bytes, st, nullptr);
   DenseSource src;
   src.xyz = xyz, src.rgb = rgb, src.votes = votes, src.thr = vote_threshold, src.row_len = row_len;
-  return dense_fuse(g, n_points, src, out_keys, out_xyz, out_rgb, out_count, nullptr, nullptr, counts_out, workspace,
-                    workspace_bytes, st);
+  return dense_fuse(g, n_points, src, out_keys, out_xyz, out_rgb, out_count, nullptr, counts_out, workspace, workspace_bytes, st);
 }
 
 int ddn_voxel_partials(const ddn_voxel_grid* grid_host, int64_t n_points, int64_t row_len, const float* xyz, const uint8_t* rgb,
-                       const uint8_t* votes, int32_t vote_threshold, uint64_t* part_keys, int64_t* part_sums,
-                       uint32_t* part_rgb, int32_t* part_count, int64_t* counts_out, void* workspace,
-                       int64_t workspace_bytes, void* stream) {
+                       const uint8_t* votes, int32_t vote_threshold, uint64_t* records, int64_t* counts_out,
+                       void* workspace, int64_t workspace_bytes, void* stream) {
   using namespace ddn;
   GridDev g;
   DDN_TRY(grid_from_host(grid_host, &g));
@@ -597,20 +593,19 @@ int ddn_voxel_partials(const ddn_voxel_grid* grid_host, int64_t n_points, int64_
   DDN_REQUIRE(counts_out != nullptr, "null counts_out");
   cudaStream_t st = (cudaStream_t)stream;
   if (n_points == 0) return check_cuda(cudaMemsetAsync(counts_out, 0, 16, st), "memset counts");
-  DDN_REQUIRE(xyz && rgb && part_keys && part_sums && part_rgb && part_count && workspace, "null pointer");
+  DDN_REQUIRE(xyz && rgb && records && workspace, "null pointer");
   if (!use_dense(g))
-    return sort_fuse_points(g, n_points, xyz, rgb, votes, vote_threshold, part_keys, nullptr, nullptr, part_count, counts_out,
-                            workspace, workspace_bytes, st, (long long*)part_sums, part_rgb);
+    return sort_fuse_points(g, n_points, xyz, rgb, votes, vote_threshold, nullptr, nullptr, nullptr, nullptr, counts_out, workspace,
+                            workspace_bytes, st, (unsigned long long*)records);
   DenseSource src;
   src.xyz = xyz, src.rgb = rgb, src.votes = votes, src.thr = vote_threshold, src.row_len = row_len;
-  return dense_fuse(g, n_points, src, part_keys, nullptr, nullptr, part_count, (long long*)part_sums, part_rgb, counts_out,
-                    workspace, workspace_bytes, st);
+  return dense_fuse(g, n_points, src, nullptr, nullptr, nullptr, nullptr, (unsigned long long*)records, counts_out, workspace,
+                    workspace_bytes, st);
 }
 
-int ddn_voxel_merge(const ddn_voxel_grid* grid_host, int64_t n_records, const uint64_t* part_keys,
-                    const int64_t* part_sums, const uint32_t* part_rgb, const int32_t* part_count,
-                    uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb, int32_t* out_count, int64_t* counts_out,
-                    void* workspace, int64_t workspace_bytes, void* stream) {
+int ddn_voxel_merge(const ddn_voxel_grid* grid_host, int64_t n_records, const uint64_t* records, uint64_t* out_keys,
+                    float* out_xyz, uint8_t* out_rgb, int32_t* out_count, int64_t* counts_out, void* workspace,
+                    int64_t workspace_bytes, void* stream) {
   using namespace ddn;
   GridDev g;
   DDN_TRY(grid_from_host(grid_host, &g));
@@ -618,15 +613,13 @@ int ddn_voxel_merge(const ddn_voxel_grid* grid_host, int64_t n_records, const ui
   DDN_REQUIRE(counts_out != nullptr, "null counts_out");
   cudaStream_t st = (cudaStream_t)stream;
   if (n_records == 0) return check_cuda(cudaMemsetAsync(counts_out, 0, 16, st), "memset counts");
-  DDN_REQUIRE(part_keys && part_sums && part_rgb && part_count && out_keys && out_xyz && out_rgb && out_count && workspace,
-              "null pointer");
+  DDN_REQUIRE(records && out_keys && out_xyz && out_rgb && out_count && workspace, "null pointer");
   if (!use_dense(g))
-    return sort_merge_records(g, n_records, part_keys, (const long long*)part_sums, part_rgb, part_count, out_keys, out_xyz,
-                              out_rgb, out_count, counts_out, workspace, workspace_bytes, st);
+    return sort_merge_records(g, n_records, (const unsigned long long*)records, out_keys, out_xyz, out_rgb, out_count, counts_out,
+                              workspace, workspace_bytes, st);
   DenseSource src;
-  src.rec_keys = part_keys, src.rec_sums = (const long long*)part_sums, src.rec_rgb = part_rgb, src.rec_count = part_count;
-  return dense_fuse(g, n_records, src, out_keys, out_xyz, out_rgb, out_count, nullptr, nullptr, counts_out, workspace,
-                    workspace_bytes, st);
+  src.records = (const unsigned long long*)records;
+  return dense_fuse(g, n_records, src, out_keys, out_xyz, out_rgb, out_count, nullptr, counts_out, workspace, workspace_bytes, st);
 }
 
 int ddn_voxel_keys(const ddn_voxel_grid* grid_host, int64_t n_points, const float* xyz, uint64_t* keys, void* stream) {

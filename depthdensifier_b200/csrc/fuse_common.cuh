@@ -76,12 +76,13 @@ __device__ __forceinline__ void finalize_voxel(const GridDev& g, float cx, float
 }
 
 // ---- sort path (fuse_sort.cu) -------------------------------------------------------------------
+// records != nullptr: partial mode, output = records [.,DDN_RECORD_WORDS] (see include/ddn_b200.h)
 int sort_fuse_workspace_bytes(int64_t n_points, int64_t* bytes_out);
 int sort_fuse_points(const GridDev& g, int64_t n, const float* xyz, const uint8_t* rgb, const uint8_t* votes, int thr,
                      uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb, int32_t* out_count, int64_t* counts_out,
-                     void* workspace, int64_t workspace_bytes, cudaStream_t st, long long* part_sums, uint32_t* part_rgb);
-int sort_merge_records(const GridDev& g, int64_t n, const uint64_t* in_keys, const long long* in_sums, const uint32_t* in_rgb,
-                       const int32_t* in_count, uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb, int32_t* out_count,
-                       int64_t* counts_out, void* workspace, int64_t workspace_bytes, cudaStream_t st);
+                     void* workspace, int64_t workspace_bytes, cudaStream_t st, unsigned long long* records);
+int sort_merge_records(const GridDev& g, int64_t n, const unsigned long long* records, uint64_t* out_keys, float* out_xyz,
+                       uint8_t* out_rgb, int32_t* out_count, int64_t* counts_out, void* workspace, int64_t workspace_bytes,
+                       cudaStream_t st);
 
 }  // namespace ddn

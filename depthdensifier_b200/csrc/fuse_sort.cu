@@ -65,8 +65,7 @@ segment_mean_kernel(GridDev g, const KeyT* __restrict__ unique_keys, const int* 
                     const int* __restrict__ run_starts, const int64_t* __restrict__ counts,
                     const uint32_t* __restrict__ sorted_idx, const float* __restrict__ xyz,
                     const uint8_t* __restrict__ rgb, uint64_t* __restrict__ out_keys, float* __restrict__ out_xyz,
-                    uint8_t* __restrict__ out_rgb, int32_t* __restrict__ out_count, long long* __restrict__ part_sums,
-                    uint32_t* __restrict__ part_rgb) {
+                    uint8_t* __restrict__ out_rgb, int32_t* __restrict__ out_count, unsigned long long* __restrict__ records) {
   const int64_t mv = counts[1];
   const float scale = voxel_fix_scale(g.voxel);
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < mv; r += (int64_t)gridDim.x * blockDim.x) {
@@ -89,16 +88,18 @@ segment_mean_kernel(GridDev g, const KeyT* __restrict__ unique_keys, const int* 
       sg += __ldg(rgb + i * 3 + 1);
       sb += __ldg(rgb + i * 3 + 2);
     }
-    out_keys[r] = (uint64_t)kx | ((uint64_t)ky << 21) | ((uint64_t)kz << 42);
-    out_count[r] = cnt;
+    const uint64_t canon = (uint64_t)kx | ((uint64_t)ky << 21) | ((uint64_t)kz << 42);
     if (kPartialOut) {
-      part_sums[r * 3 + 0] = sx;
-      part_sums[r * 3 + 1] = sy;
-      part_sums[r * 3 + 2] = sz;
-      part_rgb[r * 3 + 0] = (uint32_t)sr;
-      part_rgb[r * 3 + 1] = (uint32_t)sg;
-      part_rgb[r * 3 + 2] = (uint32_t)sb;
+      unsigned long long* o = records + (size_t)r * DDN_RECORD_WORDS;
+      o[0] = canon;
+      o[1] = (unsigned long long)sx;
+      o[2] = (unsigned long long)sy;
+      o[3] = (unsigned long long)sz;
+      o[4] = (sr << 32) | sg;
+      o[5] = (sb << 32) | (unsigned long long)(unsigned)cnt;
     } else {
+      out_keys[r] = canon;
+      out_count[r] = cnt;
       finalize_voxel(g, cx, cy, cz, sx, sy, sz, sr, sg, sb, (long long)cnt, out_xyz + r * 3, out_rgb + r * 3);
     }
   }
@@ -106,11 +107,11 @@ segment_mean_kernel(GridDev g, const KeyT* __restrict__ unique_keys, const int* 
 
 // ---- merge of partial records (multi-GPU owner side) ----------------------------------------------
 template <typename KeyT>
-__global__ void compact_key_kernel(GridDev g, int64_t n, const uint64_t* __restrict__ canon, KeyT* __restrict__ keys,
+__global__ void compact_key_kernel(GridDev g, int64_t n, const unsigned long long* __restrict__ records, KeyT* __restrict__ keys,
                                    uint32_t* __restrict__ idx) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint64_t c = canon[i];
+  const uint64_t c = records[i * DDN_RECORD_WORDS];
   const uint64_t kx = c & 0x1fffff, ky = (c >> 21) & 0x1fffff, kz = (c >> 42) & 0x1fffff;
   keys[i] = (KeyT)kx | ((KeyT)ky << g.bx) | ((KeyT)kz << (g.bx + g.by));
   idx[i] = (uint32_t)i;
@@ -126,8 +127,7 @@ template <typename KeyT>
 __global__ void __launch_bounds__(256)
 merge_segments_kernel(GridDev g, const KeyT* __restrict__ unique_keys, const int* __restrict__ run_counts,
                       const int* __restrict__ run_starts, const int64_t* __restrict__ counts,
-                      const uint32_t* __restrict__ sorted_idx, const long long* __restrict__ in_sums,
-                      const uint32_t* __restrict__ in_rgb, const int32_t* __restrict__ in_count,
+                      const uint32_t* __restrict__ sorted_idx, const unsigned long long* __restrict__ records,
                       uint64_t* __restrict__ out_keys, float* __restrict__ out_xyz, uint8_t* __restrict__ out_rgb,
                       int32_t* __restrict__ out_count) {
   const int64_t mv = counts[1];
@@ -142,13 +142,14 @@ merge_segments_kernel(GridDev g, const KeyT* __restrict__ unique_keys, const int
     unsigned long long sr = 0, sg = 0, sb = 0;
     for (int j = 0; j < nrec; ++j) {
       const size_t i = sorted_idx[start + j];
-      sx += in_sums[i * 3 + 0];
-      sy += in_sums[i * 3 + 1];
-      sz += in_sums[i * 3 + 2];
-      sr += in_rgb[i * 3 + 0];
-      sg += in_rgb[i * 3 + 1];
-      sb += in_rgb[i * 3 + 2];
-      cnt += in_count[i];
+      const unsigned long long* q = records + i * DDN_RECORD_WORDS;
+      sx += (long long)q[1];
+      sy += (long long)q[2];
+      sz += (long long)q[3];
+      sr += q[4] >> 32;
+      sg += q[4] & 0xffffffffull;
+      sb += q[5] >> 32;
+      cnt += (long long)(q[5] & 0xffffffffull);
     }
     out_keys[r] = (uint64_t)kx | ((uint64_t)ky << 21) | ((uint64_t)kz << 42);
     out_count[r] = (int32_t)cnt;
@@ -197,8 +198,7 @@ static int fuse_layout(int64_t n, FuseLayout* L) {
 template <typename KeyT>
 static int fuse_impl(const GridDev& g, int64_t n, const float* xyz, const uint8_t* rgb, const uint8_t* votes, int thr,
                      uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb, int32_t* out_count, int64_t* counts_out,
-                     void* workspace, int64_t workspace_bytes, cudaStream_t st, long long* part_sums = nullptr,
-                     uint32_t* part_rgb = nullptr) {
+                     void* workspace, int64_t workspace_bytes, cudaStream_t st, unsigned long long* records = nullptr) {
   FuseLayout L;
   DDN_TRY(fuse_layout<KeyT>(n, &L));
   if ((int64_t)L.total > workspace_bytes) {
@@ -235,20 +235,17 @@ static int fuse_impl(const GridDev& g, int64_t n, const float* xyz, const uint8_
   g_launches.fetch_add(2, std::memory_order_relaxed);
   fuse_finalize_kernel<KeyT><<<1, 1, 0, st>>>(g, n, uniq, run_counts, num_runs, counts_out);
   DDN_TRY(after_launch("fuse_finalize_kernel"));
-  if (part_sums != nullptr)
+  if (records != nullptr)
     segment_mean_kernel<KeyT, true><<<kNumSMs * 8, 256, 0, st>>>(g, uniq, run_counts, run_starts, counts_out, dv.Current(),
-                                                                xyz, rgb, out_keys, out_xyz, out_rgb, out_count, part_sums,
-                                                                part_rgb);
+                                                                xyz, rgb, out_keys, out_xyz, out_rgb, out_count, records);
   else
     segment_mean_kernel<KeyT, false><<<kNumSMs * 8, 256, 0, st>>>(g, uniq, run_counts, run_starts, counts_out, dv.Current(),
-                                                                 xyz, rgb, out_keys, out_xyz, out_rgb, out_count, nullptr,
-                                                                 nullptr);
+                                                                 xyz, rgb, out_keys, out_xyz, out_rgb, out_count, nullptr);
   return after_launch("segment_mean_kernel");
 }
 
 template <typename KeyT>
-static int merge_impl(const GridDev& g, int64_t n, const uint64_t* in_keys, const long long* in_sums, const uint32_t* in_rgb,
-                      const int32_t* in_count, uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb, int32_t* out_count,
+static int merge_impl(const GridDev& g, int64_t n, const unsigned long long* records, uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb, int32_t* out_count,
                       int64_t* counts_out, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
   FuseLayout L;
   DDN_TRY(fuse_layout<KeyT>(n, &L));
@@ -267,7 +264,7 @@ static int merge_impl(const GridDev& g, int64_t n, const uint64_t* in_keys, cons
   int* num_runs = (int*)(base + L.num_runs);
   void* temp = base + L.cub_temp;
   size_t temp_bytes = L.cub_temp_bytes;
-  compact_key_kernel<KeyT><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, n, in_keys, keys_a, idx_a);
+  compact_key_kernel<KeyT><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, n, records, keys_a, idx_a);
   DDN_TRY(after_launch("compact_key_kernel"));
   cub::DoubleBuffer<KeyT> dk(keys_a, keys_b);
   cub::DoubleBuffer<uint32_t> dv(idx_a, idx_b);
@@ -283,8 +280,8 @@ static int merge_impl(const GridDev& g, int64_t n, const uint64_t* in_keys, cons
   g_launches.fetch_add(2, std::memory_order_relaxed);
   merge_finalize_counts_kernel<KeyT><<<1, 1, 0, st>>>(n, num_runs, counts_out);
   DDN_TRY(after_launch("merge_finalize_counts_kernel"));
-  merge_segments_kernel<KeyT><<<kNumSMs * 8, 256, 0, st>>>(g, uniq, run_counts, run_starts, counts_out, dv.Current(), in_sums,
-                                                          in_rgb, in_count, out_keys, out_xyz, out_rgb, out_count);
+  merge_segments_kernel<KeyT><<<kNumSMs * 8, 256, 0, st>>>(g, uniq, run_counts, run_starts, counts_out, dv.Current(), records,
+                                                          out_keys, out_xyz, out_rgb, out_count);
   return after_launch("merge_segments_kernel");
 }
 
@@ -297,22 +294,20 @@ int sort_fuse_workspace_bytes(int64_t n_points, int64_t* bytes_out) {
 
 int sort_fuse_points(const GridDev& g, int64_t n, const float* xyz, const uint8_t* rgb, const uint8_t* votes, int thr,
                      uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb, int32_t* out_count, int64_t* counts_out,
-                     void* workspace, int64_t workspace_bytes, cudaStream_t st, long long* part_sums, uint32_t* part_rgb) {
+                     void* workspace, int64_t workspace_bytes, cudaStream_t st, unsigned long long* records) {
   if (g.bx + g.by + g.bz <= 31)
     return fuse_impl<uint32_t>(g, n, xyz, rgb, votes, thr, out_keys, out_xyz, out_rgb, out_count, counts_out, workspace,
-                               workspace_bytes, st, part_sums, part_rgb);
+                               workspace_bytes, st, records);
   return fuse_impl<uint64_t>(g, n, xyz, rgb, votes, thr, out_keys, out_xyz, out_rgb, out_count, counts_out, workspace,
-                             workspace_bytes, st, part_sums, part_rgb);
+                             workspace_bytes, st, records);
 }
 
-int sort_merge_records(const GridDev& g, int64_t n, const uint64_t* in_keys, const long long* in_sums, const uint32_t* in_rgb,
-                       const int32_t* in_count, uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb, int32_t* out_count,
-                       int64_t* counts_out, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+int sort_merge_records(const GridDev& g, int64_t n, const unsigned long long* records, uint64_t* out_keys, float* out_xyz,
+                       uint8_t* out_rgb, int32_t* out_count, int64_t* counts_out, void* workspace, int64_t workspace_bytes,
+                       cudaStream_t st) {
   if (g.bx + g.by + g.bz <= 32)
-    return merge_impl<uint32_t>(g, n, in_keys, in_sums, in_rgb, in_count, out_keys, out_xyz, out_rgb, out_count, counts_out,
-                                workspace, workspace_bytes, st);
-  return merge_impl<uint64_t>(g, n, in_keys, in_sums, in_rgb, in_count, out_keys, out_xyz, out_rgb, out_count, counts_out,
-                              workspace, workspace_bytes, st);
+    return merge_impl<uint32_t>(g, n, records, out_keys, out_xyz, out_rgb, out_count, counts_out, workspace, workspace_bytes, st);
+  return merge_impl<uint64_t>(g, n, records, out_keys, out_xyz, out_rgb, out_count, counts_out, workspace, workspace_bytes, st);
 }
 
 }  // namespace ddn

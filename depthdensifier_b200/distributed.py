@@ -203,7 +203,7 @@ class ShardedDensifier:
             k, x, c, n, counts = mark("voxel_fuse", lambda: self.ops.voxel_fuse(
                 xyz.view(-1, 3), rgb_s.view(-1, 3), votes.view(-1), self.thr, grid, trim=False, row_len=xyz.shape[2]))
         else:
-            k, x, c, n, counts = mark("voxel_fuse", lambda: self._fuse_sharded(xyz, rgb_s, votes, grid))
+            k, x, c, n, counts = mark("voxel_fuse", lambda: self._fuse_sharded(xyz, rgb_s, votes, grid, mark))
         res.grid, res.voxel_keys, res.voxel_xyz, res.voxel_rgb, res.voxel_count, res.counts = grid, k, x, c, n, counts
         return res
 
@@ -214,12 +214,19 @@ class ShardedDensifier:
         pad = torch.full((self.n_slots - self.n_local, self.K), -1, dtype=torch.int32, device=self.device)
         return torch.cat([self.nbr_slots, pad], 0).contiguous()
 
-    def _fuse_sharded(self, xyz, rgb, votes, grid):
+    def _fuse_sharded(self, xyz, rgb, votes, grid, mark=None):
+        if mark is None:
+            mark = lambda name, fn: fn()
+        rec, counts = mark("fuse_partials", lambda: self.ops.voxel_fuse_partial(
+            xyz.view(-1, 3), rgb.view(-1, 3), votes.view(-1), self.thr, grid, row_len=xyz.shape[2]))
+        return mark("fuse_exchange_merge", lambda: self._exchange_and_merge(rec, counts, grid, mark))
+
+    def _exchange_and_merge(self, rec, counts, grid, mark):
         import torch.distributed as dist
 
-        pk, psum, prgb, pcnt, counts = self.ops.voxel_fuse_partial(xyz.view(-1, 3), rgb.view(-1, 3), votes.view(-1), self.thr, grid, row_len=xyz.shape[2])
         mv = int(counts[1].item())
-        pk, psum, prgb, pcnt = pk[:mv], psum[:mv], prgb[:mv], pcnt[:mv]
+        rec = rec[:mv]
+        pk = rec[:, 0]
         R = self.world
         # sampled splitters: R-1 local quantile keys per rank -> global quantiles of the R*(R-1) samples
         if mv > 0:
@@ -231,22 +238,25 @@ class ShardedDensifier:
         dist.all_gather_into_tensor(allsamp, samples.contiguous(), group=self.group)
         allsamp, _ = torch.sort(allsamp)
         splitters = allsamp[torch.arange(1, R, device=self.device) * (R - 1) - 1]
-        cuts = torch.searchsorted(pk, splitters)  # local sorted keys: slice r = [cuts[r-1], cuts[r])
+        cuts = torch.searchsorted(pk.contiguous(), splitters)  # local sorted keys: slice r = [cuts[r-1], cuts[r])
         bnd = torch.cat([torch.zeros(1, dtype=torch.int64, device=self.device), cuts, torch.tensor([mv], device=self.device)])
         send_counts = (bnd[1:] - bnd[:-1]).contiguous()
         recv_counts = torch.empty_like(send_counts)
         dist.all_to_all_single(recv_counts, send_counts, group=self.group)
-        sc, rc = send_counts.cpu().tolist(), recv_counts.cpu().tolist()
+        both = torch.stack([send_counts, recv_counts]).cpu().tolist()  # one readback for both
+        sc, rc = both
         n_recv = int(sum(rc))
+        W = rec.shape[1]
 
-        def exchange(t, width):
-            out = torch.empty((n_recv,) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device)
-            dist.all_to_all_single(out.view(-1), t.contiguous().view(-1), output_split_sizes=[c * width for c in rc],
-                                   input_split_sizes=[c * width for c in sc], group=self.group)
+        def exchange():
+            # the sorted records of one destination are one contiguous slice: no pack kernel, one collective
+            out = torch.empty((n_recv, W), dtype=rec.dtype, device=self.device)
+            dist.all_to_all_single(out.view(-1), rec.reshape(-1), output_split_sizes=[c * W for c in rc],
+                                   input_split_sizes=[c * W for c in sc], group=self.group)
             return out
 
-        rk, rsum, rrgb, rcnt = exchange(pk, 1), exchange(psum, 3), exchange(prgb, 3), exchange(pcnt, 1)
-        k, x, c, n, mcounts = self.ops.voxel_merge_partials(rk, rsum, rrgb, rcnt, grid)
+        got = mark("fuse_alltoall", exchange)
+        k, x, c, n, mcounts = mark("fuse_merge", lambda: self.ops.voxel_merge_partials(got, grid))
         counts2 = torch.stack([counts[0], mcounts[1]])  # (points fused locally, voxels owned)
         return k, x, c, n, counts2
 

@@ -269,9 +269,9 @@ def voxel_fuse(xyz, rgb, votes, vote_threshold: int, grid: _lib.VoxelGrid, trim:
 
 
 def voxel_fuse_partial(xyz, rgb, votes, vote_threshold: int, grid: _lib.VoxelGrid, row_len: int = 0):
-    """Rank-local stage 4: per-voxel partial sums (keys ascending).  Returns part_keys [N] i64,
-    part_sums [N,3] i64, part_rgb [N,3] i32 (uint32 bits), part_count [N] i32 (all sized for the worst
-    case N) and the device counts [2] = (participating points, local voxels)."""
+    """Rank-local stage 4: per-voxel partial RECORDS, keys ascending (layout: include/ddn_b200.h,
+    ``unpack_records`` below).  Returns records [N, 6] i64 (sized for the worst case N) and the device
+    counts [2] = (participating points, local voxels)."""
     lib = _lib.load()
     dev = _require_cuda(xyz, rgb, votes)
     N = xyz.shape[0]
@@ -279,28 +279,30 @@ def voxel_fuse_partial(xyz, rgb, votes, vote_threshold: int, grid: _lib.VoxelGri
     nbytes = C.c_int64(0)
     _lib.check(lib.ddn_fuse_workspace_bytes(C.byref(grid), N, C.byref(nbytes)))
     ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
-    pk = torch.empty(N, dtype=torch.int64, device=dev)
-    ps = torch.empty((N, 3), dtype=torch.int64, device=dev)
-    pr = torch.empty((N, 3), dtype=torch.int32, device=dev)
-    pc = torch.empty(N, dtype=torch.int32, device=dev)
+    rec = torch.empty((max(N, 1), _lib.RECORD_WORDS), dtype=torch.int64, device=dev)
     counts = torch.zeros(2, dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
         _lib.check(
             lib.ddn_voxel_partials(
-                C.byref(grid), N, int(row_len), _p(xyz), _p(rgb), _p(votes), int(vote_threshold), _p(pk), _p(ps), _p(pr), _p(pc),
-                _p(counts), _p(ws), nbytes.value, _stream(),
+                C.byref(grid), N, int(row_len), _p(xyz), _p(rgb), _p(votes), int(vote_threshold), _p(rec), _p(counts), _p(ws),
+                nbytes.value, _stream(),
             )
         )
-    return pk, ps, pr, pc, counts
+    return rec, counts
 
 
-def voxel_merge_partials(part_keys, part_sums, part_rgb, part_count, grid: _lib.VoxelGrid, trim: bool = False):
-    """Owner-side merge of partial records (any order) into final voxels."""
+def unpack_records(rec):
+    """(keys, sums [n,3], colour sums [n,3], count) from records [n, 6] i64 (torch or numpy)."""
+    lo = 0xFFFFFFFF
+    return rec[:, 0], rec[:, 1:4], (rec[:, 4] >> 32) & lo, rec[:, 4] & lo, (rec[:, 5] >> 32) & lo, rec[:, 5] & lo
+
+
+def voxel_merge_partials(records, grid: _lib.VoxelGrid, trim: bool = False):
+    """Owner-side merge of partial records [n, 6] i64 (any order) into final voxels."""
     lib = _lib.load()
-    dev = _require_cuda(part_keys, part_sums, part_rgb, part_count)
-    n = part_keys.shape[0]
-    assert part_keys.dtype == torch.int64 and part_sums.dtype == torch.int64 and part_rgb.dtype == torch.int32
-    assert part_count.dtype == torch.int32 and tuple(part_sums.shape) == (n, 3) and tuple(part_rgb.shape) == (n, 3)
+    dev = _require_cuda(records)
+    n = records.shape[0]
+    assert records.dtype == torch.int64 and (n == 0 or tuple(records.shape) == (n, _lib.RECORD_WORDS))
     nbytes = C.c_int64(0)
     _lib.check(lib.ddn_fuse_workspace_bytes(C.byref(grid), max(n, 1), C.byref(nbytes)))
     ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
@@ -313,8 +315,8 @@ def voxel_merge_partials(part_keys, part_sums, part_rgb, part_count, grid: _lib.
     with torch.cuda.device(dev):
         _lib.check(
             lib.ddn_voxel_merge(
-                C.byref(grid), n, _p(part_keys), _p(part_sums), _p(part_rgb), _p(part_count), _p(out_keys), _p(out_xyz),
-                _p(out_rgb), _p(out_cnt), _p(counts), _p(ws), nbytes.value, _stream(),
+                C.byref(grid), n, _p(records), _p(out_keys), _p(out_xyz), _p(out_rgb), _p(out_cnt), _p(counts), _p(ws),
+                nbytes.value, _stream(),
             )
         )
     if trim:

@@ -172,17 +172,19 @@ DDN_API int ddn_voxel_fuse(const ddn_voxel_grid* grid_host, int64_t n_points, in
                    int64_t* counts_out, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Multi-GPU form of stage 4.  ddn_voxel_partials fuses the rank's own points into per-voxel PARTIAL
- * sums (keys ascending): part_sums [N,3] i64 = sum of (p - voxel centre) in units of voxel * 2^-20,
- * part_rgb [N,3] u32 colour sums, part_count [N] i32.  Integer sums make the final means independent
- * of how points are split over ranks.  ddn_voxel_merge adds the records of equal key (any input
- * order, e.g. the concatenation of the sorted runs received from R ranks) and finalises them. */
+ * records, keys ascending.  A record is DDN_RECORD_WORDS u64:
+ *   [0] key   [1..3] sum of (p - voxel centre) * fl(1/voxel) * 2^20 per axis (two's complement)
+ *   [4] sum(r) << 32 | sum(g)   [5] sum(b) << 32 | count
+ * Integer sums make the final means independent of how points are split over ranks, and because the
+ * records are sorted a destination rank's share is one contiguous slice.  ddn_voxel_merge adds the
+ * records of equal key (any input order, e.g. the concatenation of the runs received from R ranks)
+ * and finalises them.  records: [N, DDN_RECORD_WORDS] u64, 16-byte aligned, sized for the worst case. */
+#define DDN_RECORD_WORDS 6
 DDN_API int ddn_voxel_partials(const ddn_voxel_grid* grid_host, int64_t n_points, int64_t row_len, const float* xyz,
-                       const uint8_t* rgb, const uint8_t* votes, int32_t vote_threshold,
-                       uint64_t* part_keys, int64_t* part_sums, uint32_t* part_rgb, int32_t* part_count,
+                       const uint8_t* rgb, const uint8_t* votes, int32_t vote_threshold, uint64_t* records,
                        int64_t* counts_out, void* workspace, int64_t workspace_bytes, void* stream);
 
-DDN_API int ddn_voxel_merge(const ddn_voxel_grid* grid_host, int64_t n_records, const uint64_t* part_keys,
-                    const int64_t* part_sums, const uint32_t* part_rgb, const int32_t* part_count,
+DDN_API int ddn_voxel_merge(const ddn_voxel_grid* grid_host, int64_t n_records, const uint64_t* records,
                     uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb, int32_t* out_count,
                     int64_t* counts_out, void* workspace, int64_t workspace_bytes, void* stream);
 

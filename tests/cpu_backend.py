@@ -43,6 +43,23 @@ def partial_sums_numpy(xyz32, rgb, voxel, origin):
     return uk, sums, csum, cnt.astype(np.int32)
 
 
+def pack_records(keys, sums, csum, cnt):
+    """The 6-word partial record of include/ddn_b200.h (int64 view of the u64 words)."""
+    rec = np.zeros((len(keys), 6), np.int64)
+    rec[:, 0] = keys.astype(np.int64)
+    rec[:, 1:4] = sums
+    c = csum.astype(np.int64)
+    rec[:, 4] = (c[:, 0] << 32) | c[:, 1]
+    rec[:, 5] = (c[:, 2] << 32) | cnt.astype(np.int64)
+    return rec
+
+
+def unpack_records(rec):
+    lo = np.int64(0xFFFFFFFF)
+    csum = np.stack([(rec[:, 4] >> 32) & lo, rec[:, 4] & lo, (rec[:, 5] >> 32) & lo], 1)
+    return rec[:, 0], rec[:, 1:4], csum, (rec[:, 5] & lo).astype(np.int32)
+
+
 def finalize_numpy(keys, sums, csum, cnt, voxel, origin):
     kx, ky, kz = keys & 0x1FFFFF, (keys >> 21) & 0x1FFFFF, (keys >> 42) & 0x1FFFFF
     k = np.stack([kx, ky, kz], 1)
@@ -156,17 +173,17 @@ class OracleBackend:
         x, c, voxel, origin = self._select(xyz, rgb, votes, thr, grid)
         uk, sums, csum, cnt = partial_sums_numpy(x, c, voxel, origin)
         counts = torch.tensor([len(x), len(uk)], dtype=torch.int64)
-        return (torch.from_numpy(uk.astype(np.int64)), torch.from_numpy(sums), torch.from_numpy(csum.astype(np.int32)),
-                torch.from_numpy(cnt), counts)
+        return torch.from_numpy(pack_records(uk, sums, csum, cnt)), counts
 
-    def voxel_merge_partials(self, pk, psum, prgb, pcnt, grid, trim=False):
+    def voxel_merge_partials(self, records, grid, trim=False):
         voxel, origin, _ = grid_tuple(grid)
-        uk, s, c, n = merge_numpy(pk.numpy(), psum.numpy(), prgb.numpy().astype(np.int64), pcnt.numpy())
+        pk, psum, prgb, pcnt = unpack_records(records.numpy())
+        uk, s, c, n = merge_numpy(pk, psum, prgb, pcnt)
         xyz, col = finalize_numpy(uk, s, c, n, voxel, origin)
         counts = torch.tensor([len(pk), len(uk)], dtype=torch.int64)
         return torch.from_numpy(uk.astype(np.int64)), torch.from_numpy(xyz), torch.from_numpy(col), torch.from_numpy(n), counts
 
     def voxel_fuse(self, xyz, rgb, votes, thr, grid, trim=True, row_len=0):
-        pk, ps, pr, pc, counts = self.voxel_fuse_partial(xyz, rgb, votes, thr, grid)
-        k, x, c, n, _ = self.voxel_merge_partials(pk, ps, pr, pc, grid)
+        rec, counts = self.voxel_fuse_partial(xyz, rgb, votes, thr, grid)
+        k, x, c, n, _ = self.voxel_merge_partials(rec, grid)
         return k, x, c, n, counts

@@ -284,7 +284,7 @@ def test_pipeline_end_to_end_vs_oracle(lib_built):
 def test_voxel_partials_and_merge_bit_exact(lib_built):
     """Multi-GPU form of N4: partial sums and their merge are integer arithmetic -> bit-exact against the
     numpy statement in tests/cpu_backend.py, and merge(partials of two halves) == fuse(all)."""
-    from cpu_backend import finalize_numpy, merge_numpy, partial_sums_numpy
+    from cpu_backend import finalize_numpy, merge_numpy, pack_records, partial_sums_numpy, unpack_records
     from depthdensifier_b200 import ops
 
     rng = np.random.default_rng(5)
@@ -295,18 +295,17 @@ def test_voxel_partials_and_merge_bit_exact(lib_built):
     grid = ops.make_grid(xyz.min(0), xyz.max(0), voxel)
     origin = np.array(list(grid.origin), np.float32)
     uk, sums, csum, cnt = partial_sums_numpy(xyz, rgb, np.float32(voxel), origin)
-    pk, ps, pr, pc, counts = ops.voxel_fuse_partial(_cuda(xyz), _cuda(rgb), None, 1, grid)
+    rec, counts = ops.voxel_fuse_partial(_cuda(xyz), _cuda(rgb), None, 1, grid, row_len=300)
     mv = int(counts[1])
     assert counts.cpu().tolist() == [n, len(uk)]
-    assert np.array_equal(pk[:mv].cpu().numpy(), uk)
-    assert np.array_equal(ps[:mv].cpu().numpy(), sums)
-    assert np.array_equal(pr[:mv].cpu().numpy().astype(np.int64), csum)
-    assert np.array_equal(pc[:mv].cpu().numpy(), cnt)
+    assert np.array_equal(rec[:mv].cpu().numpy(), pack_records(uk, sums, csum, cnt))
+    pk, ps, pr, pc = unpack_records(rec[:mv].cpu().numpy())
+    assert np.array_equal(pk, uk) and np.array_equal(ps, sums) and np.array_equal(pr, csum) and np.array_equal(pc, cnt)
     # split the points in two "ranks", fuse partially, merge the concatenated records
     h = n // 3
     parts = [ops.voxel_fuse_partial(_cuda(xyz[a:b]), _cuda(rgb[a:b]), None, 1, grid) for a, b in ((0, h), (h, n))]
-    cat = [torch.cat([p[i][: int(p[4][1])] for p in parts]).contiguous() for i in range(4)]
-    k, x, c, m, mc = ops.voxel_merge_partials(*cat, grid, trim=True)
+    cat = torch.cat([p[0][: int(p[1][1])] for p in parts]).contiguous()
+    k, x, c, m, mc = ops.voxel_merge_partials(cat, grid, trim=True)
     full = ops.voxel_fuse(_cuda(xyz), _cuda(rgb), None, 1, grid)
     assert np.array_equal(k.cpu().numpy(), full[0].cpu().numpy()) and np.array_equal(m.cpu().numpy(), full[3].cpu().numpy())
     assert np.array_equal(x.cpu().numpy(), full[1].cpu().numpy()) and np.array_equal(c.cpu().numpy(), full[2].cpu().numpy())

@@ -41,7 +41,7 @@ def test_argument_validation_without_gpu(lib_built):
     assert abs(f.depth_threshold - 0.7) < 1e-7 and abs(f.grazing_cos - 0.087) < 1e-7 and f.stride == 1
     g = _lib.VoxelGrid()
     g.voxel = -1.0
-    assert lib.ddn_voxel_fuse(ctypes.byref(g), 10, None, None, None, 1, None, None, None, None, None, None, 0, None) == -1
+    assert lib.ddn_voxel_fuse(ctypes.byref(g), 10, 0, None, None, None, 1, None, None, None, None, None, None, 0, None) == -1
 
 
 def test_no_cpu_fallback():
