@@ -33,7 +33,10 @@ constexpr int kFilterChunk = kFilterThreads * kFilterPX;
 // pair_table[s][k][24]: rows 0..2 of K_t [M | t_ts], M = R_t R_s^T Kinv_s (12 floats) - i.e. the pixel
 //   (x, y) at depth d maps to (U, V, Z) = rows * (d x, d y, d, 1) and lands at u = U/Z, v = V/Z;
 //   camera centre of t (3), target view index (int bits), fx_t fy_t cx_t cy_t, own-view flag, pad.
-// src_table[s][16]: rows of R_s^T Kinv_s with c_s appended (12 floats), cx_s, cy_s, pad.
+//   The entries of a source view are COMPACTED: valid neighbours other than the view itself first
+//   (n_hot of them, in table order), then the n_own entries of the view itself (only the
+//   reference-parity table K = V lists it); entry 0 carries n_hot and n_own in floats 22, 23 (int bits).  K4's hot loop therefore runs over n_hot entries without any validity test.
+// src_table[s][16]: rows of R_s^T Kinv_s with c_s appended (12 floats), cx_s, cy_s, fx_s, fy_s.
 // ------------------------------------------------------------------------------------------------
 __global__ void build_pair_tables_kernel(int n_total, int src_begin, int n_src, int k_nbr,
                                          const double* __restrict__ poses,
@@ -71,13 +74,25 @@ __global__ void build_pair_tables_kernel(int n_total, int src_begin, int n_src, 
     return;
   }
   const int k = idx - sl * k_nbr;
-  const int t = nbr[(size_t)s * k_nbr + k];
-  float* o = pair_table + (size_t)idx * DDN_PAIR_TABLE_FLOATS;
-  if (t < 0 || t >= n_total) {
-    for (int i = 0; i < DDN_PAIR_TABLE_FLOATS; ++i) o[i] = 0.f;
-    o[15] = __int_as_float(-1);
-    return;
+  const int32_t* row = nbr + (size_t)s * k_nbr;
+  const int t = row[k];
+  int n_hot = 0, n_own = 0, hot_before = 0, own_before = 0;
+  for (int q = 0; q < k_nbr; ++q) {
+    const int tq = row[q];
+    const bool own = tq == s, hot = tq >= 0 && tq < n_total && !own;
+    n_hot += hot ? 1 : 0;
+    n_own += own ? 1 : 0;
+    hot_before += (hot && q < k) ? 1 : 0;
+    own_before += (own && q < k) ? 1 : 0;
   }
+  if (k == 0) {
+    float* e0 = pair_table + (size_t)sl * k_nbr * DDN_PAIR_TABLE_FLOATS;
+    e0[22] = __int_as_float(n_hot);
+    e0[23] = __int_as_float(n_own);
+  }
+  if (t < 0 || t >= n_total) return;
+  const int pos = (t == s) ? n_hot + own_before : hot_before;
+  float* o = pair_table + ((size_t)sl * k_nbr + pos) * DDN_PAIR_TABLE_FLOATS;
   const double* Pt = poses + (size_t)t * 12;
   double Rt[3][3], tt[3];
   for (int i = 0; i < 3; ++i) {
@@ -107,7 +122,7 @@ __global__ void build_pair_tables_kernel(int n_total, int src_begin, int n_src, 
   o[18] = (float)intr[t * 4 + 2];
   o[19] = (float)intr[t * 4 + 3];
   o[20] = (t == s) ? 1.f : 0.f;
-  o[21] = o[22] = o[23] = 0.f;
+  o[21] = 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -184,9 +199,8 @@ __device__ __forceinline__ void stage_floats(float* smem, float* gptr, int n) {
 // the grazing gate passes").
 template <bool kBilinear, bool kTwoSided>
 __device__ __forceinline__ bool pair_candidate(const float4& r0, const float4& r1, const float4& r2, float P, float Q,
-                                               float d, const float* __restrict__ depth_all, unsigned map_off,
-                                               unsigned W, int H, unsigned wbits, unsigned hbits, unsigned idx_bias,
-                                               float thr, float tau) {
+                                               float d, const float* __restrict__ depth_all, unsigned off_k,
+                                               unsigned W, int H, unsigned wbits, unsigned hbits, float thr, float tau) {
   const float U = fmaf(r0.x, P, fmaf(r0.y, Q, fmaf(r0.z, d, r0.w)));
   const float V = fmaf(r1.x, P, fmaf(r1.y, Q, fmaf(r1.z, d, r1.w)));
   const float Z = fmaf(r2.x, P, fmaf(r2.y, Q, fmaf(r2.z, d, r2.w)));
@@ -199,12 +213,12 @@ __device__ __forceinline__ bool pair_candidate(const float4& r0, const float4& r
   const unsigned ub = (unsigned)trunc_biased(u), vb = (unsigned)trunc_biased(v);
   float D;
   if (!kBilinear) {
-    // 32-bit element offset from the start of refined_all (modular arithmetic removes the 2^23 biases);
-    // out-of-bounds lanes read the first pixel of the map and are masked by `inb`.
-    const unsigned off = inb ? vb * W + ub + (map_off - idx_bias) : map_off;
+    // 32-bit element offset from the start of refined_all; off_k = t*H*W - bias*(W+1) removes the 2^23
+    // biases by modular arithmetic.  Out-of-bounds lanes read element 0 and are masked by `inb`.
+    const unsigned off = inb ? vb * W + ub + off_k : 0u;
     D = __ldg(depth_all + off);
   } else {
-    const float* __restrict__ depth_t = depth_all + map_off;
+    const float* __restrict__ depth_t = depth_all + (off_k + (unsigned)kTruncBias * (W + 1u));
     // N3: 4 taps at floor(u), floor(v), +1 clamped; all taps must be > 0
     const int x0 = inb ? ub - kTruncBias : 0, y0 = inb ? vb - kTruncBias : 0;
     const int x1 = min(x0 + 1, (int)W - 1), y1 = min(y0 + 1, H - 1);
@@ -263,8 +277,16 @@ __global__ void __launch_bounds__(kFilterThreads, kBilinear ? 3 : DDN_K4_MINBLOC
   const float* __restrict__ depth_s = p.refined_all + (size_t)s * HW;
   const float* __restrict__ normal_s = p.normal + (size_t)sl * HW * 3;
 
-  for (int i = tid; i < p.K * DDN_PAIR_TABLE_FLOATS; i += kFilterThreads)
-    s_pair[i] = __ldg(p.pair_table + (size_t)sl * p.K * DDN_PAIR_TABLE_FLOATS + i);
+  // pair entries -> shared memory; float 16 of every entry (unused by this kernel) is replaced by the
+  // entry's gather offset t*H*W - bias*(W+1) (see pair_candidate)
+  const unsigned idx_bias = (unsigned)kTruncBias * (unsigned)(p.W + 1);
+  for (int i = tid; i < p.K * DDN_PAIR_TABLE_FLOATS; i += kFilterThreads) {
+    const int f = i % DDN_PAIR_TABLE_FLOATS;
+    const float val = __ldg(p.pair_table + (size_t)sl * p.K * DDN_PAIR_TABLE_FLOATS + i);
+    if (f == 16) continue;
+    s_pair[i] = val;
+    if (f == 15) s_pair[i + 1] = __uint_as_float((unsigned)__float_as_int(val) * (unsigned)HW - idx_bias);
+  }
   if (tid < 16) s_src[tid] = __ldg(p.src_table + (size_t)sl * 16 + tid);
   if (tid < 6) s_bbox[tid] = tid < 3 ? 0x7fffffff : (int)0x80000000;
 
@@ -310,6 +332,7 @@ __global__ void __launch_bounds__(kFilterThreads, kBilinear ? 3 : DDN_K4_MINBLOC
         s_xyz[l * 3 + 2] = valid ? Z : 0.f;
       }
       d[j] = valid ? dd[j] : qnan;
+      asm volatile("" : "+f"(d[j]));  // keep the NaN-tagged depth in a register (no per-neighbour recompute)
       P[j] = d[j] * (float)px[j];
       Q[j] = d[j] * (float)py[j];
       nvotes[j] = 0;
@@ -326,10 +349,9 @@ __global__ void __launch_bounds__(kFilterThreads, kBilinear ? 3 : DDN_K4_MINBLOC
   }
 
   const unsigned wbits = __float_as_uint((float)p.W), hbits = __float_as_uint((float)p.H);
-  const unsigned idx_bias = (unsigned)kTruncBias * (unsigned)(p.W + 1);
   const float thr = p.depth_threshold, gcos = p.grazing_cos, tau = p.two_sided_tau;
   const bool in_world = p.normals_in_world != 0;
-  bool any_own = false;
+  const int n_hot = __float_as_int(s_pair[22]), n_own = __float_as_int(s_pair[23]);
 
   // Hot loop: branch-free candidate test for every (pixel, neighbour); the four gathers of a thread
   // issue back to back.  Candidates ("would vote if the grazing gate passes") are only recorded as a
@@ -337,33 +359,28 @@ __global__ void __launch_bounds__(kFilterThreads, kBilinear ? 3 : DDN_K4_MINBLOC
   // resolved after each block of 32 neighbours, once per pixel that has a candidate at all.
   if (any_live) {
     const bool all_live = live[0] & live[1] & live[2] & live[3];
-    for (int k0 = 0; k0 < p.K; k0 += 32) {
-      const int k1 = min(k0 + 32, p.K);
+    for (int k0 = 0; k0 < n_hot; k0 += 32) {
+      const int k1 = min(k0 + 32, n_hot);
       unsigned cm[kFilterPX];
 #pragma unroll
       for (int j = 0; j < kFilterPX; ++j) cm[j] = 0u;
-      for (int k = k0; k < k1; ++k) {
+      unsigned bit = 1u;
+      for (int k = k0; k < k1; ++k, bit <<= 1) {
         const float4* t4 = reinterpret_cast<const float4*>(s_pair + k * DDN_PAIR_TABLE_FLOATS);
-        const int t = __float_as_int(t4[3].w);
-        if (t < 0) continue;
-        if (t4[5].x != 0.f) {  // own view: handled after the main loop
-          any_own = true;
-          continue;
-        }
         const float4 r0 = t4[0], r1 = t4[1], r2 = t4[2];
-        const unsigned map_off = (unsigned)t * (unsigned)HW;
-        const unsigned bit = 1u << (k - k0);
+        const unsigned off_k = __float_as_uint(s_pair[k * DDN_PAIR_TABLE_FLOATS + 16]);
         if (all_live) {
 #pragma unroll
           for (int j = 0; j < kFilterPX; ++j)
-            cm[j] |= pair_candidate<kBilinear, kTwoSided>(r0, r1, r2, P[j], Q[j], d[j], p.refined_all, map_off, (unsigned)p.W,
-                                                          p.H, wbits, hbits, idx_bias, thr, tau) ? bit : 0u;
+            if (pair_candidate<kBilinear, kTwoSided>(r0, r1, r2, P[j], Q[j], d[j], p.refined_all, off_k, (unsigned)p.W, p.H,
+                                                     wbits, hbits, thr, tau))
+              cm[j] |= bit;
         } else {
 #pragma unroll
           for (int j = 0; j < kFilterPX; ++j)
-            if (live[j])
-              cm[j] |= pair_candidate<kBilinear, kTwoSided>(r0, r1, r2, P[j], Q[j], d[j], p.refined_all, map_off,
-                                                            (unsigned)p.W, p.H, wbits, hbits, idx_bias, thr, tau) ? bit : 0u;
+            if (live[j] && pair_candidate<kBilinear, kTwoSided>(r0, r1, r2, P[j], Q[j], d[j], p.refined_all, off_k,
+                                                                (unsigned)p.W, p.H, wbits, hbits, thr, tau))
+              cm[j] |= bit;
         }
       }
       // dot(n, -(Xw - c_t)/|Xw - c_t|) > cos  <=>  dot(n, c_t - Xw) > cos * |c_t - Xw|
@@ -389,15 +406,14 @@ __global__ void __launch_bounds__(kFilterThreads, kBilinear ? 3 : DDN_K4_MINBLOC
     }
   }
 
-  if (any_own) {
+  if (n_own > 0) {
     // Own view (only present in the reference-parity table K = V).  The reference normalises by (z + 1e-8)
     // before applying K (scripts/test.py:71-75), so u = x * z/(z+1e-8) lands ~x*1e-8/z BELOW the integer x
     // (far above float64 round-off) and the truncation at :308-309 looks up pixel (x-1, y-1) for
     // x, y >= 1.  Reproduced in integer arithmetic; z is the pixel's own depth.  (x == 0 or y == 0 is a
     // round-off tie in the reference.)
-    for (int k = 0; k < p.K; ++k) {
+    for (int k = n_hot; k < n_hot + n_own; ++k) {
       const float4* t4 = reinterpret_cast<const float4*>(s_pair + k * DDN_PAIR_TABLE_FLOATS);
-      if (__float_as_int(t4[3].w) < 0 || t4[5].x == 0.f) continue;
       const float4 cc = t4[3];
 #pragma unroll
       for (int j = 0; j < kFilterPX; ++j) {
