@@ -17,6 +17,8 @@
 //     the views in flight stay L2 resident;
 //   * float->int truncation uses FADD.RZ with 2^23 instead of F2I (keeps the XU pipe free for the
 //     one MUFU.RCP and one MUFU.SQRT per pair).
+#include <string.h>
+
 #include "common.cuh"
 
 namespace ddn {
@@ -140,6 +142,7 @@ struct FilterParams {
   int vote_threshold;
   float depth_threshold, grazing_cos, two_sided_tau;
   int normals_in_world;
+  unsigned wbits, hbits;  // bit patterns of (float)W, (float)H for the bounds test on raw bits
 };
 
 __device__ __forceinline__ float rcp_approx(float x) {
@@ -195,23 +198,23 @@ __device__ __forceinline__ void stage_floats(float* smem, float* gptr, int n) {
   }
 }
 
-// One (pixel, neighbour) evaluation up to the depth lookup: returns the candidate flag ("would vote if
-// the grazing gate passes").
-template <bool kBilinear, bool kTwoSided>
-__device__ __forceinline__ bool pair_candidate(const float4& r0, const float4& r1, const float4& r2, float P, float Q,
-                                               float d, const float* __restrict__ depth_all, unsigned off_k,
-                                               unsigned W, int H, unsigned wbits, unsigned hbits, float thr, float tau) {
+// One (pixel, neighbour) evaluation, in two steps so that the gathers of a thread's four pixels are all in
+// flight before the first one is consumed.  pair_gather: project, bounds test, issue the depth lookup.
+// pair_test: the candidate flag ("would vote if the grazing gate passes").
+template <bool kBilinear>
+__device__ __forceinline__ void pair_gather(const float4& r0, const float4& r1, const float4& r2, float P, float Q, float d,
+                                            const float* __restrict__ depth_all, unsigned off_k, unsigned W, int H,
+                                            unsigned wbits, unsigned hbits, float& Z, float& D, bool& inb) {
   const float U = fmaf(r0.x, P, fmaf(r0.y, Q, fmaf(r0.z, d, r0.w)));
   const float V = fmaf(r1.x, P, fmaf(r1.y, Q, fmaf(r1.z, d, r1.w)));
-  const float Z = fmaf(r2.x, P, fmaf(r2.y, Q, fmaf(r2.z, d, r2.w)));
+  Z = fmaf(r2.x, P, fmaf(r2.y, Q, fmaf(r2.z, d, r2.w)));
   const float inv = rcp_approx(Z);
   const float u = U * inv;
   const float v = V * inv;
   // 0 <= u < W and 0 <= v < H on the raw bits (negative floats and NaN compare as huge unsigned);
   // invalid pixels carry NaN depth, so Z > 0 rejects them too.
-  const bool inb = (__float_as_uint(u) < wbits) & (__float_as_uint(v) < hbits) & (Z > 0.f);
+  inb = (__float_as_uint(u) < wbits) & (__float_as_uint(v) < hbits) & (Z > 0.f);
   const unsigned ub = (unsigned)trunc_biased(u), vb = (unsigned)trunc_biased(v);
-  float D;
   if (!kBilinear) {
     // 32-bit element offset from the start of refined_all; off_k = t*H*W - bias*(W+1) removes the 2^23
     // biases by modular arithmetic.  Out-of-bounds lanes read element 0 and are masked by `inb`.
@@ -231,6 +234,10 @@ __device__ __forceinline__ bool pair_candidate(const float4& r0, const float4& r
                                 __fmul_rn(__fmul_rn(fxw, fyw), td));
     D = ((ta > 0.f) & (tb > 0.f) & (tc > 0.f) & (td > 0.f)) ? acc : 0.f;
   }
+}
+
+template <bool kTwoSided>
+__device__ __forceinline__ bool pair_test(float Z, float D, bool inb, float thr, float tau) {
   if (kTwoSided) return inb & (D > 0.f) & (fabsf(Z - D) > tau * D);
   // one-sided floater test z < float32(thr * D) (scripts/test.py:319-321, NEP-50 product in float32).
   // The lookup-valid gate D > 0 (:315) is implied: inb has Z > 0 and thr > 0, so Z < thr*D needs D > 0.
@@ -348,7 +355,7 @@ __global__ void __launch_bounds__(kFilterThreads, kBilinear ? 3 : DDN_K4_MINBLOC
     any_live |= live[j];
   }
 
-  const unsigned wbits = __float_as_uint((float)p.W), hbits = __float_as_uint((float)p.H);
+  const unsigned wbits = p.wbits, hbits = p.hbits;
   const float thr = p.depth_threshold, gcos = p.grazing_cos, tau = p.two_sided_tau;
   const bool in_world = p.normals_in_world != 0;
   const int n_hot = __float_as_int(s_pair[22]), n_own = __float_as_int(s_pair[23]);
@@ -369,18 +376,25 @@ __global__ void __launch_bounds__(kFilterThreads, kBilinear ? 3 : DDN_K4_MINBLOC
         const float4* t4 = reinterpret_cast<const float4*>(s_pair + k * DDN_PAIR_TABLE_FLOATS);
         const float4 r0 = t4[0], r1 = t4[1], r2 = t4[2];
         const unsigned off_k = __float_as_uint(s_pair[k * DDN_PAIR_TABLE_FLOATS + 16]);
+        float Z[kFilterPX], D[kFilterPX];
+        bool inb[kFilterPX];
         if (all_live) {
 #pragma unroll
           for (int j = 0; j < kFilterPX; ++j)
-            if (pair_candidate<kBilinear, kTwoSided>(r0, r1, r2, P[j], Q[j], d[j], p.refined_all, off_k, (unsigned)p.W, p.H,
-                                                     wbits, hbits, thr, tau))
-              cm[j] |= bit;
-        } else {
+            pair_gather<kBilinear>(r0, r1, r2, P[j], Q[j], d[j], p.refined_all, off_k, (unsigned)p.W, p.H, wbits, hbits, Z[j], D[j],
+                                   inb[j]);
 #pragma unroll
           for (int j = 0; j < kFilterPX; ++j)
-            if (live[j] && pair_candidate<kBilinear, kTwoSided>(r0, r1, r2, P[j], Q[j], d[j], p.refined_all, off_k,
-                                                                (unsigned)p.W, p.H, wbits, hbits, thr, tau))
-              cm[j] |= bit;
+            if (pair_test<kTwoSided>(Z[j], D[j], inb[j], thr, tau)) cm[j] |= bit;
+        } else {
+#pragma unroll
+          for (int j = 0; j < kFilterPX; ++j) {
+            if (live[j]) {
+              pair_gather<kBilinear>(r0, r1, r2, P[j], Q[j], d[j], p.refined_all, off_k, (unsigned)p.W, p.H, wbits, hbits, Z[j],
+                                     D[j], inb[j]);
+              if (pair_test<kTwoSided>(Z[j], D[j], inb[j], thr, tau)) cm[j] |= bit;
+            }
+          }
         }
       }
       // dot(n, -(Xw - c_t)/|Xw - c_t|) > cos  <=>  dot(n, c_t - Xw) > cos * |c_t - Xw|
@@ -548,6 +562,11 @@ int ddn_backproject_filter(const ddn_filter_config* cfg, int64_t n_views_total, 
   p.grazing_cos = cfg->grazing_cos;
   p.two_sided_tau = cfg->two_sided_tau;
   p.normals_in_world = cfg->normals_in_world;
+  {
+    const float wf = (float)p.W, hf = (float)p.H;
+    memcpy(&p.wbits, &wf, 4);
+    memcpy(&p.hbits, &hf, 4);
+  }
   const int Ps = p.Hs * p.Ws;
   dim3 grid((Ps + kFilterChunk - 1) / kFilterChunk, (unsigned)n_src);
   DDN_REQUIRE(n_src <= 65535, "too many source views per call");
