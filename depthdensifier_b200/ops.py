@@ -339,3 +339,29 @@ def voxel_keys(xyz, voxel: float, origin) -> torch.Tensor:
     with torch.cuda.device(dev):
         _lib.check(lib.ddn_voxel_keys(C.byref(g), xyz.shape[0], _p(xyz), _p(keys), _stream()))
     return keys
+
+
+def project_points_device(points3d, cam_from_world34, kmat33):
+    """float64 device form of the reference's project_points (scripts/test.py:58-76)."""
+    lib = _lib.load()
+    dev = _require_cuda(points3d, cam_from_world34, kmat33)
+    n = points3d.shape[0]
+    assert points3d.dtype == torch.float64 and cam_from_world34.dtype == torch.float64 and kmat33.dtype == torch.float64
+    uv = torch.empty((n, 2), dtype=torch.float64, device=dev)
+    z = torch.empty(n, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ddn_project_points(n, _p(points3d), _p(cam_from_world34), _p(kmat33), _p(uv), _p(z), _stream()))
+    return uv, z
+
+
+def unproject_points_device(points2d, depth, params4):
+    """float64 device form of the reference's unproject_points (scripts/test.py:79-90); depth is float32."""
+    lib = _lib.load()
+    dev = _require_cuda(points2d, depth)
+    n = points2d.shape[0]
+    assert points2d.dtype == torch.float64 and depth.dtype == torch.float32 and len(params4) == 4
+    out = torch.empty((n, 3), dtype=torch.float64, device=dev)
+    par = (C.c_double * 4)(*[float(v) for v in params4])
+    with torch.cuda.device(dev):
+        _lib.check(lib.ddn_unproject_points(n, _p(points2d), _p(depth), par, _p(out), _stream()))
+    return out

@@ -142,6 +142,16 @@ DDN_API int ddn_backproject_filter(const ddn_filter_config* cfg, int64_t n_views
 
 DDN_API int ddn_bbox_init(float* bbox, void* stream);
 
+/* Stand-alone helpers with the reference script's own semantics, float64 (device arrays except params4_host):
+ * ddn_project_points   = project_points, scripts/test.py:58-76: points3d [N,3], cam_from_world [3,4],
+ *                        kmat [3,3] -> points2d [N,2], depths [N] (no validity handling, +1e-8 in the divide);
+ * ddn_unproject_points = unproject_points, scripts/test.py:79-90: points2d [N,2], depth [N] f32, PINHOLE
+ *                        params (fx, fy, cx, cy) on the HOST -> camera-frame points [N,3]. */
+DDN_API int ddn_project_points(int64_t n_points, const double* points3d, const double* cam_from_world,
+                       const double* kmat, double* points2d, double* depths, void* stream);
+DDN_API int ddn_unproject_points(int64_t n_points, const double* points2d, const float* depth,
+                         const double* params4_host, double* points3d_cam, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Stage 4 - voxel-grid fusion (new capability; the reference only concatenates,
  * scripts/test.py:353-359).  key = kx | ky<<21 | kz<<42 with k = floor((p - origin)/voxel) in
