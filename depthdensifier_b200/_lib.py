@@ -89,13 +89,14 @@ SYMBOLS = {
         C.c_int,
         [C.POINTER(VoxelGrid), _i64, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     ),
+    "ddn_fuse_tile_info": (C.c_int, [C.POINTER(VoxelGrid), C.POINTER(_i64), C.POINTER(_i64)]),
     "ddn_voxel_partials": (
         C.c_int,
-        [C.POINTER(VoxelGrid), _i64, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i64, _vp],
+        [C.POINTER(VoxelGrid), _i64, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i64, _vp],
     ),
     "ddn_voxel_merge": (
         C.c_int,
-        [C.POINTER(VoxelGrid), _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
+        [C.POINTER(VoxelGrid), _i64, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     ),
     "ddn_voxel_keys": (C.c_int, [C.POINTER(VoxelGrid), _i64, _vp, _vp, _vp]),
 }

@@ -19,6 +19,8 @@
 // Integer sums make the result independent of the order of points and of how they are split over
 // ranks (ddn_voxel_partials / ddn_voxel_merge use the same passes with a different output / input).
 // Grids with more than 2^35 cells take the sort path in fuse_sort.cu.
+#include <algorithm>
+
 #include "fuse_common.cuh"
 
 namespace ddn {
@@ -29,6 +31,10 @@ constexpr int kUnitBits = 96;
 constexpr int kUnitsPerThread = 8;
 constexpr int kScanThreads = 256;
 constexpr int kTileUnits = kScanThreads * kUnitsPerThread;  // units per CTA in the rank passes (32 KB)
+// Ownership granularity of the multi-GPU form: a "tile" of the C ABI is kOwnUnits consecutive units
+// (24,576 cells in key order), fine enough to cut a dense z-layer of the grid into balanced shares.
+constexpr int kOwnUnits = kScanThreads;
+constexpr int kOwnPerScanTile = kTileUnits / kOwnUnits;
 constexpr int kAccWords = 5;                                // sx, sy, sz, r:g, b:count (u64 each)
 // Partial-sum RECORD exchanged between ranks: {key, sx, sy, sz, r:g, b:count} = DDN_RECORD_WORDS u64.  In
 // partial mode the accumulators ARE words 1..5 of the output records (stride 6), so there is no
@@ -125,12 +131,13 @@ mark_points_kernel(GridDev g, float rv, int64_t n, const float* __restrict__ xyz
 
 __global__ void __launch_bounds__(256)
 mark_records_kernel(GridDev g, int64_t n, const uint64_t* __restrict__ records, uint32_t* __restrict__ units,
-                    unsigned long long* __restrict__ n_in) {
+                    uint64_t cell_begin, uint64_t cell_end, unsigned long long* __restrict__ n_in) {
   __shared__ int s_count;
   if (threadIdx.x == 0) s_count = 0;
   __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  const uint64_t cell = i < n ? cell_of_key(g, __ldg(records + i * kRecWords)) : kNoCell;
+  uint64_t cell = i < n ? cell_of_key(g, __ldg(records + i * kRecWords)) : kNoCell;
+  if (cell < cell_begin || cell >= cell_end) cell = kNoCell;  // not owned by this call's tile range
   if (cell != kNoCell) set_cell_bit(units, cell);
   const int c = __popc(__ballot_sync(0xffffffffu, cell != kNoCell));
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_count, c);
@@ -142,9 +149,9 @@ mark_records_kernel(GridDev g, int64_t n, const uint64_t* __restrict__ records, 
 __device__ __forceinline__ int popc3(const uint4& u) { return __popc(u.x) + __popc(u.y) + __popc(u.z); }
 
 __global__ void __launch_bounds__(kScanThreads)
-tile_count_kernel(const uint4* __restrict__ units, uint32_t n_units, uint32_t* __restrict__ tile_sums) {
+tile_count_kernel(const uint4* __restrict__ units, uint32_t n_units, uint32_t tile_begin, uint32_t* __restrict__ tile_sums) {
   __shared__ int s_warp[kScanThreads / 32];
-  const uint32_t base = blockIdx.x * kTileUnits;
+  const uint32_t base = (tile_begin + blockIdx.x) * kTileUnits;
   int sum = 0;
 #pragma unroll
   for (int j = 0; j < kUnitsPerThread; ++j) {
@@ -197,18 +204,31 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t* __restrict__ 
     if (threadIdx.x == 1023) s_carry = carry + s_warp[31];
     __syncthreads();
   }
-  if (threadIdx.x == 0) counts_out[1] = (int64_t)s_carry;
+  if (threadIdx.x == 0) {
+    counts_out[1] = (int64_t)s_carry;
+    tile_sums[tiles] = s_carry;  // exclusive prefix with the total appended: [tiles + 1] entries
+  }
 }
 
 // Per unit: exclusive rank prefix -> word w of the unit.  Per set bit: canonical key of the cell ->
 // keys[slot].  The cell coordinates are decoded once per non-empty unit and then stepped along x.
 __global__ void __launch_bounds__(kScanThreads)
-unit_prefix_kernel(GridDev g, uint4* __restrict__ units, uint32_t n_units, const uint32_t* __restrict__ tile_excl,
-                   uint64_t* __restrict__ keys, int key_stride) {
+unit_prefix_kernel(GridDev g, uint4* __restrict__ units, uint32_t n_units, uint32_t tile_begin,
+                   const uint32_t* __restrict__ tile_excl, uint64_t* __restrict__ keys, int key_stride,
+                   uint32_t* __restrict__ own_prefix, uint32_t own_tiles) {
   __shared__ uint32_t s_warp[kScanThreads / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t base = blockIdx.x * kTileUnits;
+  const uint32_t base = (tile_begin + blockIdx.x) * kTileUnits;
   uint32_t carry = tile_excl[blockIdx.x];
+  const uint32_t own0 = (tile_begin + blockIdx.x) * kOwnPerScanTile;
+  // empty tile (most of the grid is): its units keep the zero prefix word of the memset and are never
+  // looked up, nothing to emit
+  if (tile_excl[blockIdx.x + 1] == carry) {
+    if (own_prefix != nullptr && threadIdx.x <= kOwnPerScanTile && own0 + threadIdx.x <= own_tiles &&
+        (threadIdx.x < kOwnPerScanTile || blockIdx.x == gridDim.x - 1))
+      own_prefix[own0 + threadIdx.x] = carry;
+    return;
+  }
   const uint64_t nxy = (uint64_t)g.nx * (uint64_t)g.ny;
 #pragma unroll 1
   for (int j = 0; j < kUnitsPerThread; ++j) {
@@ -233,6 +253,7 @@ unit_prefix_kernel(GridDev g, uint4* __restrict__ units, uint32_t n_units, const
     }
     __syncthreads();
     uint32_t slot = carry + before + inc - cnt;
+    if (own_prefix != nullptr && threadIdx.x == 0 && own0 + j <= own_tiles) own_prefix[own0 + j] = carry;
     carry += total;
     if (ui < n_units) units[ui].w = slot;
     if (cnt) {
@@ -260,6 +281,8 @@ unit_prefix_kernel(GridDev g, uint4* __restrict__ units, uint32_t n_units, const
       }
     }
   }
+  if (own_prefix != nullptr && threadIdx.x == 0 && blockIdx.x == gridDim.x - 1 && own0 + kOwnPerScanTile <= own_tiles)
+    own_prefix[own0 + kOwnPerScanTile] = carry;  // total, when the ownership tiles end exactly at this scan tile
 }
 
 // accumulators of the counts[1] voxels -> 0 (device-side count, no host round trip)
@@ -393,12 +416,12 @@ accumulate_points_kernel(GridDev g, float rv, int64_t n, int row_len, const floa
 
 __global__ void __launch_bounds__(256)
 accumulate_records_kernel(GridDev g, int64_t n, const unsigned long long* __restrict__ records, const uint4* __restrict__ units,
-                          unsigned long long* __restrict__ accum) {
+                          uint64_t cell_begin, uint64_t cell_end, unsigned long long* __restrict__ accum) {
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
   const unsigned long long* r = records + i * kRecWords;
   const uint64_t cell = cell_of_key(g, __ldg(r));
-  if (cell == kNoCell) return;
+  if (cell == kNoCell || cell < cell_begin || cell >= cell_end) return;
   unsigned long long* a = accum + (size_t)slot_of_cell(cell, units) * kAccWords;
 #pragma unroll
   for (int q = 0; q < kAccWords; ++q) atomicAdd(a + q, __ldg(r + 1 + q));
@@ -438,7 +461,7 @@ __global__ void canonical_key_kernel(GridDev g, int64_t n, const float* __restri
 
 // ---- host side ---------------------------------------------------------------------------------
 struct DenseLayout {
-  uint64_t cells, n_units, tiles;
+  uint64_t cells, n_units, tiles, own_tiles;
   size_t units, units_bytes, tile_sums, accum, total;
 };
 
@@ -449,6 +472,7 @@ static void dense_layout(const GridDev& g, int64_t n, DenseLayout* L) {  // size
   L->cells = grid_cells(g);
   L->n_units = (L->cells + kUnitBits - 1) / kUnitBits;
   L->tiles = (L->n_units + kTileUnits - 1) / kTileUnits;
+  L->own_tiles = (L->n_units + kOwnUnits - 1) / kOwnUnits;
   const uint64_t max_vox = (uint64_t)n < L->cells ? (uint64_t)n : L->cells;
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -475,11 +499,25 @@ struct DenseSource {
 };
 
 // records_out != nullptr: partial mode (output = records, no finalisation); else final voxels.
+// tile range [tile_begin, tile_end) (records source only; 0, 0 = whole grid): only that slice of the occupancy
+// array is cleared / scanned and records outside it are ignored - an owner rank merges its key range at a
+// cost proportional to its share of the grid.  tile_prefix_out (optional): [tiles + 1] exclusive prefix of
+// the voxel count per tile, i.e. where each tile's records start in the sorted output.
 static int dense_fuse(const GridDev& g, int64_t n, const DenseSource& src, uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb,
                       int32_t* out_count, unsigned long long* records_out, int64_t* counts_out, void* workspace,
-                      int64_t workspace_bytes, cudaStream_t st) {
+                      int64_t workspace_bytes, cudaStream_t st, int64_t tile_begin = 0, int64_t tile_end = 0,
+                      uint32_t* tile_prefix_out = nullptr) {
   DenseLayout L;
   dense_layout(g, n, &L);
+  // ownership tiles -> owned cell range and the scan tiles that enclose it
+  if (tile_end <= 0) tile_begin = 0, tile_end = (int64_t)L.own_tiles;
+  DDN_REQUIRE(tile_begin >= 0 && tile_begin <= tile_end && tile_end <= (int64_t)L.own_tiles, "tile range");
+  const uint64_t cell_begin = (uint64_t)tile_begin * kOwnUnits * kUnitBits;
+  const uint64_t cell_end = (uint64_t)tile_end * kOwnUnits * kUnitBits;
+  const int64_t own_begin = tile_begin, own_end = tile_end;
+  tile_begin = own_begin / kOwnPerScanTile;
+  tile_end = (own_end + kOwnPerScanTile - 1) / kOwnPerScanTile;
+  const uint32_t n_tiles = own_end > own_begin ? (uint32_t)(tile_end - tile_begin) : 0u;
   if ((int64_t)L.total > workspace_bytes) {
     set_error("fuse workspace too small: %lld < %lld", (long long)workspace_bytes, (long long)L.total);
     return DDN_ERR_WORKSPACE_TOO_SMALL;
@@ -499,8 +537,12 @@ static int dense_fuse(const GridDev& g, int64_t n, const DenseSource& src, uint6
   const bool vec = points && ((uintptr_t)src.xyz % 16 == 0) && (src.votes == nullptr || (uintptr_t)src.votes % 4 == 0);
   DDN_REQUIRE((uintptr_t)zero_base % 16 == 0, "record / accumulator buffer must be 16-byte aligned");
 
-  DDN_TRY(check_cuda(cudaMemsetAsync(units, 0, L.units_bytes, st), "memset occupancy"));
   DDN_TRY(check_cuda(cudaMemsetAsync(counts_out, 0, 16, st), "memset counts"));
+  if (n_tiles == 0) return DDN_OK;
+  {
+    const size_t ub = (size_t)tile_begin * kTileUnits, ue = std::min((size_t)tile_end * kTileUnits, (size_t)L.n_units);
+    DDN_TRY(check_cuda(cudaMemsetAsync(units + ub, 0, (ue - ub) * 16, st), "memset occupancy"));
+  }
   if (points) {
     const unsigned mblocks = (unsigned)((n + 256 * kMarkPX - 1) / (256 * kMarkPX));
     if (vec)
@@ -510,16 +552,18 @@ static int dense_fuse(const GridDev& g, int64_t n, const DenseSource& src, uint6
       mark_points_kernel<false><<<mblocks, 256, 0, st>>>(g, rv, n, src.xyz, src.votes, src.thr, (uint32_t*)units,
                                                          (unsigned long long*)counts_out);
   } else {
-    mark_records_kernel<<<blocks, 256, 0, st>>>(g, n, (const uint64_t*)src.records, (uint32_t*)units, (unsigned long long*)counts_out);
+    mark_records_kernel<<<blocks, 256, 0, st>>>(g, n, (const uint64_t*)src.records, (uint32_t*)units, cell_begin, cell_end,
+                                                (unsigned long long*)counts_out);
   }
   DDN_TRY(after_launch("mark_kernel"));
-  tile_count_kernel<<<(unsigned)L.tiles, kScanThreads, 0, st>>>(units, (uint32_t)L.n_units, tile_sums);
+  tile_count_kernel<<<n_tiles, kScanThreads, 0, st>>>(units, (uint32_t)L.n_units, (uint32_t)tile_begin, tile_sums);
   DDN_TRY(after_launch("tile_count_kernel"));
-  tile_scan_kernel<<<1, 1024, 0, st>>>(tile_sums, (int)L.tiles, counts_out);
+  tile_scan_kernel<<<1, 1024, 0, st>>>(tile_sums, (int)n_tiles, counts_out);
   DDN_TRY(after_launch("tile_scan_kernel"));
   zero_accum_kernel<<<kNumSMs * 8, 256, 0, st>>>((ulonglong2*)zero_base, counts_out, stride);
   DDN_TRY(after_launch("zero_accum_kernel"));
-  unit_prefix_kernel<<<(unsigned)L.tiles, kScanThreads, 0, st>>>(g, units, (uint32_t)L.n_units, tile_sums, keys, partial ? kRecWords : 1);
+  unit_prefix_kernel<<<n_tiles, kScanThreads, 0, st>>>(g, units, (uint32_t)L.n_units, (uint32_t)tile_begin, tile_sums, keys,
+                                                       partial ? kRecWords : 1, tile_prefix_out, (uint32_t)L.own_tiles);
   DDN_TRY(after_launch("unit_prefix_kernel"));
   if (points) {
     const bool tiled = src.row_len >= 8 && src.row_len < (1 << 30);
@@ -531,7 +575,7 @@ static int dense_fuse(const GridDev& g, int64_t n, const DenseSource& src, uint6
     else
       accumulate_points_kernel<false><<<ablocks, 256, 0, st>>>(g, rv, n, 0, src.xyz, src.rgb, src.votes, src.thr, units, accum, stride);
   } else {
-    accumulate_records_kernel<<<blocks, 256, 0, st>>>(g, n, src.records, units, accum);
+    accumulate_records_kernel<<<blocks, 256, 0, st>>>(g, n, src.records, units, cell_begin, cell_end, accum);
   }
   DDN_TRY(after_launch("accumulate_kernel"));
   if (partial) return DDN_OK;
@@ -582,9 +626,24 @@ int ddn_voxel_fuse(const ddn_voxel_grid* grid_host, int64_t n_points, int64_t ro
   return dense_fuse(g, n_points, src, out_keys, out_xyz, out_rgb, out_count, nullptr, counts_out, workspace, workspace_bytes, st);
 }
 
+int ddn_fuse_tile_info(const ddn_voxel_grid* grid_host, int64_t* n_tiles, int64_t* cells_per_tile) {
+  using namespace ddn;
+  DDN_REQUIRE(n_tiles != nullptr && cells_per_tile != nullptr, "null output");
+  GridDev g;
+  DDN_TRY(grid_from_host(grid_host, &g));
+  *n_tiles = 0;
+  *cells_per_tile = (int64_t)kOwnUnits * kUnitBits;
+  if (use_dense(g)) {
+    DenseLayout L;
+    dense_layout(g, 1, &L);
+    *n_tiles = (int64_t)L.own_tiles;
+  }
+  return DDN_OK;
+}
+
 int ddn_voxel_partials(const ddn_voxel_grid* grid_host, int64_t n_points, int64_t row_len, const float* xyz, const uint8_t* rgb,
-                       const uint8_t* votes, int32_t vote_threshold, uint64_t* records, int64_t* counts_out,
-                       void* workspace, int64_t workspace_bytes, void* stream) {
+                       const uint8_t* votes, int32_t vote_threshold, uint64_t* records, uint32_t* tile_prefix,
+                       int64_t* counts_out, void* workspace, int64_t workspace_bytes, void* stream) {
   using namespace ddn;
   GridDev g;
   DDN_TRY(grid_from_host(grid_host, &g));
@@ -592,7 +651,14 @@ int ddn_voxel_partials(const ddn_voxel_grid* grid_host, int64_t n_points, int64_
   DDN_REQUIRE(row_len >= 0, "row_len");
   DDN_REQUIRE(counts_out != nullptr, "null counts_out");
   cudaStream_t st = (cudaStream_t)stream;
-  if (n_points == 0) return check_cuda(cudaMemsetAsync(counts_out, 0, 16, st), "memset counts");
+  if (n_points == 0) {
+    if (tile_prefix != nullptr && use_dense(g)) {
+      DenseLayout L;
+      dense_layout(g, 1, &L);
+      DDN_TRY(check_cuda(cudaMemsetAsync(tile_prefix, 0, (size_t)(L.own_tiles + 1) * 4, st), "memset tile prefix"));
+    }
+    return check_cuda(cudaMemsetAsync(counts_out, 0, 16, st), "memset counts");
+  }
   DDN_REQUIRE(xyz && rgb && records && workspace, "null pointer");
   if (!use_dense(g))
     return sort_fuse_points(g, n_points, xyz, rgb, votes, vote_threshold, nullptr, nullptr, nullptr, nullptr, counts_out, workspace,
@@ -600,12 +666,12 @@ int ddn_voxel_partials(const ddn_voxel_grid* grid_host, int64_t n_points, int64_
   DenseSource src;
   src.xyz = xyz, src.rgb = rgb, src.votes = votes, src.thr = vote_threshold, src.row_len = row_len;
   return dense_fuse(g, n_points, src, nullptr, nullptr, nullptr, nullptr, (unsigned long long*)records, counts_out, workspace,
-                    workspace_bytes, st);
+                    workspace_bytes, st, 0, 0, tile_prefix);
 }
 
-int ddn_voxel_merge(const ddn_voxel_grid* grid_host, int64_t n_records, const uint64_t* records, uint64_t* out_keys,
-                    float* out_xyz, uint8_t* out_rgb, int32_t* out_count, int64_t* counts_out, void* workspace,
-                    int64_t workspace_bytes, void* stream) {
+int ddn_voxel_merge(const ddn_voxel_grid* grid_host, int64_t n_records, const uint64_t* records, int64_t tile_begin,
+                    int64_t tile_end, uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb, int32_t* out_count,
+                    int64_t* counts_out, void* workspace, int64_t workspace_bytes, void* stream) {
   using namespace ddn;
   GridDev g;
   DDN_TRY(grid_from_host(grid_host, &g));
@@ -619,7 +685,8 @@ int ddn_voxel_merge(const ddn_voxel_grid* grid_host, int64_t n_records, const ui
                               workspace, workspace_bytes, st);
   DenseSource src;
   src.records = (const unsigned long long*)records;
-  return dense_fuse(g, n_records, src, out_keys, out_xyz, out_rgb, out_count, nullptr, counts_out, workspace, workspace_bytes, st);
+  return dense_fuse(g, n_records, src, out_keys, out_xyz, out_rgb, out_count, nullptr, counts_out, workspace, workspace_bytes, st,
+                    tile_begin, tile_end);
 }
 
 int ddn_voxel_keys(const ddn_voxel_grid* grid_host, int64_t n_points, const float* xyz, uint64_t* keys, void* stream) {

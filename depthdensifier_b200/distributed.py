@@ -153,11 +153,11 @@ class ShardedDensifier:
         if self.world > 1:
             import torch.distributed as dist
 
-            # order-preserving int encoding: min/max of the encodings == encodings of the min/max
-            lo3, hi3 = bbox[:3].clone(), bbox[3:].clone()
-            dist.all_reduce(lo3, op=dist.ReduceOp.MIN, group=self.group)
-            dist.all_reduce(hi3, op=dist.ReduceOp.MAX, group=self.group)
-            bb = self.ops.decode_bbox(torch.cat([lo3, hi3]))
+            # order-preserving int encoding: min/max of the encodings == encodings of the min/max; ~x reverses
+            # the order without overflow, so ONE all-reduce(MIN) over (lo, ~hi) does both
+            both = torch.cat([bbox[:3], ~bbox[3:]])
+            dist.all_reduce(both, op=dist.ReduceOp.MIN, group=self.group)
+            bb = self.ops.decode_bbox(torch.cat([both[:3], ~both[3:]]))
         return bb
 
     # -- pipeline ---------------------------------------------------------------------------------------
@@ -217,18 +217,41 @@ class ShardedDensifier:
     def _fuse_sharded(self, xyz, rgb, votes, grid, mark=None):
         if mark is None:
             mark = lambda name, fn: fn()
+        n_tiles, _ = self.ops.fuse_tile_info(grid)
+        tile_prefix = torch.empty(n_tiles + 1, dtype=torch.int32, device=self.device) if n_tiles > 0 else None
         rec, counts = mark("fuse_partials", lambda: self.ops.voxel_fuse_partial(
-            xyz.view(-1, 3), rgb.view(-1, 3), votes.view(-1), self.thr, grid, row_len=xyz.shape[2]))
-        return mark("fuse_exchange_merge", lambda: self._exchange_and_merge(rec, counts, grid, mark))
+            xyz.view(-1, 3), rgb.view(-1, 3), votes.view(-1), self.thr, grid, row_len=xyz.shape[2], tile_prefix=tile_prefix))
+        return mark("fuse_exchange_merge", lambda: self._exchange_and_merge(rec, counts, grid, mark, tile_prefix))
 
-    def _exchange_and_merge(self, rec, counts, grid, mark):
+    def _plan_by_tiles(self, tile_prefix):
+        """Ownership by tile ranges.  Every rank all-gathers the [n_tiles + 1] record prefix of its sorted
+        partial records; the R-1 cut tiles that balance the GLOBAL record count follow from the summed
+        prefixes, and the same table gives what every rank sends to and receives from every other - no key
+        sampling, no search, no separate count exchange.  One small collective, one readback."""
         import torch.distributed as dist
 
-        mv = int(counts[1].item())
-        rec = rec[:mv]
-        pk = rec[:, 0]
+        R, r = self.world, self.rank
+        flat = torch.empty(R * tile_prefix.numel(), dtype=torch.int32, device=self.device)
+        dist.all_gather_into_tensor(flat, tile_prefix.contiguous(), group=self.group)
+        allp = flat.view(R, -1).long()
+        cum = allp.sum(0)  # global number of records in tiles [0, t)
+        total = cum[-1]
+        targets = (total * torch.arange(1, R, device=self.device)) // R
+        cuts = torch.searchsorted(cum, targets, right=False).clamp_(0, cum.numel() - 1)
+        bnd = torch.cat([cuts.new_zeros(1), cuts, cuts.new_full((1,), cum.numel() - 1)])  # R + 1 tile boundaries
+        bnd = torch.cummax(bnd, 0).values
+        at = allp[:, bnd]  # [R, R + 1] record index of every rank at every boundary
+        send = at[r, 1:] - at[r, :-1]
+        recv = at[:, r + 1] - at[:, r]
+        host = torch.cat([send, recv, bnd[r:r + 2], at[r, -1:]]).cpu().tolist()  # the one readback
+        return host[:R], host[R:2 * R], (host[2 * R], host[2 * R + 1]), host[2 * R + 2]
+
+    def _plan_by_samples(self, rec, mv):
+        """Sort-path fallback (grids too large for tiles): R-1 sampled splitter keys."""
+        import torch.distributed as dist
+
         R = self.world
-        # sampled splitters: R-1 local quantile keys per rank -> global quantiles of the R*(R-1) samples
+        pk = rec[:mv, 0]
         if mv > 0:
             q = torch.linspace(0, mv - 1, R + 1, device=self.device)[1:-1].round().long()
             samples = pk[q]
@@ -243,8 +266,18 @@ class ShardedDensifier:
         send_counts = (bnd[1:] - bnd[:-1]).contiguous()
         recv_counts = torch.empty_like(send_counts)
         dist.all_to_all_single(recv_counts, send_counts, group=self.group)
-        both = torch.stack([send_counts, recv_counts]).cpu().tolist()  # one readback for both
-        sc, rc = both
+        sc, rc = torch.stack([send_counts, recv_counts]).cpu().tolist()
+        return sc, rc, (0, 0), mv
+
+    def _exchange_and_merge(self, rec, counts, grid, mark, tile_prefix=None):
+        import torch.distributed as dist
+
+        if tile_prefix is not None:
+            sc, rc, tile_range, mv = self._plan_by_tiles(tile_prefix)
+        else:
+            mv = int(counts[1].item())
+            sc, rc, tile_range, mv = self._plan_by_samples(rec, mv)
+        rec = rec[:mv]
         n_recv = int(sum(rc))
         W = rec.shape[1]
 
@@ -256,7 +289,7 @@ class ShardedDensifier:
             return out
 
         got = mark("fuse_alltoall", exchange)
-        k, x, c, n, mcounts = mark("fuse_merge", lambda: self.ops.voxel_merge_partials(got, grid))
+        k, x, c, n, mcounts = mark("fuse_merge", lambda: self.ops.voxel_merge_partials(got, grid, tile_range=tile_range))
         counts2 = torch.stack([counts[0], mcounts[1]])  # (points fused locally, voxels owned)
         return k, x, c, n, counts2
 

@@ -268,10 +268,19 @@ def voxel_fuse(xyz, rgb, votes, vote_threshold: int, grid: _lib.VoxelGrid, trim:
     return out_keys, out_xyz, out_rgb, out_cnt, counts
 
 
-def voxel_fuse_partial(xyz, rgb, votes, vote_threshold: int, grid: _lib.VoxelGrid, row_len: int = 0):
+def fuse_tile_info(grid: _lib.VoxelGrid) -> tuple[int, int]:
+    """(number of ownership tiles, cells per tile); 0 tiles = grid too large for the dense path."""
+    lib = _lib.load()
+    nt, cpt = C.c_int64(0), C.c_int64(0)
+    _lib.check(lib.ddn_fuse_tile_info(C.byref(grid), C.byref(nt), C.byref(cpt)))
+    return nt.value, cpt.value
+
+
+def voxel_fuse_partial(xyz, rgb, votes, vote_threshold: int, grid: _lib.VoxelGrid, row_len: int = 0, tile_prefix=None):
     """Rank-local stage 4: per-voxel partial RECORDS, keys ascending (layout: include/ddn_b200.h,
     ``unpack_records`` below).  Returns records [N, 6] i64 (sized for the worst case N) and the device
-    counts [2] = (participating points, local voxels)."""
+    counts [2] = (participating points, local voxels).  ``tile_prefix``: optional int32 [n_tiles + 1] output,
+    the index of each tile's first record."""
     lib = _lib.load()
     dev = _require_cuda(xyz, rgb, votes)
     N = xyz.shape[0]
@@ -284,8 +293,8 @@ def voxel_fuse_partial(xyz, rgb, votes, vote_threshold: int, grid: _lib.VoxelGri
     with torch.cuda.device(dev):
         _lib.check(
             lib.ddn_voxel_partials(
-                C.byref(grid), N, int(row_len), _p(xyz), _p(rgb), _p(votes), int(vote_threshold), _p(rec), _p(counts), _p(ws),
-                nbytes.value, _stream(),
+                C.byref(grid), N, int(row_len), _p(xyz), _p(rgb), _p(votes), int(vote_threshold), _p(rec), _p(tile_prefix),
+                _p(counts), _p(ws), nbytes.value, _stream(),
             )
         )
     return rec, counts
@@ -297,8 +306,9 @@ def unpack_records(rec):
     return rec[:, 0], rec[:, 1:4], (rec[:, 4] >> 32) & lo, rec[:, 4] & lo, (rec[:, 5] >> 32) & lo, rec[:, 5] & lo
 
 
-def voxel_merge_partials(records, grid: _lib.VoxelGrid, trim: bool = False):
-    """Owner-side merge of partial records [n, 6] i64 (any order) into final voxels."""
+def voxel_merge_partials(records, grid: _lib.VoxelGrid, trim: bool = False, tile_range: tuple[int, int] = (0, 0)):
+    """Owner-side merge of partial records [n, 6] i64 (any order) into final voxels.  ``tile_range``: the
+    tiles this rank owns ((0, 0) = all); records of other tiles are ignored."""
     lib = _lib.load()
     dev = _require_cuda(records)
     n = records.shape[0]
@@ -315,8 +325,8 @@ def voxel_merge_partials(records, grid: _lib.VoxelGrid, trim: bool = False):
     with torch.cuda.device(dev):
         _lib.check(
             lib.ddn_voxel_merge(
-                C.byref(grid), n, _p(records), _p(out_keys), _p(out_xyz), _p(out_rgb), _p(out_cnt), _p(counts), _p(ws),
-                nbytes.value, _stream(),
+                C.byref(grid), n, _p(records), int(tile_range[0]), int(tile_range[1]), _p(out_keys), _p(out_xyz), _p(out_rgb),
+                _p(out_cnt), _p(counts), _p(ws), nbytes.value, _stream(),
             )
         )
     if trim:

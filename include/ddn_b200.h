@@ -190,13 +190,25 @@ DDN_API int ddn_voxel_fuse(const ddn_voxel_grid* grid_host, int64_t n_points, in
  * records of equal key (any input order, e.g. the concatenation of the runs received from R ranks)
  * and finalises them.  records: [N, DDN_RECORD_WORDS] u64, 16-byte aligned, sized for the worst case. */
 #define DDN_RECORD_WORDS 6
+/* Ownership is by TILE: a tile is cells_per_tile consecutive cells of the grid in key order, so a range of
+ * tiles is a key range.  *n_tiles = 0 means the grid is too large for the dense path (no tiles: partition by
+ * sampled splitter keys instead). */
+DDN_API int ddn_fuse_tile_info(const ddn_voxel_grid* grid_host, int64_t* n_tiles, int64_t* cells_per_tile);
+
+/* tile_prefix (optional, dense path only): [n_tiles + 1] u32, tile_prefix[t] = index of the first record of
+ * tile t in `records` (the last entry is the record count) - what a rank needs to cut its records at tile
+ * boundaries without searching. */
 DDN_API int ddn_voxel_partials(const ddn_voxel_grid* grid_host, int64_t n_points, int64_t row_len, const float* xyz,
                        const uint8_t* rgb, const uint8_t* votes, int32_t vote_threshold, uint64_t* records,
-                       int64_t* counts_out, void* workspace, int64_t workspace_bytes, void* stream);
+                       uint32_t* tile_prefix, int64_t* counts_out, void* workspace, int64_t workspace_bytes,
+                       void* stream);
 
+/* [tile_begin, tile_end): the tiles this call owns (0, 0 = the whole grid).  Only that slice of the grid is
+ * scanned; records of other tiles are ignored. */
 DDN_API int ddn_voxel_merge(const ddn_voxel_grid* grid_host, int64_t n_records, const uint64_t* records,
-                    uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb, int32_t* out_count,
-                    int64_t* counts_out, void* workspace, int64_t workspace_bytes, void* stream);
+                    int64_t tile_begin, int64_t tile_end, uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb,
+                    int32_t* out_count, int64_t* counts_out, void* workspace, int64_t workspace_bytes,
+                    void* stream);
 
 /* Stand-alone pieces of stage 4 (used by the multi-GPU path and by tests). */
 DDN_API int ddn_voxel_keys(const ddn_voxel_grid* grid_host, int64_t n_points, const float* xyz,

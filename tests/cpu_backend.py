@@ -165,19 +165,39 @@ class OracleBackend:
         c = rgb.numpy().reshape(-1, 3)
         sel = votes.numpy().reshape(-1) < thr if votes is not None else np.ones(len(x), bool)
         k = np.floor((x - origin) / voxel)
-        inside = ((k >= 0) & (k < np.array([1 << b for b in bits]))).all(1)
+        inside = ((k >= 0) & (k < np.array([int(d) for d in grid.dims]))).all(1)
         sel = sel & inside
         return x[sel], c[sel], voxel, origin
 
-    def voxel_fuse_partial(self, xyz, rgb, votes, thr, grid, row_len=0):
+    CELLS_PER_TILE = 256 * 96  # kOwnUnits * kUnitBits (csrc/fuse.cu)
+
+    def fuse_tile_info(self, grid):
+        dims = [int(d) for d in grid.dims]
+        cells = dims[0] * dims[1] * dims[2]
+        return -(-(-(-cells // 96)) // 256), self.CELLS_PER_TILE
+
+    def _tile_of_keys(self, keys, grid):
+        nx, ny = int(grid.dims[0]), int(grid.dims[1])
+        k = keys.astype(np.int64)
+        cell = (k & 0x1FFFFF) + nx * (((k >> 21) & 0x1FFFFF) + ny * ((k >> 42) & 0x1FFFFF))
+        return cell // self.CELLS_PER_TILE
+
+    def voxel_fuse_partial(self, xyz, rgb, votes, thr, grid, row_len=0, tile_prefix=None):
         x, c, voxel, origin = self._select(xyz, rgb, votes, thr, grid)
         uk, sums, csum, cnt = partial_sums_numpy(x, c, voxel, origin)
         counts = torch.tensor([len(x), len(uk)], dtype=torch.int64)
+        if tile_prefix is not None:
+            tiles = self._tile_of_keys(uk, grid)
+            tile_prefix.copy_(torch.from_numpy(np.searchsorted(tiles, np.arange(tile_prefix.numel())).astype(np.int32)))
         return torch.from_numpy(pack_records(uk, sums, csum, cnt)), counts
 
-    def voxel_merge_partials(self, records, grid, trim=False):
+    def voxel_merge_partials(self, records, grid, trim=False, tile_range=(0, 0)):
         voxel, origin, _ = grid_tuple(grid)
-        pk, psum, prgb, pcnt = unpack_records(records.numpy())
+        rec = records.numpy()
+        if tile_range[1] > 0:
+            t = self._tile_of_keys(rec[:, 0], grid)
+            rec = rec[(t >= tile_range[0]) & (t < tile_range[1])]
+        pk, psum, prgb, pcnt = unpack_records(rec)
         uk, s, c, n = merge_numpy(pk, psum, prgb, pcnt)
         xyz, col = finalize_numpy(uk, s, c, n, voxel, origin)
         counts = torch.tensor([len(pk), len(uk)], dtype=torch.int64)

@@ -306,6 +306,20 @@ def test_voxel_partials_and_merge_bit_exact(lib_built):
     parts = [ops.voxel_fuse_partial(_cuda(xyz[a:b]), _cuda(rgb[a:b]), None, 1, grid) for a, b in ((0, h), (h, n))]
     cat = torch.cat([p[0][: int(p[1][1])] for p in parts]).contiguous()
     k, x, c, m, mc = ops.voxel_merge_partials(cat, grid, trim=True)
+    # ownership tiles: the prefix of records per tile, and merges restricted to tile ranges
+    from cpu_backend import OracleBackend
+
+    n_tiles, cells_per_tile = ops.fuse_tile_info(grid)
+    assert (n_tiles, cells_per_tile) == OracleBackend().fuse_tile_info(grid)
+    tp = torch.full((n_tiles + 1,), -7, dtype=torch.int32, device="cuda")
+    rec2, _ = ops.voxel_fuse_partial(_cuda(xyz), _cuda(rgb), None, 1, grid, tile_prefix=tp)
+    tiles_of = OracleBackend()._tile_of_keys(uk, grid)
+    assert np.array_equal(tp.cpu().numpy(), np.searchsorted(tiles_of, np.arange(n_tiles + 1)))
+    cut = int(np.searchsorted(np.cumsum(np.bincount(tiles_of, minlength=n_tiles)), len(uk) // 2))
+    halves = [ops.voxel_merge_partials(cat, grid, trim=True, tile_range=r) for r in ((0, cut), (cut, n_tiles))]
+    assert len(halves[0][0]) > 0 and len(halves[1][0]) > 0
+    for i in range(4):
+        assert np.array_equal(torch.cat([halves[0][i], halves[1][i]]).cpu().numpy(), (k, x, c, m)[i].cpu().numpy())
     full = ops.voxel_fuse(_cuda(xyz), _cuda(rgb), None, 1, grid)
     assert np.array_equal(k.cpu().numpy(), full[0].cpu().numpy()) and np.array_equal(m.cpu().numpy(), full[3].cpu().numpy())
     assert np.array_equal(x.cpu().numpy(), full[1].cpu().numpy()) and np.array_equal(c.cpu().numpy(), full[2].cpu().numpy())
