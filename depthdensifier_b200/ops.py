@@ -276,7 +276,8 @@ def fuse_tile_info(grid: _lib.VoxelGrid) -> tuple[int, int]:
     return nt.value, cpt.value
 
 
-def voxel_fuse_partial(xyz, rgb, votes, vote_threshold: int, grid: _lib.VoxelGrid, row_len: int = 0, tile_prefix=None):
+def voxel_fuse_partial(xyz, rgb, votes, vote_threshold: int, grid: _lib.VoxelGrid, row_len: int = 0, tile_prefix=None,
+                       out=None):
     """Rank-local stage 4: per-voxel partial RECORDS, keys ascending (layout: include/ddn_b200.h,
     ``unpack_records`` below).  Returns records [N, 6] i64 (sized for the worst case N) and the device
     counts [2] = (participating points, local voxels).  ``tile_prefix``: optional int32 [n_tiles + 1] output,
@@ -288,7 +289,11 @@ def voxel_fuse_partial(xyz, rgb, votes, vote_threshold: int, grid: _lib.VoxelGri
     nbytes = C.c_int64(0)
     _lib.check(lib.ddn_fuse_workspace_bytes(C.byref(grid), N, C.byref(nbytes)))
     ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
-    rec = torch.empty((max(N, 1), _lib.RECORD_WORDS), dtype=torch.int64, device=dev)
+    if out is not None:  # caller-provided record buffer (e.g. NVLink-visible symmetric memory)
+        assert out.dtype == torch.int64 and out.is_contiguous() and out.shape[0] >= N and out.shape[1] == _lib.RECORD_WORDS
+        rec = out
+    else:
+        rec = torch.empty((max(N, 1), _lib.RECORD_WORDS), dtype=torch.int64, device=dev)
     counts = torch.zeros(2, dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
         _lib.check(

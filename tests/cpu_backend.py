@@ -182,7 +182,7 @@ class OracleBackend:
         cell = (k & 0x1FFFFF) + nx * (((k >> 21) & 0x1FFFFF) + ny * ((k >> 42) & 0x1FFFFF))
         return cell // self.CELLS_PER_TILE
 
-    def voxel_fuse_partial(self, xyz, rgb, votes, thr, grid, row_len=0, tile_prefix=None):
+    def voxel_fuse_partial(self, xyz, rgb, votes, thr, grid, row_len=0, tile_prefix=None, out=None):
         x, c, voxel, origin = self._select(xyz, rgb, votes, thr, grid)
         uk, sums, csum, cnt = partial_sums_numpy(x, c, voxel, origin)
         counts = torch.tensor([len(x), len(uk)], dtype=torch.int64)
