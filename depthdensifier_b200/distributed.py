@@ -193,47 +193,35 @@ class ShardedDensifier:
         dist.all_to_all_single(recv, send, output_split_sizes=[c * hw for c in self.plan.recv_counts],
                                input_split_sizes=[len(s) * hw for s in self.plan.send_views], group=self.group)
 
-    def _align_ranges(self, depth, mask, sparse_xyz, sparse_offsets, out, ranges):
-        stats = []
-        for c0, c1 in ranges:
-            if c1 > c0:
-                _, s_c = self.ops.align_views(depth[c0:c1], None if mask is None else mask[c0:c1],
-                                              self.poses_slots[c0:c1].contiguous(), self.kmat[c0:c1].contiguous(), sparse_xyz,
-                                              sparse_offsets[c0:c1 + 1].contiguous(), self._max_sparse, self.cfg.align,
-                                              out=out[c0:c1])
-                stats.append((c0, s_c))
-        return stats
-
-    def _align_and_pull_halo(self, depth, mask, sparse_xyz, sparse_offsets, mark):
-        """Stage 1 + halo exchange over peer memory, overlapped: the views some peer needs (the two ends of the
-        contiguous block for ring-ordered cameras) are aligned first; after a device-side barrier the
-        neighbour maps are pulled from the peers' HBM on a side stream WHILE the interior views are aligned."""
+    def _interior_range(self) -> tuple[int, int]:
+        """Longest run [i0, i1) of own source views whose neighbours are all own views (no halo needed)."""
+        local = ((self.plan.nbr_slots < self.n_local)).all(axis=1)
+        best, i = (0, 0), 0
         n = self.n_local
-        buf, hdl, views = self.peer.buffer("refined", (self._slots_max, self.H, self.W), torch.float32)
-        refined_slots = buf[: self.n_slots]
-        need = np.zeros(n, dtype=bool)
-        for sv in self.plan.send_views:
-            need[sv] = True
-        idx = np.flatnonzero(need)
-        if len(idx):  # minimal head / tail ranges covering the views to publish
-            head_end = int(idx[idx < (n + 1) // 2].max()) + 1 if (idx < (n + 1) // 2).any() else 0
-            tail_begin = int(idx[idx >= (n + 1) // 2].min()) if (idx >= (n + 1) // 2).any() else n
-        else:
-            head_end, tail_begin = 0, n
+        while i < n:
+            if local[i]:
+                j = i
+                while j < n and local[j]:
+                    j += 1
+                if j - i > best[1] - best[0]:
+                    best = (i, j)
+                i = j
+            else:
+                i += 1
+        return best
+
+    def _pull_halo_async(self, refined_slots):
+        """Halo exchange over peer memory: after a device-side barrier (every rank's refined maps are in
+        place) the neighbour maps are pulled from the peers' HBM on a side stream, so the caller can keep
+        the main stream busy with the source views that need no halo.  Returns the join function."""
+        _, hdl, views = self.peer.buffer("refined", (self._slots_max, self.H, self.W), torch.float32)
         cur = torch.cuda.current_stream(self.device)
-        hdl.barrier()  # peers finished reading last step's maps before they are overwritten
-        st = mark("align_boundary", lambda: self._align_ranges(depth, mask, sparse_xyz, sparse_offsets, refined_slots,
-                                                               [(0, head_end), (tail_begin, n)]))
-        hdl.barrier()  # every rank's boundary views are in place
+        hdl.barrier()
         self._side.wait_stream(cur)
         with torch.cuda.stream(self._side):
             for slot, q, j in self._halo_src:
                 refined_slots[slot].copy_(views[q][j], non_blocking=True)
-        st += mark("align", lambda: self._align_ranges(depth, mask, sparse_xyz, sparse_offsets, refined_slots,
-                                                      [(head_end, tail_begin)]))
-        cur.wait_stream(self._side)
-        stats = torch.cat([s_c for _, s_c in sorted(st, key=lambda t: t[0])]) if st else torch.zeros((0, 8), dtype=torch.int32)
-        return refined_slots, stats
+        return lambda: cur.wait_stream(self._side)
 
     def _global_bbox(self, bbox: torch.Tensor) -> np.ndarray:
         bb = self.ops.decode_bbox(bbox) if self.world == 1 else None
@@ -265,18 +253,43 @@ class ShardedDensifier:
         if self._max_sparse is None:
             off = sparse_offsets.cpu().numpy()
             self._max_sparse = max(int(np.max(np.diff(off))) if len(off) > 1 else 1, 1)
+        join_halo = None
         if self.peer is not None:
-            refined_slots, stats = self._align_and_pull_halo(depth, mask, sparse_xyz, sparse_offsets, mark)
+            buf, hdl, _ = self.peer.buffer("refined", (self._slots_max, self.H, self.W), torch.float32)
+            refined_slots = buf[: self.n_slots]
+            hdl.barrier()  # peers finished reading last step's maps before they are overwritten
         else:
             refined_slots = torch.empty((self.n_slots, self.H, self.W), dtype=torch.float32, device=self.device)
-            _, stats = mark("align", lambda: self.ops.align_views(
-                depth, mask, self.poses_slots[: self.n_local].contiguous(), self.kmat, sparse_xyz, sparse_offsets,
-                self._max_sparse, cfg.align, out=refined_slots[: self.n_local]))
+        _, stats = mark("align", lambda: self.ops.align_views(
+            depth, mask, self.poses_slots[: self.n_local].contiguous(), self.kmat, sparse_xyz, sparse_offsets,
+            self._max_sparse, cfg.align, out=refined_slots[: self.n_local]))
+        if self.peer is not None:
+            join_halo = mark("halo_exchange", lambda: self._pull_halo_async(refined_slots))
+        else:
             mark("halo_exchange", lambda: self._exchange_halo(refined_slots))
         pair, src = mark("pair_tables", lambda: self.ops.build_pair_tables(self.poses_slots, self.intr_slots, self._nbr_full(), 0, self.n_local))
         bbox = self.ops.new_bbox(self.device)
-        xyz, votes = mark("backproject_filter", lambda: self.ops.backproject_filter(
-            refined_slots, normal, self.nbr_slots, pair, src, 0, self.thr, cfg.filter, bbox=bbox))
+        s_ = cfg.filter.stride
+        Hs, Ws = (self.H + s_ - 1) // s_, (self.W + s_ - 1) // s_
+        xyz = torch.empty((self.n_local, Hs, Ws, 3), dtype=torch.float32, device=self.device)
+        votes = torch.empty((self.n_local, Hs, Ws), dtype=torch.uint8, device=self.device)
+
+        def k4(c0, c1):
+            if c1 <= c0:
+                return
+            whole = c0 == 0 and c1 == self.n_local
+            self.ops.backproject_filter(refined_slots, normal if whole else normal[c0:c1], self.nbr_slots,
+                                        pair if whole else pair[c0:c1], src if whole else src[c0:c1], c0, self.thr, cfg.filter,
+                                        bbox=bbox, xyz_out=xyz[c0:c1], votes_out=votes[c0:c1])
+
+        if join_halo is not None:
+            # source views whose neighbours are all local run while the halo maps are still in flight
+            i0, i1 = self._interior_range()
+            mark("backproject_filter", lambda: k4(i0, i1))
+            join_halo()
+            mark("backproject_filter_boundary", lambda: (k4(0, i0), k4(i1, self.n_local)))
+        else:
+            mark("backproject_filter", lambda: k4(0, self.n_local))
         res = ShardResult(refined=refined_slots[: self.n_local], stats=stats, xyz=xyz, votes=votes, vote_threshold=self.thr,
                           bbox=bbox, events=ev)
         if cfg.voxel is None:

@@ -124,7 +124,8 @@ class OracleBackend:
     def new_bbox(self, dev):
         return torch.from_numpy(_encode([np.inf] * 3 + [-np.inf] * 3))
 
-    def backproject_filter(self, refined_all, normal, nbr, pair, src, src_begin, thr, opts, bbox=None):
+    def backproject_filter(self, refined_all, normal, nbr, pair, src, src_begin, thr, opts, bbox=None, xyz_out=None,
+                           votes_out=None):
         poses, intr, _ = pair
         nbr = nbr.numpy()
         ref = refined_all.numpy()
@@ -157,6 +158,12 @@ class OracleBackend:
             b = bbox.numpy()
             b[:3] = np.minimum(b[:3], enc[:3])
             b[3:] = np.maximum(b[3:], enc[3:])
+        if xyz_out is not None:
+            xyz_out.copy_(xyz)
+            xyz = xyz_out
+        if votes_out is not None:
+            votes_out.copy_(votes)
+            votes = votes_out
         return xyz, votes
 
     def _select(self, xyz, rgb, votes, thr, grid):
