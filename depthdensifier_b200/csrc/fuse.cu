@@ -348,15 +348,22 @@ accumulate_points_kernel(GridDev g, float rv, int64_t n, int row_len, const floa
     n_tiles = (uint32_t)((n + 31) / 32);
   }
   const int dx = lane & 7, dy = lane >> 3;
+  const uint32_t t_begin = warp * kAccTilesPerWarp;
+  if (t_begin >= n_tiles) return;
+  const uint32_t t_end = min(t_begin + (uint32_t)kAccTilesPerWarp, n_tiles);
   uint32_t ty = 0, tx = 0;
   if (kTiled) {
-    ty = (warp * kAccTilesPerWarp) / tiles_x;
-    tx = (warp * kAccTilesPerWarp) - ty * tiles_x;
+    ty = t_begin / tiles_x;
+    tx = t_begin - ty * tiles_x;
   }
-#pragma unroll 1
-  for (int q = 0; q < kAccTilesPerWarp; ++q) {
-    const uint32_t t = warp * kAccTilesPerWarp + q;
-    if (t >= n_tiles) break;  // warp-uniform
+  // The point of the NEXT tile is loaded (vote, position and colour at once - no dependent round trips)
+  // before the current tile is processed, so its latency hides behind the aggregation and the atomics.
+  struct In {
+    float x, y, z;
+    uint32_t rg, bb;
+    bool take;
+  };
+  auto load_tile = [&](uint32_t t) -> In {
     int64_t i;
     bool in;
     if (kTiled) {
@@ -368,21 +375,32 @@ accumulate_points_kernel(GridDev g, float rv, int64_t n, int row_len, const floa
       i = (int64_t)t * 32 + lane;
       in = i < n;
     }
-    const bool take = in && (votes == nullptr || (int)__ldg(votes + i) < thr);
+    In r = {0.f, 0.f, 0.f, 0u, 0u, false};
+    if (in) {
+      const int v = votes != nullptr ? (int)__ldg(votes + i) : 0;
+      r.x = __ldg(xyz + i * 3 + 0), r.y = __ldg(xyz + i * 3 + 1), r.z = __ldg(xyz + i * 3 + 2);
+      r.rg = ((uint32_t)__ldg(rgb + i * 3 + 0) << 16) | (uint32_t)__ldg(rgb + i * 3 + 1);
+      r.bb = (uint32_t)__ldg(rgb + i * 3 + 2);
+      r.take = v < thr || votes == nullptr;
+    }
+    return r;
+  };
+  In nxt = load_tile(t_begin);
+#pragma unroll 1
+  for (uint32_t t = t_begin; t < t_end; ++t) {
+    const In cur = nxt;
+    if (t + 1 < t_end) nxt = load_tile(t + 1);
     uint64_t cell = kNoCell;
     int ox = 0, oy = 0, oz = 0;
-    uint32_t rg = 0, bb = 0;
-    if (take) {
-      const float x = __ldg(xyz + i * 3 + 0), y = __ldg(xyz + i * 3 + 1), z = __ldg(xyz + i * 3 + 2);
+    const uint32_t rg = cur.rg, bb = cur.bb;
+    if (cur.take) {
       uint32_t kx, ky, kz;
-      cell = cell_of_point(g, rv, x, y, z, kx, ky, kz);
+      cell = cell_of_point(g, rv, cur.x, cur.y, cur.z, kx, ky, kz);
       if (cell != kNoCell) {
         // p - centre is exact in float32 for points inside the voxel
-        ox = voxel_offset_fix(x, voxel_centre(g.ox, kx, g.voxel), fix_scale);
-        oy = voxel_offset_fix(y, voxel_centre(g.oy, ky, g.voxel), fix_scale);
-        oz = voxel_offset_fix(z, voxel_centre(g.oz, kz, g.voxel), fix_scale);
-        rg = ((uint32_t)__ldg(rgb + i * 3 + 0) << 16) | (uint32_t)__ldg(rgb + i * 3 + 1);
-        bb = (uint32_t)__ldg(rgb + i * 3 + 2);
+        ox = voxel_offset_fix(cur.x, voxel_centre(g.ox, kx, g.voxel), fix_scale);
+        oy = voxel_offset_fix(cur.y, voxel_centre(g.oy, ky, g.voxel), fix_scale);
+        oz = voxel_offset_fix(cur.z, voxel_centre(g.oz, kz, g.voxel), fix_scale);
       }
     }
     const bool valid = cell != kNoCell;
