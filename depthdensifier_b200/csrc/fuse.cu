@@ -306,22 +306,6 @@ __device__ __forceinline__ uint32_t slot_of_cell(uint64_t cell, const uint4* __r
   return s;
 }
 
-struct RunAcc {
-  long long sx, sy, sz;
-  uint32_t r, g, b, n;
-};
-
-__device__ __forceinline__ void flush_run(uint64_t cell, const RunAcc& acc, const uint4* __restrict__ units,
-                                          unsigned long long* __restrict__ accum, int stride) {
-  if (cell == kNoCell || acc.n == 0) return;
-  unsigned long long* a = accum + (size_t)slot_of_cell(cell, units) * stride;
-  atomicAdd(a + 0, (unsigned long long)acc.sx);
-  atomicAdd(a + 1, (unsigned long long)acc.sy);
-  atomicAdd(a + 2, (unsigned long long)acc.sz);
-  atomicAdd(a + 3, ((unsigned long long)acc.r << 32) | acc.g);
-  atomicAdd(a + 4, ((unsigned long long)acc.b << 32) | acc.n);
-}
-
 // accumulate: one point per lane, aggregated ACROSS THE WARP before touching memory.  With a row length
 // (points are pixels of [rows, row_len] images) a warp covers an 8 x 4 pixel tile, otherwise 32
 // consecutive points.  Lanes whose points fall into the same cell are found with MATCH.ANY; every lane
