@@ -193,8 +193,11 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        # rank 0 prints ONE JSON line on stdout: keep NCCL's own messages (its version banner goes to stdout
+        # at any NCCL_DEBUG level) on stderr
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ.pop("NCCL_DEBUG")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
         dist.init_process_group("nccl", device_id=dev)
         dist.barrier()
