@@ -201,7 +201,7 @@ __device__ __forceinline__ void stage_floats(float* smem, float* gptr, int n) {
 // One (pixel, neighbour) evaluation, in two steps so that the gathers of a thread's four pixels are all in
 // flight before the first one is consumed.  pair_gather: project, bounds test, issue the depth lookup.
 // pair_test: the candidate flag ("would vote if the grazing gate passes").
-template <bool kBilinear>
+template <bool kBilinear, bool kFoldMask>
 __device__ __forceinline__ void pair_gather(const float4& r0, const float4& r1, const float4& r2, float P, float Q, float d,
                                             const float* __restrict__ depth_all, unsigned off_k, unsigned W, int H,
                                             unsigned wbits, unsigned hbits, float& Z, float& D, bool& inb) {
@@ -215,6 +215,7 @@ __device__ __forceinline__ void pair_gather(const float4& r0, const float4& r1, 
   // invalid pixels carry NaN depth, so Z > 0 rejects them too.
   inb = (__float_as_uint(u) < wbits) & (__float_as_uint(v) < hbits) & (Z > 0.f);
   const unsigned ub = (unsigned)trunc_biased(u), vb = (unsigned)trunc_biased(v);
+  if (kFoldMask && !inb) Z = INFINITY;  // folds the bounds mask into the one-sided test: inf < thr*D is false
   if (!kBilinear) {
     // 32-bit element offset from the start of refined_all; off_k = t*H*W - bias*(W+1) removes the 2^23
     // biases by modular arithmetic.  Out-of-bounds lanes read element 0 and are masked by `inb`.
@@ -234,6 +235,12 @@ __device__ __forceinline__ void pair_gather(const float4& r0, const float4& r1, 
                                 __fmul_rn(__fmul_rn(fxw, fyw), td));
     D = ((ta > 0.f) & (tb > 0.f) & (tc > 0.f) & (td > 0.f)) ? acc : 0.f;
   }
+}
+
+// cm |= bit when a < b, as one compare and one predicated OR (the compiler would otherwise build the bit with
+// two selects)
+__device__ __forceinline__ void or_bit_if_less(unsigned& cm, float a, float b, unsigned bit) {
+  asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(cm) : "f"(a), "f"(b), "r"(bit));
 }
 
 template <bool kTwoSided>
@@ -381,16 +388,21 @@ __global__ void __launch_bounds__(kFilterThreads, kBilinear ? 3 : DDN_K4_MINBLOC
         if (all_live) {
 #pragma unroll
           for (int j = 0; j < kFilterPX; ++j)
-            pair_gather<kBilinear>(r0, r1, r2, P[j], Q[j], d[j], p.refined_all, off_k, (unsigned)p.W, p.H, wbits, hbits, Z[j], D[j],
+            pair_gather<kBilinear, !kBilinear && !kTwoSided>(r0, r1, r2, P[j], Q[j], d[j], p.refined_all, off_k, (unsigned)p.W, p.H, wbits, hbits, Z[j], D[j],
                                    inb[j]);
 #pragma unroll
-          for (int j = 0; j < kFilterPX; ++j)
+          for (int j = 0; j < kFilterPX; ++j) {
+            if (!kBilinear && !kTwoSided) {
+              or_bit_if_less(cm[j], Z[j], __fmul_rn(thr, D[j]), bit);  // Z is +inf for out-of-bounds lanes
+              continue;
+            }
             if (pair_test<kTwoSided>(Z[j], D[j], inb[j], thr, tau)) cm[j] |= bit;
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < kFilterPX; ++j) {
             if (live[j]) {
-              pair_gather<kBilinear>(r0, r1, r2, P[j], Q[j], d[j], p.refined_all, off_k, (unsigned)p.W, p.H, wbits, hbits, Z[j],
+              pair_gather<kBilinear, !kBilinear && !kTwoSided>(r0, r1, r2, P[j], Q[j], d[j], p.refined_all, off_k, (unsigned)p.W, p.H, wbits, hbits, Z[j],
                                      D[j], inb[j]);
               if (pair_test<kTwoSided>(Z[j], D[j], inb[j], thr, tau)) cm[j] |= bit;
             }
