@@ -153,6 +153,26 @@ DDN_API int ddn_unproject_points(int64_t n_points, const double* points2d, const
                          const double* params4_host, double* points3d_cam, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Alternative stage 1: the per-pixel part of FastPCHIPRefiner, src/depthdensifier/fast_pchip_refiner.py
+ * (SURVEY.md 8(f) rank 3).  One view per call; the O(C) correspondence logic stays on the host as in the
+ * reference.
+ *
+ * ddn_pchip_edge_mask: _detect_depth_edges :226-273 (gray == NULL) or _detect_image_edges :187-224 (gray =
+ *   float64 grey image [H,W]).  gauss_weights_host[0..radius] = the normalised taps of scipy's Gaussian at
+ *   distance 0..radius (host array); normal [H,W,3] and mask [H,W] may be NULL.  edge_out [H,W] u8.
+ * ddn_pchip_apply: _apply_edge_aware_transformation :550-579 with the cubic-Hermite evaluation :300-366 for the
+ *   float32 knots (ascending x); mask and edge [H,W] u8; refined [H,W] f32.
+ * ------------------------------------------------------------------------------------------ */
+DDN_API int ddn_pchip_workspace_bytes(int64_t height, int64_t width, int64_t* bytes_out);
+DDN_API int ddn_pchip_edge_mask(int64_t height, int64_t width, const float* depth, const uint8_t* mask,
+                        const float* normal, const double* gray, const double* gauss_weights_host,
+                        int32_t radius, float edge_threshold, double image_edge_threshold, uint8_t* edge_out,
+                        void* workspace, int64_t workspace_bytes, void* stream);
+DDN_API int ddn_pchip_apply(int64_t height, int64_t width, const float* depth, const uint8_t* mask,
+                    const uint8_t* edge, const float* knots_x, const float* knots_y, int32_t n_knots,
+                    float* refined, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Stage 4 - voxel-grid fusion (new capability; the reference only concatenates,
  * scripts/test.py:353-359).  key = kx | ky<<21 | kz<<42 with k = floor((p - origin)/voxel) in
  * IEEE float32.

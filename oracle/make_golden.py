@@ -16,7 +16,7 @@ import numpy as np
 from depthdensifier_b200.hashperm import hash_perm
 from depthdensifier_b200.synthetic import SceneConfig, make_scene
 from oracle.restatement import kmatrix
-from oracle.run_reference import run_reference_main, run_reference_refiner
+from oracle.run_reference import run_reference_main, run_reference_pchip, run_reference_refiner
 
 GOLDEN = Path(__file__).resolve().parent.parent / "tests" / "golden"
 
@@ -90,6 +90,30 @@ def main():
             cases[f"{name}/{v}/scale"] = np.float64(r["scale_factor"])
     np.savez_compressed(GOLDEN / "ref_refiner_cases.npz", **a, **cases)
     print("ref_refiner_cases:", len(cases) // 4, "cases")
+
+    # (4) FastPCHIPRefiner.refine_depth cases (fast_pchip_refiner.py:386-548)
+    sc4 = make_scene(SceneConfig(n_views=2, width=176, height=128, n_sparse=900, seed=9))
+    b = scene_arrays(sc4)
+    pc = {}
+    pspecs = {
+        "default": dict(kw={}, mask=True, rgb=False, normal=True),
+        "mask_none_no_normal": dict(kw={}, mask=False, rgb=False, normal=False),
+        "image_edges": dict(kw=dict(use_image_edges=True, image_edge_threshold=12.0), mask=True, rgb=True, normal=True),
+        "not_robust_tight": dict(kw=dict(robust=False, edge_threshold=0.02, edge_margin=5), mask=True, rgb=False, normal=True),
+        "too_few": dict(kw=dict(min_correspondences=100000), mask=True, rgb=False, normal=True),
+        "too_few_after_outliers": dict(kw=dict(outlier_threshold=1e-9, min_correspondences=50), mask=True, rgb=False, normal=True),
+    }
+    for name, sp in pspecs.items():
+        for v in range(2):
+            lo, hi = int(b["sparse_offsets"][v]), int(b["sparse_offsets"][v + 1])
+            r = run_reference_pchip(
+                b["mono_depth"][v].copy(), b["normal"][v] if sp["normal"] else None, b["sparse_xyz"][lo:hi], b["cam_from_world"][v],
+                kmatrix(b["intrinsics"][v]), b["mask"][v] if sp["mask"] else None, rgb_image=b["rgb"][v] if sp["rgb"] else None, **sp["kw"])
+            pc[f"{name}/{v}/refined"] = np.asarray(r["refined_depth"], dtype=np.float32)
+            pc[f"{name}/{v}/scale"] = np.float64(r["scale"])
+            pc[f"{name}/{v}/iters"] = np.int64(r["num_iterations"])
+    np.savez_compressed(GOLDEN / "ref_pchip_cases.npz", **b, **pc)
+    print("ref_pchip_cases:", len(pc) // 3, "cases")
 
 
 if __name__ == "__main__":

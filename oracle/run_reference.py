@@ -167,3 +167,25 @@ def run_reference_main(scene, downsample_density=1, vote_threshold=5, depth_thre
         "kept_colors": np.array(rec.added_rgb, dtype=np.uint8).reshape(-1, 3),
     }
     return out
+
+
+def import_reference_pchip():
+    """The reference's fast_pchip_refiner module (it imports pycolmap at module top -> stand-in)."""
+    from . import standins
+
+    standins.install()
+    src = str(REFERENCE_ROOT / "src")
+    if src not in sys.path:
+        sys.path.insert(0, src)
+    import importlib
+
+    return importlib.import_module("depthdensifier.fast_pchip_refiner")
+
+
+def run_reference_pchip(depth, normal, points3D, cam_from_world, K, mask, rgb_image=None, **kwargs):
+    """Reference FastPCHIPRefiner.refine_depth (fast_pchip_refiner.py:386-548) on CPU."""
+    mod = import_reference_pchip()
+    kwargs.setdefault("verbose", 0)
+    ref = mod.FastPCHIPRefiner(**kwargs)
+    ref.device = "cpu"
+    return ref.refine_depth(depth, normal, points3D, cam_from_world, K, mask=mask, rgb_image=rgb_image)
