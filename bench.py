@@ -189,6 +189,11 @@ def main():
         ddn_build.build()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = None
+    if world > 1:  # keep each rank's pinned host buffers on the socket next to its GPU
+        from depthdensifier_b200.hostmem import bind_to_gpu_numa
+
+        numa_cpus = bind_to_gpu_numa(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -351,6 +356,7 @@ def main():
                        "l2": "inputs per step (>= 3.9 GB at cfg2) are far larger than the 126 MB L2; no explicit flush",
                        "valid_pixels": n_valid, "kept_points": n_kept, "voxels": n_vox},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+            "host_cpus_rank0": (f"{numa_cpus[0]}-{numa_cpus[-1]} ({len(numa_cpus)})" if numa_cpus else None),
             "clocks": clocks, "stages_ms": stage_ms,
             "stage_GBps_algorithmic": {
                 "align_remap": 9 * (hi - lo) * H * W / (stage_ms.get("align", float("nan")) * 1e-3) / 1e9,
