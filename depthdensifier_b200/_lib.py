@@ -88,6 +88,11 @@ SYMBOLS = {
         [_i64, _i64, _vp, _vp, _vp, _vp, C.POINTER(C.c_double), _i32, C.c_float, C.c_double, _vp, _vp, _i64, _vp],
     ),
     "ddn_pchip_apply": (C.c_int, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp]),
+    "ddn_gradient_mask": (
+        C.c_int,
+        [_i64, _i64, _vp, _vp, C.POINTER(C.c_float), _i32, C.c_float, C.c_float, _vp, _vp, _i64, _vp],
+    ),
+    "ddn_transform_normals": (C.c_int, [_i64, _vp, C.POINTER(C.c_double), _i32, _vp, _vp]),
     "ddn_project_points": (C.c_int, [_i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ddn_unproject_points": (C.c_int, [_i64, _vp, _vp, C.POINTER(C.c_double), _vp, _vp]),
     "ddn_fuse_workspace_bytes": (C.c_int, [C.POINTER(VoxelGrid), _i64, C.POINTER(_i64)]),

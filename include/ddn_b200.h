@@ -142,6 +142,21 @@ DDN_API int ddn_backproject_filter(const ddn_filter_config* cfg, int64_t n_views
 
 DDN_API int ddn_bbox_init(float* bbox, void* stream);
 
+/* Neighbouring per-pixel helpers.
+ * ddn_gradient_mask: compute_depth_normal_gradient_mask, src/depthdensifier/initilizer.py:236-328 - mask_out [H,W]
+ *   u8 = 1 where the Sobel magnitude of the (zero-padded, separable) Gaussian-smoothed depth relative to that depth
+ *   exceeds depth_threshold, or the torch.gradient magnitude over the three normal channels exceeds
+ *   normal_threshold.  taps_host: the n_taps (odd; 0 = no smoothing) float32 Gaussian taps; depth or normal may be
+ *   NULL; workspace >= two float planes + 512 bytes when smoothing.
+ * ddn_transform_normals: COLMAPVisualizer._transform_normals, src/depthdensifier/visualizer.py:346-376 -
+ *   normal_world [N,3] f64 = normalise(R^T n_cam); cam_from_world_host is a row-major [3,4] or [4,4] HOST matrix
+ *   (row_stride 4) or a 3x3 rotation (row_stride 3). */
+DDN_API int ddn_gradient_mask(int64_t height, int64_t width, const float* depth, const float* normal,
+                      const float* taps_host, int32_t n_taps, float depth_threshold, float normal_threshold,
+                      uint8_t* mask_out, void* workspace, int64_t workspace_bytes, void* stream);
+DDN_API int ddn_transform_normals(int64_t n_points, const float* normal_cam, const double* cam_from_world_host,
+                          int32_t row_stride, double* normal_world, void* stream);
+
 /* Stand-alone helpers with the reference script's own semantics, float64 (device arrays except params4_host):
  * ddn_project_points   = project_points, scripts/test.py:58-76: points3d [N,3], cam_from_world [3,4],
  *                        kmat [3,3] -> points2d [N,2], depths [N] (no validity handling, +1e-8 in the divide);

@@ -115,6 +115,26 @@ def main():
     np.savez_compressed(GOLDEN / "ref_pchip_cases.npz", **b, **pc)
     print("ref_pchip_cases:", len(pc) // 3, "cases")
 
+    # (5) compute_depth_normal_gradient_mask (initilizer.py:236-328) on the same maps
+    import importlib.util
+
+    import torch
+    from oracle.run_reference import REFERENCE_ROOT
+
+    spec = importlib.util.spec_from_file_location("ddn_reference_init", REFERENCE_ROOT / "src" / "depthdensifier" / "initilizer.py")
+    init = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(init)
+    mc = {"mono_depth": b["mono_depth"], "normal": b["normal"]}
+    for name, kw in {"default": {}, "tight": dict(depth_threshold=0.02, normal_threshold=0.1, edge_sigma=2.0),
+                     "no_blur": dict(edge_sigma=0.0, depth_threshold=0.05)}.items():
+        for v in range(2):
+            for with_normal in (True, False):
+                m = init.compute_depth_normal_gradient_mask(torch.from_numpy(b["mono_depth"][v]),
+                                                            torch.from_numpy(b["normal"][v]) if with_normal else None, **kw)
+                mc[f"{name}/{v}/{int(with_normal)}"] = m.numpy()
+    np.savez_compressed(GOLDEN / "ref_mask_cases.npz", **mc)
+    print("ref_mask_cases:", len(mc) - 2, "cases")
+
 
 if __name__ == "__main__":
     main()
