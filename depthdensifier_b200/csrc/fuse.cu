@@ -11,7 +11,7 @@
 //   rank        popcount scan over the occupancy: one exclusive prefix per 96-bit unit, stored in the
 //               unit's fourth word; the pass also emits the sorted keys
 //   accumulate  integer fixed-point sums per voxel with 64-bit RED.ADD.  The L2 atomic units bound this
-//               pass, so a warp first merges the points of its 8 x 4 pixel tile that share a cell
+//               pass, so a warp first merges the points of its 16 x 2 pixel tile that share a cell
 //               (MATCH.ANY + shuffles); the group's first lane looks the slot up (ONE 16 B load:
 //               96 bits + prefix) and issues the atomics.
 //   finalize    one thread per voxel: mean = centre + sum/count, colour = round-half-up
@@ -307,14 +307,15 @@ __device__ __forceinline__ uint32_t slot_of_cell(uint64_t cell, const uint4* __r
 }
 
 // accumulate: one point per lane, aggregated ACROSS THE WARP before touching memory.  With a row length
-// (points are pixels of [rows, row_len] images) a warp covers an 8 x 4 pixel tile, otherwise 32
-// consecutive points.  Lanes whose points fall into the same cell are found with MATCH.ANY; every lane
+// (points are pixels of [rows, row_len] images) a warp covers a 16 x 2 pixel tile, otherwise 32
+// consecutive points (the tile shape is kAccTileW).  Lanes whose points fall into the same cell are found with MATCH.ANY; every lane
 // walks its peer mask with shuffles (32-bit partial sums: at most 32 points of |offset| <= 2^19), and
 // the lowest lane of each group looks the slot up and issues the five 64-bit REDs.  The L2 atomic units
-// are the bound of this pass, so points per RED group is what matters: ~3 for 8 x 4 tiles at cfg 2.
+// are the bound of this pass, so points per RED group is what matters: ~2 at cfg 2.
 constexpr int kAccTilesPerWarp = 8;
+constexpr int kAccTileW = 16;  // pixel tile of a warp: 16 x 2 (measured at cfg 2: 4 x 8 4.46, 8 x 4 4.35, 16 x 2 4.34, 32 x 1 4.54 ms)
 
-template <bool kTiled>
+template <int kTW>  // tile width in pixels (tile = kTW x 32/kTW); 0 = no row structure, 32 consecutive points
 __global__ void __launch_bounds__(256)
 accumulate_points_kernel(GridDev g, float rv, int64_t n, int row_len, const float* __restrict__ xyz,
                          const uint8_t* __restrict__ rgb, const uint8_t* __restrict__ votes, int thr,
@@ -323,15 +324,17 @@ accumulate_points_kernel(GridDev g, float rv, int64_t n, int row_len, const floa
   const float fix_scale = voxel_fix_scale(g.voxel);
   // n < 2^31, so tile indices fit 32 bits
   const uint32_t warp = blockIdx.x * 8u + (threadIdx.x >> 5);
+  constexpr bool kTiled = kTW > 0;
+  constexpr int kTWs = kTiled ? kTW : 32, kTH = 32 / kTWs;
   uint32_t tiles_x = 0, n_tiles;
   if (kTiled) {
-    tiles_x = ((uint32_t)row_len + 7u) / 8u;
+    tiles_x = ((uint32_t)row_len + kTWs - 1u) / kTWs;
     const uint32_t n_rows = (uint32_t)((n + row_len - 1) / row_len);
-    n_tiles = tiles_x * ((n_rows + 3u) / 4u);
+    n_tiles = tiles_x * ((n_rows + kTH - 1u) / kTH);
   } else {
     n_tiles = (uint32_t)((n + 31) / 32);
   }
-  const int dx = lane & 7, dy = lane >> 3;
+  const int dx = lane % kTWs, dy = lane / kTWs;
   const uint32_t t_begin = warp * kAccTilesPerWarp;
   if (t_begin >= n_tiles) return;
   const uint32_t t_end = min(t_begin + (uint32_t)kAccTilesPerWarp, n_tiles);
@@ -351,8 +354,8 @@ accumulate_points_kernel(GridDev g, float rv, int64_t n, int row_len, const floa
     int64_t i;
     bool in;
     if (kTiled) {
-      const int x = (int)tx * 8 + dx;
-      i = (int64_t)(ty * 4u + dy) * row_len + x;
+      const int x = (int)tx * kTWs + dx;
+      i = (int64_t)(ty * kTH + dy) * row_len + x;
       in = x < row_len && i < n;
       if (++tx == tiles_x) tx = 0, ++ty;
     } else {
@@ -568,14 +571,15 @@ static int dense_fuse(const GridDev& g, int64_t n, const DenseSource& src, uint6
                                                        partial ? kRecWords : 1, tile_prefix_out, (uint32_t)L.own_tiles);
   DDN_TRY(after_launch("unit_prefix_kernel"));
   if (points) {
-    const bool tiled = src.row_len >= 8 && src.row_len < (1 << 30);
-    const int64_t n_tiles = tiled ? ((src.row_len + 7) / 8) * (((n + src.row_len - 1) / src.row_len + 3) / 4) : (n + 31) / 32;
+    const bool tiled = src.row_len >= 32 && src.row_len < (1 << 30);
+    const int tw = tiled ? kAccTileW : 0;
+    const int th = tw ? 32 / tw : 1, twe = tw ? tw : 32;
+    const int64_t n_tiles = tiled ? ((src.row_len + twe - 1) / twe) * (((n + src.row_len - 1) / src.row_len + th - 1) / th) : (n + 31) / 32;
     const unsigned ablocks = (unsigned)((n_tiles + 8 * kAccTilesPerWarp - 1) / (8 * kAccTilesPerWarp));
-    if (tiled)
-      accumulate_points_kernel<true><<<ablocks, 256, 0, st>>>(g, rv, n, (int)src.row_len, src.xyz, src.rgb, src.votes, src.thr, units,
-                                                              accum, stride);
-    else
-      accumulate_points_kernel<false><<<ablocks, 256, 0, st>>>(g, rv, n, 0, src.xyz, src.rgb, src.votes, src.thr, units, accum, stride);
+#define DDN_ACC(TW) accumulate_points_kernel<TW><<<ablocks, 256, 0, st>>>(g, rv, n, (int)src.row_len, src.xyz, src.rgb, src.votes, src.thr, units, accum, stride)
+    if (tw == kAccTileW) DDN_ACC(kAccTileW);
+    else DDN_ACC(0);
+#undef DDN_ACC
   } else {
     accumulate_records_kernel<<<blocks, 256, 0, st>>>(g, n, src.records, units, cell_begin, cell_end, accum);
   }
