@@ -172,6 +172,13 @@ class ShardedDensifier:
                     q = next(i for i, (a, b) in enumerate(bounds) if a <= v < b)
                     self._halo_src.append((self.n_local + j, q, int(v) - bounds[q][0]))
                 self._side = torch.cuda.Stream(device=self.device)
+                # allocate and map both exchange buffers now (collective): a platform without symmetric memory
+                # fails here, on every rank alike, and the collectives take over
+                s_ = cfg.filter.stride
+                self.peer_records_shape = (self._local_max * ((height + s_ - 1) // s_) * ((width + s_ - 1) // s_), 6)
+                self.peer.buffer("refined", (self._slots_max, self.H, self.W), torch.float32)
+                if cfg.voxel is not None:
+                    self.peer.buffer("records", self.peer_records_shape, torch.int64)
             except Exception as e:  # pragma: no cover - depends on the platform
                 print(f"[depthdensifier_b200] symmetric memory unavailable ({e!r}); using NCCL collectives")
                 self.peer = None
@@ -253,43 +260,11 @@ class ShardedDensifier:
         if self._max_sparse is None:
             off = sparse_offsets.cpu().numpy()
             self._max_sparse = max(int(np.max(np.diff(off))) if len(off) > 1 else 1, 1)
-        join_halo = None
-        if self.peer is not None:
-            buf, hdl, _ = self.peer.buffer("refined", (self._slots_max, self.H, self.W), torch.float32)
-            refined_slots = buf[: self.n_slots]
-            hdl.barrier()  # peers finished reading last step's maps before they are overwritten
-        else:
-            refined_slots = torch.empty((self.n_slots, self.H, self.W), dtype=torch.float32, device=self.device)
+        refined_slots = self._new_refined_slots()
         _, stats = mark("align", lambda: self.ops.align_views(
             depth, mask, self.poses_slots[: self.n_local].contiguous(), self.kmat, sparse_xyz, sparse_offsets,
             self._max_sparse, cfg.align, out=refined_slots[: self.n_local]))
-        if self.peer is not None:
-            join_halo = mark("halo_exchange", lambda: self._pull_halo_async(refined_slots))
-        else:
-            mark("halo_exchange", lambda: self._exchange_halo(refined_slots))
-        pair, src = mark("pair_tables", lambda: self.ops.build_pair_tables(self.poses_slots, self.intr_slots, self._nbr_full(), 0, self.n_local))
-        bbox = self.ops.new_bbox(self.device)
-        s_ = cfg.filter.stride
-        Hs, Ws = (self.H + s_ - 1) // s_, (self.W + s_ - 1) // s_
-        xyz = torch.empty((self.n_local, Hs, Ws, 3), dtype=torch.float32, device=self.device)
-        votes = torch.empty((self.n_local, Hs, Ws), dtype=torch.uint8, device=self.device)
-
-        def k4(c0, c1):
-            if c1 <= c0:
-                return
-            whole = c0 == 0 and c1 == self.n_local
-            self.ops.backproject_filter(refined_slots, normal if whole else normal[c0:c1], self.nbr_slots,
-                                        pair if whole else pair[c0:c1], src if whole else src[c0:c1], c0, self.thr, cfg.filter,
-                                        bbox=bbox, xyz_out=xyz[c0:c1], votes_out=votes[c0:c1])
-
-        if join_halo is not None:
-            # source views whose neighbours are all local run while the halo maps are still in flight
-            i0, i1 = self._interior_range()
-            mark("backproject_filter", lambda: k4(i0, i1))
-            join_halo()
-            mark("backproject_filter_boundary", lambda: (k4(0, i0), k4(i1, self.n_local)))
-        else:
-            mark("backproject_filter", lambda: k4(0, self.n_local))
+        xyz, votes, bbox = self._halo_and_filter(refined_slots, normal, mark)
         res = ShardResult(refined=refined_slots[: self.n_local], stats=stats, xyz=xyz, votes=votes, vote_threshold=self.thr,
                           bbox=bbox, events=ev)
         if cfg.voxel is None:
@@ -310,6 +285,49 @@ class ShardedDensifier:
         res.grid, res.voxel_keys, res.voxel_xyz, res.voxel_rgb, res.voxel_count, res.counts = grid, k, x, c, n, counts
         return res
 
+    def _new_refined_slots(self) -> torch.Tensor:
+        """[n_slots,H,W] buffer for own + halo refined maps; NVLink-visible when peer memory is in use."""
+        if self.peer is not None:
+            buf, hdl, _ = self.peer.buffer("refined", (self._slots_max, self.H, self.W), torch.float32)
+            hdl.barrier()  # peers finished reading last step's maps before they are overwritten
+            return buf[: self.n_slots]
+        return torch.empty((self.n_slots, self.H, self.W), dtype=torch.float32, device=self.device)
+
+    def _halo_and_filter(self, refined_slots, normal, mark, wait_normal=None):
+        """Halo exchange + stages 2-3.  With peer memory the halo maps are pulled on a side stream while K4
+        already runs on the source views whose neighbours are all local."""
+        cfg = self.cfg
+        join_halo = None
+        if self.peer is not None:
+            join_halo = mark("halo_exchange", lambda: self._pull_halo_async(refined_slots))
+        else:
+            mark("halo_exchange", lambda: self._exchange_halo(refined_slots))
+        pair, src = mark("pair_tables", lambda: self.ops.build_pair_tables(self.poses_slots, self.intr_slots, self._nbr_full(), 0, self.n_local))
+        bbox = self.ops.new_bbox(self.device)
+        s_ = cfg.filter.stride
+        Hs, Ws = (self.H + s_ - 1) // s_, (self.W + s_ - 1) // s_
+        xyz = torch.empty((self.n_local, Hs, Ws, 3), dtype=torch.float32, device=self.device)
+        votes = torch.empty((self.n_local, Hs, Ws), dtype=torch.uint8, device=self.device)
+        if wait_normal is not None:
+            wait_normal()
+
+        def k4(c0, c1):
+            if c1 <= c0:
+                return
+            whole = c0 == 0 and c1 == self.n_local
+            self.ops.backproject_filter(refined_slots, normal if whole else normal[c0:c1], self.nbr_slots,
+                                        pair if whole else pair[c0:c1], src if whole else src[c0:c1], c0, self.thr, cfg.filter,
+                                        bbox=bbox, xyz_out=xyz[c0:c1], votes_out=votes[c0:c1])
+
+        if join_halo is not None:
+            i0, i1 = self._interior_range()
+            mark("backproject_filter", lambda: k4(i0, i1))
+            join_halo()
+            mark("backproject_filter_boundary", lambda: (k4(0, i0), k4(i1, self.n_local)))
+        else:
+            mark("backproject_filter", lambda: k4(0, self.n_local))
+        return xyz, votes, bbox
+
     def _nbr_full(self) -> torch.Tensor:
         """Neighbour table padded to n_slots rows (build_pair_tables indexes it by global slot)."""
         if self.n_slots == self.n_local:
@@ -324,8 +342,6 @@ class ShardedDensifier:
         tile_prefix = torch.empty(n_tiles + 1, dtype=torch.int32, device=self.device) if n_tiles > 0 else None
         rec_out = None
         if self.peer is not None and tile_prefix is not None:
-            n_max = self._local_max * xyz.shape[1] * xyz.shape[2]
-            self.peer_records_shape = (n_max, 6)
             rec_out, hdl, _ = self.peer.buffer("records", self.peer_records_shape, torch.int64)
             hdl.barrier()  # peers finished pulling last step's records
         rec, counts = mark("fuse_partials", lambda: self.ops.voxel_fuse_partial(
@@ -477,7 +493,7 @@ class ShardedDensifier:
         with torch.cuda.stream(copy):
             upload(st["sparse_xyz"], sparse_xyz)
             upload(st["sparse_offsets"], sparse_offsets)
-        refined_slots = torch.empty((self.n_slots, self.H, self.W), dtype=torch.float32, device=self.device)
+        refined_slots = self._new_refined_slots()
         poses_local = self.poses_slots[:n]
         stats = []
         for c0 in range(0, n, max(int(chunk_views), 1)):
@@ -505,11 +521,7 @@ class ShardedDensifier:
             upload(st["rgb"], rgb)
             ev_rgb = torch.cuda.Event()
             ev_rgb.record(copy)
-        self._exchange_halo(refined_slots)
-        pair, src = self.ops.build_pair_tables(self.poses_slots, self.intr_slots, self._nbr_full(), 0, n)
-        bbox = self.ops.new_bbox(self.device)
-        comp.wait_event(ev_n)
-        xyz, votes = self.ops.backproject_filter(refined_slots, normal_arg, self.nbr_slots, pair, src, 0, self.thr, cfg.filter, bbox=bbox)
+        xyz, votes, bbox = self._halo_and_filter(refined_slots, normal_arg, lambda name, fn: fn(), wait_normal=lambda: comp.wait_event(ev_n))
         out = {"h2d_bytes": h2d, "d2h_bytes": 0, "num_points": 0, "stats": torch.cat(stats) if stats else None}
         if cfg.voxel is None:
             torch.cuda.synchronize(self.device)

@@ -34,8 +34,11 @@ def main():
     nbr = nearest_views_table(sc.cam_from_world.numpy(), K)
     off = sc.sparse_offsets.numpy()
 
+    sharded = {}
+
     def run(r, w, lo, hi, group):
         sd = ShardedDensifier(DensifyConfig(voxel=voxel), dev, r, w, V, lo, hi, sc.cam_from_world, sc.intrinsics, nbr, H, W)
+        sharded[w] = sd
         res = sd.run(sc.mono_depth[lo:hi].to(dev), sc.normal[lo:hi].to(dev), sc.mask[lo:hi].to(dev), sc.rgb[lo:hi].to(dev),
                      sc.sparse_xyz[off[lo]:off[hi]].to(dev), (sc.sparse_offsets[lo:hi + 1] - off[lo]).to(dev))
         mv = int(res.counts[1])
@@ -57,6 +60,20 @@ def main():
             print(f"{k:8s} {'identical' if same else 'DIFFERENT'}  {cat[k].shape}")
         ok &= sum(g["n"] for g in gathered) == one["n"]
         print("voxels per rank:", [len(g["keys"]) for g in gathered], "points:", one["n"])
+    # the end-to-end host entry point (pinned host arrays, normals read in place, peer-memory exchanges) must give the same cloud
+    sd = sharded[world]
+    host = sd.pin_host_inputs(sc.mono_depth[lo:hi], sc.normal[lo:hi], sc.mask[lo:hi], sc.rgb[lo:hi], sc.sparse_xyz[off[lo]:off[hi]],
+                              sc.sparse_offsets[lo:hi + 1] - off[lo])
+    for _ in range(2):
+        out = sd.run_host(*host, chunk_views=5)
+    mine_h = {k: out[k].numpy().copy() for k in ("keys", "xyz", "rgb", "count")} if "keys" in out else None
+    gathered_h = [None] * world
+    dist.gather_object(mine_h, gathered_h if rank == 0 else None, dst=0)
+    if rank == 0:
+        for k in ("keys", "count", "rgb", "xyz"):
+            same = np.array_equal(np.concatenate([g[k] for g in gathered_h]), one[k])
+            ok &= same
+            print(f"run_host {k:6s} {'identical' if same else 'DIFFERENT'}")
         print("MULTI-GPU CHECK", "PASSED" if ok else "FAILED")
     dist.barrier()
     dist.destroy_process_group()
