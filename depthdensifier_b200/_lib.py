@@ -9,8 +9,11 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+import os
+
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "libddn_b200.so"
+# DDN_LIB_PATH: load another build of the same library (kernel tuning experiments: build.py --suffix)
+LIB_PATH = Path(os.environ["DDN_LIB_PATH"]) if os.environ.get("DDN_LIB_PATH") else PKG_DIR / "libddn_b200.so"
 
 
 class DDNError(RuntimeError):

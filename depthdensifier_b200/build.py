@@ -42,13 +42,16 @@ def needs_build() -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, suffix: str = "") -> Path:
+    """``suffix``: build a variant next to the product library (libddn_b200<suffix>.so, own object directory) with
+    the flags in $DDN_NVCC_EXTRA, e.g. -DDDN_K4_MINBLOCKS=4; load it with DDN_LIB_PATH.  Tuning experiments only."""
+    lib_path = LIB_PATH if not suffix else PKG_DIR / f"libddn_b200{suffix}.so"
+    if not suffix and not force and not needs_build():
         return LIB_PATH
     nvcc = nvcc_path()
-    extra = os.environ.get("DDN_NVCC_EXTRA", "").split()  # tuning experiments, e.g. -DDDN_K4_MINBLOCKS=4
+    extra = os.environ.get("DDN_NVCC_EXTRA", "").split()
     objs = []
-    build_dir = PKG_DIR / "build"
+    build_dir = PKG_DIR / ("build" + suffix)
     build_dir.mkdir(exist_ok=True)
     log = []
     procs = []
@@ -64,16 +67,17 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             raise RuntimeError(f"nvcc failed on {src}")
         objs.append(str(obj))
     (build_dir / "ptxas.log").write_text("\n".join(log))
-    cmd = [nvcc, "-shared", "-o", str(LIB_PATH), *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
+    cmd = [nvcc, "-shared", "-o", str(lib_path), *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
         raise RuntimeError("link failed")
     if verbose:
         print("\n".join(log))
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":
-    p = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    sfx = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--suffix=")), "")
+    p = build(force="--force" in sys.argv, verbose="-v" in sys.argv, suffix=sfx)
     print(p)

@@ -312,7 +312,10 @@ __device__ __forceinline__ uint32_t slot_of_cell(uint64_t cell, const uint4* __r
 // walks its peer mask with shuffles (32-bit partial sums: at most 32 points of |offset| <= 2^19), and
 // the lowest lane of each group looks the slot up and issues the five 64-bit REDs.  The L2 atomic units
 // are the bound of this pass, so points per RED group is what matters: ~2 at cfg 2.
-constexpr int kAccTilesPerWarp = 8;
+#ifndef DDN_ACC_TPW
+#define DDN_ACC_TPW 8
+#endif
+constexpr int kAccTilesPerWarp = DDN_ACC_TPW;
 constexpr int kAccTileW = 16;  // pixel tile of a warp: 16 x 2 (measured at cfg 2: 4 x 8 4.46, 8 x 4 4.35, 16 x 2 4.34, 32 x 1 4.54 ms)
 
 template <int kTW>  // tile width in pixels (tile = kTW x 32/kTW); 0 = no row structure, 32 consecutive points
