@@ -142,7 +142,10 @@ def run_reference_arm(args):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     V, W, H, K, C, desc = WORKLOADS[args.workload]
-    px, times, sample, k = cpu_port_sample(args.workload, args.cpu_views, repeats=args.warmup + args.steps)
+    # bounded sample: one step costs ~1.2 s per sampled cfg-2 view on these cores; keep the whole run to minutes
+    reps = args.warmup + args.steps
+    n_views = args.cpu_views if reps <= 8 else min(args.cpu_views, 6) if reps <= 20 else min(args.cpu_views, 4)
+    px, times, sample, k = cpu_port_sample(args.workload, n_views, repeats=reps)
     timed = times[args.warmup:]
     ms = 1e3 * float(np.mean(timed))
     value = px / (ms / 1e3)
