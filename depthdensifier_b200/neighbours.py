@@ -40,6 +40,42 @@ def nearest_views_table(cam_from_world: np.ndarray, k: int) -> np.ndarray:
     return nbr
 
 
+def covisibility_table(observed_ids: list[np.ndarray], k: int, cam_from_world: np.ndarray | None = None) -> np.ndarray:
+    """K other views sharing the most sparse 3D points with each view (``observed_ids[v]`` = the point3D ids
+    view v observes - what the reference collects per image at scripts/test.py:135).  Ties, and views that share
+    nothing, fall back to camera-centre distance when poses are given, else to the lower index.  Rows are padded
+    with -1 when V-1 < K.  A COLMAP model already knows which views see the same surface; camera distance does
+    not (two cameras back to back are close and share nothing)."""
+    V = len(observed_ids)
+    nbr = np.full((V, k), -1, dtype=np.int32)
+    if V == 0:
+        return nbr
+    all_ids = np.concatenate([np.unique(np.asarray(o, dtype=np.int64)) for o in observed_ids]) if V else np.zeros(0, np.int64)
+    owner = np.concatenate([np.full(len(np.unique(np.asarray(o, dtype=np.int64))), v, dtype=np.int64) for v, o in enumerate(observed_ids)])
+    shared = np.zeros((V, V), dtype=np.int64)
+    if len(all_ids):
+        order = np.argsort(all_ids, kind="stable")
+        ids_s, own_s = all_ids[order], owner[order]
+        starts = np.flatnonzero(np.r_[True, ids_s[1:] != ids_s[:-1]])
+        ends = np.r_[starts[1:], len(ids_s)]
+        for a, b in zip(starts, ends):  # one track = the views observing one 3D point
+            if b - a > 1:
+                views = own_s[a:b]
+                shared[np.ix_(views, views)] += 1
+    dist = None
+    if cam_from_world is not None:
+        c = camera_centers(cam_from_world)
+        dist = np.linalg.norm(c[:, None] - c[None], axis=2)
+    for s in range(V):
+        score = shared[s].astype(np.float64)
+        score[s] = -1.0
+        tie = dist[s] if dist is not None else np.arange(V, dtype=np.float64)
+        order = np.lexsort((tie, -score))  # most shared points first, then nearest / lowest index
+        order = order[order != s][: min(k, V - 1)]
+        nbr[s, : len(order)] = order
+    return nbr
+
+
 def default_vote_threshold(k: int) -> int:
     """ceil(K/2): the reference default of 5 (scripts/test.py:43) is meaningless for K <= 4."""
     return int(math.ceil(k / 2))

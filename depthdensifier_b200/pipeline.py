@@ -33,7 +33,7 @@ from . import ops
 from .colmap_io import Camera, Image, Reconstruction
 from .depth_refiner import RefinerConfig
 from .engine import DensifyConfig, DensifyEngine
-from .neighbours import nearest_views_table
+from .neighbours import covisibility_table, nearest_views_table
 
 
 # ==============================================================================================
@@ -77,6 +77,8 @@ class FilteringConfig:
     """Threshold to identify a floater (projected_depth < T * refined_depth)."""
     num_neighbours: int | None = None
     """new: test each view against its K nearest views; None = against every view (reference)."""
+    neighbour_mode: str = "covisibility"
+    """new, with num_neighbours: 'covisibility' (views sharing the most sparse points) or 'nearest' (camera centres)."""
     sample_mode: str = "nearest"
     """new: 'nearest' (reference) or 'bilinear'."""
 
@@ -218,7 +220,7 @@ def main(config: ScriptConfig, depth_provider: DepthProvider | None = None, retu
     # --- 3/4a. gather the per-view inputs (host): sparse points, image, mono depth ---
     t0 = time.time()
     factor = max(int(config.processing.pipeline_downsample_factor), 1)
-    views, depths, normals, masks, rgbs, sparse, poses, intr = [], [], [], [], [], [], [], []
+    views, depths, normals, masks, rgbs, sparse, poses, intr, observed = [], [], [], [], [], [], [], [], []
     for image in [im for im in rec.images.values() if im.has_pose]:
         pts = rec.sparse_xyz_of_image(image)
         if len(pts) == 0:  # scripts/test.py:136-137
@@ -232,6 +234,7 @@ def main(config: ScriptConfig, depth_provider: DepthProvider | None = None, retu
             raise ValueError(f"camera {camera.camera_id} is {camera.model_name}; the reference's unproject_points "
                              "(scripts/test.py:81) only supports PINHOLE - undistort the model first")
         views.append(image.image_id)
+        observed.append(image.observed_point3D_ids())
         depths.append(depth)
         normals.append(normal)
         masks.append(mask)
@@ -253,8 +256,12 @@ def main(config: ScriptConfig, depth_provider: DepthProvider | None = None, retu
     poses_np = np.stack(poses)
     if K is None or K >= V:
         nbr = np.tile(np.arange(V, dtype=np.int32), (V, 1))  # every view incl. its own, in image order (reference)
-    else:
+    elif config.filtering.neighbour_mode == "covisibility":
+        nbr = covisibility_table(observed, int(K), poses_np)
+    elif config.filtering.neighbour_mode == "nearest":
         nbr = nearest_views_table(poses_np, int(K)).astype(np.int32)
+    else:
+        raise ValueError("filtering.neighbour_mode must be 'covisibility' or 'nearest'")
     rc = config.refiner
     align = ops.AlignOptions(min_correspondences=rc.min_correspondences, edge_margin=rc.edge_margin, robust=rc.robust,
                              outlier_threshold=rc.outlier_threshold, skip_smoothing=rc.skip_smoothing,
