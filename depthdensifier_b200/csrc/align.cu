@@ -418,7 +418,7 @@ align_stats_kernel(ddn_align_config cfg, int H, int W, const float* __restrict__
 // with a sliding window down each column: the three values of a row are sorted once and reused by the
 // three windows that contain them (median9 = med3(max of the minima, med3 of the middles, min of the
 // maxima)), 3 LDS and ~20 min/max per pixel instead of 9 LDS and 38.
-constexpr int kTileW = 128, kTileH = 32, kRemapThreads = 256;
+constexpr int kTileW = 126, kTileH = 32, kRemapThreads = 256;
 constexpr int kHaloW = kTileW + 2, kHaloH = kTileH + 2;
 constexpr int kLutSmemMax = 4096;  // knots kept in shared memory (32 KB); larger tables read global
 
@@ -512,30 +512,36 @@ remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y
   }
   const float a_s = st.affine_scale, a_t = st.affine_shift;
 
-  // phase 1: remap tile + 1-pixel replicate halo into shared memory
-  for (int i = tid; i < kHaloW * kHaloH; i += kRemapThreads) {
-    const int hy = i / kHaloW, hx = i - hy * kHaloW;
-    const int y = min(max(ty0 + hy - 1, 0), H - 1), x = min(max(tx0 + hx - 1, 0), W - 1);
-    const int g = y * W + x;
-    const float d = __ldg(dmap + g);
-    const bool mk = mmap ? (__ldg(mmap + g) != 0) : (d > 0.f);
-    float val = 0.f;
-    if (mk) {
-      if (bucketed) val = pwl_eval_bucketed(d, sx, sy, n, sb, xmin, bscale);
-      else if (cfg.mode == 0) val = (n >= 2) ? pwl_eval(d, gxs, gys, n) : __fmul_rn(d, __fdiv_rn(gys[0], __fadd_rn(gxs[0], 1e-6f)));
-      else val = fmaxf(__fadd_rn(__fmul_rn(d, a_s), a_t), 1e-3f);
+  // phase 1: remap tile + 1-pixel replicate halo into shared memory.  The halo is exactly 128 wide: a thread owns
+  // halo column hx (clamp hoisted) and every second halo row - no index division, no idle lanes.
+  static_assert(kHaloW == 128 && kRemapThreads == 256, "phase 1 maps two halo rows per pass");
+  {
+    const int hx = tid & (kHaloW - 1);
+    const int x = min(max(tx0 + hx - 1, 0), W - 1);
+#pragma unroll 1
+    for (int hy = tid >> 7; hy < kHaloH; hy += 2) {
+      const int y = min(max(ty0 + hy - 1, 0), H - 1);
+      const int g = y * W + x;
+      const float d = __ldg(dmap + g);
+      const bool mk = mmap ? (__ldg(mmap + g) != 0) : (d > 0.f);
+      float val = 0.f;
+      if (mk) {
+        if (bucketed) val = pwl_eval_bucketed(d, sx, sy, n, sb, xmin, bscale);
+        else if (cfg.mode == 0) val = (n >= 2) ? pwl_eval(d, gxs, gys, n) : __fmul_rn(d, __fdiv_rn(gys[0], __fadd_rn(gxs[0], 1e-6f)));
+        else val = fmaxf(__fadd_rn(__fmul_rn(d, a_s), a_t), 1e-3f);
+      }
+      s_val[hy][hx] = val;
+      s_msk[hy][hx] = mk ? 1 : 0;
     }
-    s_val[hy][hx] = val;
-    s_msk[hy][hx] = mk ? 1 : 0;
   }
   __syncthreads();
 
   // phase 2: column lx, rows [ly0, ly0 + 16)
-  const int lx = tid & (kTileW - 1);
+  const int lx = tid & (kHaloW - 1);
   const int x = tx0 + lx;
-  if (x >= W) return;
-  constexpr int kRowsPerThread = kTileH / (kRemapThreads / kTileW);
-  const int ly0 = (tid / kTileW) * kRowsPerThread;
+  if (lx >= kTileW || x >= W) return;
+  constexpr int kRowsPerThread = kTileH / (kRemapThreads / kHaloW);
+  const int ly0 = (tid / kHaloW) * kRowsPerThread;
   if (cfg.skip_smoothing) {
 #pragma unroll 4
     for (int r = 0; r < kRowsPerThread; ++r) {
