@@ -27,7 +27,10 @@ namespace ddn {
 #define DDN_K4_MINBLOCKS 5
 #endif
 constexpr int kFilterThreads = 256;
-constexpr int kFilterPX = 4;  // pixels per thread
+#ifndef DDN_K4_PX
+#define DDN_K4_PX 4
+#endif
+constexpr int kFilterPX = DDN_K4_PX;  // pixels per thread
 constexpr int kFilterChunk = kFilterThreads * kFilterPX;
 
 // ------------------------------------------------------------------------------------------------
@@ -168,16 +171,18 @@ __device__ __forceinline__ void stage_floats(float* smem, float* gptr, int n) {
   float4* g4 = reinterpret_cast<float4*>(gptr);
   float4* s4 = reinterpret_cast<float4*>(smem);
   if (aligned && n == kFilterChunk * 3) {
+    constexpr int kV = kFilterChunk * 3 / 4 / kFilterThreads;  // float4 moves per thread
+    float4 v[kV];
     if (kLoad) {
-      const float4 a = __ldcs(g4 + tid), b = __ldcs(g4 + tid + kFilterThreads), c = __ldcs(g4 + tid + 2 * kFilterThreads);
-      s4[tid] = a;
-      s4[tid + kFilterThreads] = b;
-      s4[tid + 2 * kFilterThreads] = c;
+#pragma unroll
+      for (int q = 0; q < kV; ++q) v[q] = __ldcs(g4 + tid + q * kFilterThreads);
+#pragma unroll
+      for (int q = 0; q < kV; ++q) s4[tid + q * kFilterThreads] = v[q];
     } else {
-      const float4 a = s4[tid], b = s4[tid + kFilterThreads], c = s4[tid + 2 * kFilterThreads];
-      __stcs(g4 + tid, a);
-      __stcs(g4 + tid + kFilterThreads, b);
-      __stcs(g4 + tid + 2 * kFilterThreads, c);
+#pragma unroll
+      for (int q = 0; q < kV; ++q) v[q] = s4[tid + q * kFilterThreads];
+#pragma unroll
+      for (int q = 0; q < kV; ++q) __stcs(g4 + tid + q * kFilterThreads, v[q]);
     }
     return;
   }
@@ -372,7 +377,9 @@ __global__ void __launch_bounds__(kFilterThreads, kBilinear ? 3 : DDN_K4_MINBLOC
   // bit per neighbour; the gate itself (scripts/test.py:284-295) needs the pixel's normal and is
   // resolved after each block of 32 neighbours, once per pixel that has a candidate at all.
   if (any_live) {
-    const bool all_live = live[0] & live[1] & live[2] & live[3];
+    bool all_live = true;
+#pragma unroll
+    for (int j = 0; j < kFilterPX; ++j) all_live &= live[j];
     for (int k0 = 0; k0 < n_hot; k0 += 32) {
       const int k1 = min(k0 + 32, n_hot);
       unsigned cm[kFilterPX];
