@@ -171,6 +171,7 @@ __device__ __forceinline__ void stage_floats(float* smem, float* gptr, int n) {
   float4* g4 = reinterpret_cast<float4*>(gptr);
   float4* s4 = reinterpret_cast<float4*>(smem);
   if (aligned && n == kFilterChunk * 3) {
+    static_assert((kFilterChunk * 3 / 4) % kFilterThreads == 0, "pixels per thread must be a multiple of 4");
     constexpr int kV = kFilterChunk * 3 / 4 / kFilterThreads;  // float4 moves per thread
     float4 v[kV];
     if (kLoad) {
