@@ -367,6 +367,8 @@ def main():
             "stage_GBps_algorithmic": {
                 "align_remap": 9 * (hi - lo) * H * W / (stage_ms.get("align", float("nan")) * 1e-3) / 1e9,
                 "backproject_filter": achieved,
+                # compulsory bytes of the fusion: 16 B per kept point in, 28 B per voxel out
+                "voxel_fuse": (16 * n_kept_local + 28 * n_vox_local) / (stage_ms.get("voxel_fuse", float("nan")) * 1e-3) / 1e9,
             },
         }
         print(json.dumps(line), flush=True)
