@@ -41,7 +41,7 @@ def test_fuse_empty_and_fully_rejected(lib_built):
     assert m[4].cpu().tolist() == [0, 0]
 
 
-@settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@settings(max_examples=25, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.function_scoped_fixture])
 @given(n=st.integers(1, 3000), voxel=st.sampled_from([0.5, 0.1, 0.03]), seed=st.integers(0, 10_000),
        row_len=st.sampled_from([0, 8, 13, 64]), clustered=st.booleans())
 def test_fuse_random_vs_numpy(lib_built, n, voxel, seed, row_len, clustered):
