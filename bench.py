@@ -106,16 +106,29 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # reference arm / cpu baseline (the ONLY place bench.py touches oracle/)
 # ----------------------------------------------------------------------------------------------
-def cpu_port_sample(workload: str, n_sample_views: int = 9, repeats: int = 1):
-    """Time the CPU port of the reference (stages 1-4) on `n_sample_views` consecutive views of the
-    workload at full resolution, every view testing against all the others (K = n-1)."""
+def workload_config(workload: str, n_gpus: int, scaling: str, sample_mode: str = "nearest") -> dict:
+    """The `config` block: identical in our arm and in the reference arm for the same command line (the numbers
+    that depend on the data go to `workload_stats`)."""
+    from depthdensifier_b200.neighbours import default_vote_threshold
+
+    V, W, H, K, C, desc = WORKLOADS[workload]
+    total = V * n_gpus if scaling == "weak" else V
+    return {"workload": workload, "description": desc, "views_total": total, "views_per_gpu": V if scaling == "weak" else -(-V // n_gpus),
+            "width": W, "height": H, "k_neighbours": K, "vote_threshold": default_vote_threshold(K), "voxel": VOXEL,
+            "sparse_per_view": C, "align_mode": "pwl", "sample_mode": sample_mode,
+            "l2": "inputs per step (>= 3.9 GB at cfg2) are far larger than the 126 MB L2; no explicit flush"}
+
+
+def cpu_port_sample(workload: str, n_sample_views: int | None = None, repeats: int = 1):
+    """Time the CPU port of the reference (stages 1-4) on consecutive views of the workload at full resolution.
+    The sample always has at least K+1 views, so every view is tested against the workload's K neighbours."""
     from depthdensifier_b200.hashperm import hash_perm
     from depthdensifier_b200.neighbours import default_vote_threshold, nearest_views_table
     from depthdensifier_b200.synthetic import SceneConfig, make_scene
     from oracle import restatement as R
 
     V, W, H, K, C, _ = WORKLOADS[workload]
-    n = min(n_sample_views, V)
+    n = min(max(n_sample_views or 0, K + 1), V)
     k = min(K, n - 1)
     sc = make_scene(SceneConfig(n_views=V, width=W, height=H, n_sparse=C, seed=0), device="cpu", views=range(n))
     poses = sc.cam_from_world.numpy()[:n]
@@ -130,9 +143,9 @@ def cpu_port_sample(workload: str, n_sample_views: int = 9, repeats: int = 1):
         out = R.densify(*args, randperm=lambda m: hash_perm(m, 0), voxel=VOXEL)
         times.append(time.perf_counter() - t0)
         px = int(len(out["points"]))
-    sample = (f"{n} consecutive views of {workload} at {W}x{H}, K={k} nearest of those views, stages 1-4 "
+    sample = (f"{n} consecutive views of {workload} at {W}x{H}, K={k} nearest of those views, vote threshold {thr}, stages 1-4 "
               f"(align, back-project, consistency vote, voxel fusion), {px} valid pixels")
-    return px, times, sample, k
+    return px, times, sample, {"views": n, "k_neighbours": k, "vote_threshold": thr}
 
 
 def run_reference_arm(args):
@@ -141,21 +154,20 @@ def run_reference_arm(args):
         return 0
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    V, W, H, K, C, desc = WORKLOADS[args.workload]
-    # bounded sample: one step costs ~1.2 s per sampled cfg-2 view on these cores; keep the whole run to minutes
-    reps = args.warmup + args.steps
-    n_views = args.cpu_views if reps <= 8 else min(args.cpu_views, 6) if reps <= 20 else min(args.cpu_views, 4)
-    px, times, sample, k = cpu_port_sample(args.workload, n_views, repeats=reps)
-    timed = times[args.warmup:]
+    # A step = one pass of the CPU port over K+1 full-resolution views (every view against the workload's K
+    # neighbours: the same per-pixel work as the GPU arm).  A CPU has nothing to warm up beyond the first pass, so
+    # at most one untimed pass is run however large --warmup is; all --steps passes are timed.
+    warm = min(args.warmup, 1)
+    px, times, sample, used = cpu_port_sample(args.workload, None, repeats=warm + args.steps)
+    timed = times[warm:]
     ms = 1e3 * float(np.mean(timed))
     value = px / (ms / 1e3)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "description": desc, "views": V, "width": W, "height": H, "k_neighbours": K,
-                   "voxel": VOXEL, "sparse_per_view": C},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+        "warmup": args.warmup, "warmup_passes_run": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.workload, args.gpus, args.scaling),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "sample_config": used,
                          "torch_threads": torch.get_num_threads(),
                          "note": "numpy stages 2-4 are effectively single-threaded, torch CPU ops of stage 1 use all threads"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -168,6 +180,134 @@ def run_reference_arm(args):
 # ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
+class Ctx:
+    """Process-wide state of one bench run (rank, device, process group)."""
+
+    def __init__(self):
+        self.rank, self.world, self.local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+        self.dev = torch.device("cuda", self.local)
+        self.dist = None
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def allreduce(self, x, op="max"):
+        if self.dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+
+def run_workload(ctx: Ctx, workload: str, scaling: str, steps: int, warmup: int, e2e: bool, sample_mode: str = "nearest",
+                 pixel_layout: int = 0, clocks: bool = True) -> dict:
+    """Device-resident timing (+ optionally the end-to-end host path) of one workload on all ranks."""
+    from depthdensifier_b200 import _lib, ops
+    from depthdensifier_b200.distributed import ShardedDensifier
+    from depthdensifier_b200.engine import DensifyConfig
+    from depthdensifier_b200.neighbours import default_vote_threshold, nearest_views_table
+    from depthdensifier_b200.synthetic import SceneConfig, make_scene
+
+    rank, world, dev = ctx.rank, ctx.world, ctx.dev
+    Vper, W, H, K, C, desc = WORKLOADS[workload]
+    if scaling == "weak":
+        V_total = Vper * world
+        lo, hi = rank * Vper, (rank + 1) * Vper
+    else:
+        V_total = Vper
+        per = (V_total + world - 1) // world
+        lo, hi = min(rank * per, V_total), min((rank + 1) * per, V_total)
+    sc = make_scene(SceneConfig(n_views=V_total, width=W, height=H, n_sparse=C, seed=0), device=dev, views=range(lo, hi))
+    nbr_np = nearest_views_table(sc.cam_from_world.cpu().numpy(), K)
+    thr = default_vote_threshold(K)
+    torch.cuda.synchronize()
+    cfg = DensifyConfig(voxel=VOXEL, vote_threshold=thr, filter=ops.FilterOptions(sample_mode=sample_mode, pixel_layout=pixel_layout))
+    sharded = ShardedDensifier(cfg, dev, rank, world, V_total, lo, hi, sc.cam_from_world, sc.intrinsics, nbr_np, H, W)
+    dev_inputs = (sc.mono_depth, sc.normal, sc.mask, sc.rgb, sc.sparse_xyz, sc.sparse_offsets)
+
+    for _ in range(warmup):
+        res = sharded.run(*dev_inputs)
+    ctx.barrier()
+    n_vox_local = res.check()  # validates grid status / capacities once (synchronises), outside the timed region
+    n_valid_local = int((res.votes != 255).sum().item())
+    n_kept_local = int(res.counts[0].item())
+    sampler = ClockSampler(ctx.local)
+    if clocks:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = _lib.launch_count()
+    ctx.barrier()
+    t_wall0 = time.time()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    stage_events = []
+    for _ in range(steps):
+        res = sharded.run(*dev_inputs, record_events=True)
+        stage_events.append(res.events)
+    ev1.record()
+    ctx.barrier()
+    t_wall1 = time.time()
+    launches = _lib.launch_count() - launches0
+    clk = sampler.stop(t_wall0, t_wall1) if clocks else None
+    res.check()
+    ms_step = ctx.allreduce(ev0.elapsed_time(ev1) / steps, "max")
+    stage_ms = {}
+    for evs in stage_events:
+        for name, (a, b) in evs.items():
+            stage_ms.setdefault(name, []).append(a.elapsed_time(b))
+    stage_ms = {k: float(np.mean(v)) for k, v in stage_ms.items()}
+    # multi-GPU runs launch K4 twice (views that need no halo first, the shard's boundary views after the halo)
+    k4_local_ms = stage_ms["backproject_filter"] + stage_ms.get("backproject_filter_boundary", 0.0)
+    n_valid = int(ctx.allreduce(float(n_valid_local), "sum"))
+    n_kept = int(ctx.allreduce(float(n_kept_local), "sum"))
+    n_vox = int(ctx.allreduce(float(n_vox_local), "sum"))
+    out = {
+        "workload": workload, "scaling": scaling, "ms_per_step": ms_step, "value": n_valid / (ms_step / 1e3), "steps": steps,
+        "stages_ms": stage_ms, "k4_local_ms": k4_local_ms, "launches": int(launches), "clocks": clk,
+        "path": "peer" if sharded.peer is not None else ("single" if world == 1 else "collective"),
+        "stats": {"valid_pixels": n_valid, "kept_points": n_kept, "voxels": n_vox, "valid_pixels_rank0": n_valid_local,
+                  "views_rank0": hi - lo},
+        "n_valid_local": n_valid_local, "n_kept_local": n_kept_local, "n_vox_local": n_vox_local, "K": K, "H": H, "W": W,
+        "views_local": hi - lo, "limits": {"gather_offset_pixels": f"{sharded.n_slots * H * W} of 2^32 per rank",
+                                           "points_per_rank": f"{(hi - lo) * H * W} of 2^31"},
+    }
+    if e2e:
+        del res
+        torch.cuda.empty_cache()
+        host = sharded.pin_host_inputs(*[t.cpu() for t in dev_inputs])
+
+        def time_e2e(**kw):
+            for _ in range(2):
+                out_host = sharded.run_host(*host, **kw)
+            ctx.barrier()
+            t0 = time.perf_counter()
+            e_steps = max(2, min(steps, 5))
+            for _ in range(e_steps):
+                out_host = sharded.run_host(*host, **kw)
+            ctx.barrier()
+            e_ms = ctx.allreduce((time.perf_counter() - t0) * 1e3 / e_steps, "max")
+            return e_ms, int(out_host["h2d_bytes"]), int(out_host["d2h_bytes"])
+
+        e_ms, h2d, d2h = time_e2e()
+        f_ms, f_h2d, f_d2h = time_e2e(normals_in_place=False)
+        tot = lambda x: int(ctx.allreduce(float(x), "sum"))
+        out["e2e"] = {
+            "value": n_valid / (e_ms / 1e3), "unit": UNIT, "ms_per_step": e_ms,
+            "h2d_bytes_per_step": tot(h2d), "d2h_bytes_per_step": tot(d2h),
+            "pcie_GBps_per_rank": (h2d + d2h) / (e_ms * 1e-3) / 1e9,
+            "value_all_copied": n_valid / (f_ms / 1e3), "ms_per_step_all_copied": f_ms, "h2d_bytes_per_step_all_copied": tot(f_h2d),
+            "pcie_GBps_per_rank_all_copied": (f_h2d + f_d2h) / (f_ms * 1e-3) / 1e9,
+            "api": "ShardedDensifier.run_host (pinned host arrays in, fused cloud out through pinned buffers)",
+            "note": "`value`: depth, mask, colours and sparse points are copied to the device every step; the normal maps "
+                    "stay in pinned host memory and the consistency kernel reads only the normals of its vote candidates over "
+                    "PCIe (not counted in h2d_bytes_per_step).  `value_all_copied`: the normal maps are copied too."}
+    del sharded, sc, dev_inputs
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -176,9 +316,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
-    ap.add_argument("--cpu-views", type=int, default=9)
+    ap.add_argument("--sample-mode", default="nearest", choices=["nearest", "bilinear"])
+    ap.add_argument("--pixel-layout", type=int, default=0, choices=[0, 1])
+    ap.add_argument("--cpu-views", type=int, default=0, help="views of the CPU sample (at least K+1 are always used)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the extra strong-scaling block (cfg3)")
+    ap.add_argument("--no-check", action="store_true", help="skip the multi-GPU equivalence check")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = max(args.warmup, 1) if args.workload == "small" else 3
@@ -188,19 +332,19 @@ def main():
     from depthdensifier_b200 import _lib
     from depthdensifier_b200 import build as ddn_build
 
-    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    ctx = Ctx()
+    rank, world, local, dev = ctx.rank, ctx.world, ctx.local, ctx.dev
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
     if world == 1 or rank == 0:
         ddn_build.build()
     torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
     numa_cpus = None
     if world > 1:  # keep each rank's pinned host buffers on the socket next to its GPU
         from depthdensifier_b200.hostmem import bind_to_gpu_numa
 
         numa_cpus = bind_to_gpu_numa(local)
-    dist = None
+    multi_gpu = None
     if world > 1:
         import torch.distributed as dist
 
@@ -209,86 +353,27 @@ def main():
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
             os.environ.pop("NCCL_DEBUG")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-
         dist.init_process_group("nccl", device_id=dev)
         dist.barrier()
+        ctx.dist = dist
     _lib.load()
+    if world > 1 and not args.no_check:
+        # hardware equivalence before anything is timed: N ranks == 1 rank, bit for bit, on the path that is timed
+        from depthdensifier_b200.selfcheck import multi_gpu_check
 
-    from depthdensifier_b200.distributed import ShardedDensifier
-    from depthdensifier_b200.engine import DensifyConfig
-    from depthdensifier_b200.neighbours import default_vote_threshold, nearest_views_table
-    from depthdensifier_b200.synthetic import SceneConfig, make_scene
+        reports = [multi_gpu_check(dev, rank, world), multi_gpu_check(dev, rank, world, n_views=29, width=203, height=131, k=3, voxel=0.03)]
+        multi_gpu = {"passed": all(r["passed"] for r in reports), "path": reports[0]["path"], "cases": reports}
+        if not multi_gpu["passed"]:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "multi_gpu_check": multi_gpu, "error": "N-rank result differs from 1-rank"}), flush=True)
+            dist.destroy_process_group()
+            return 1
 
-    Vper, W, H, K, C, desc = WORKLOADS[args.workload]
-    if args.scaling == "weak":
-        V_total = Vper * world
-        lo, hi = rank * Vper, (rank + 1) * Vper
-    else:
-        V_total = Vper
-        per = (V_total + world - 1) // world
-        lo, hi = min(rank * per, V_total), min((rank + 1) * per, V_total)
-    scfg = SceneConfig(n_views=V_total, width=W, height=H, n_sparse=C, seed=0)
-    sc = make_scene(scfg, device=dev, views=range(lo, hi))
-    poses_np = sc.cam_from_world.cpu().numpy()
-    nbr_np = nearest_views_table(poses_np, K)
-    thr = default_vote_threshold(K)
-    torch.cuda.synchronize()
-
-    sharded = ShardedDensifier(DensifyConfig(voxel=VOXEL, vote_threshold=thr), dev, rank, world, V_total, lo, hi,
-                               sc.cam_from_world, sc.intrinsics, nbr_np, H, W)
-    dev_inputs = (sc.mono_depth, sc.normal, sc.mask, sc.rgb, sc.sparse_xyz, sc.sparse_offsets)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident timing ----
-    for _ in range(args.warmup):
-        res = sharded.run(*dev_inputs)
-    barrier()
-    n_valid_local = int((res.votes != 255).sum().item())
-    n_kept_local, n_vox_local = [int(x) for x in res.counts.cpu().tolist()]
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.3)
-    launches0 = _lib.launch_count()
-    stage_ms = {}
-    barrier()
-    t_wall0 = time.time()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    stage_events = []
-    for _ in range(args.steps):
-        res = sharded.run(*dev_inputs, record_events=True)
-        stage_events.append(res.events)
-    ev1.record()
-    barrier()
-    t_wall1 = time.time()
-    launches = _lib.launch_count() - launches0
-    clocks = sampler.stop(t_wall0, t_wall1)
-    ms_total = ev0.elapsed_time(ev1)
-    ms_step = ms_total / args.steps
-    for evs in stage_events:
-        for name, (a, b) in evs.items():
-            stage_ms.setdefault(name, []).append(a.elapsed_time(b))
-    stage_ms = {k: float(np.mean(v)) for k, v in stage_ms.items()}
-    # multi-GPU runs launch K4 twice (views that need no halo first, the shard's boundary views after the halo)
-    k4_local_ms = stage_ms["backproject_filter"] + stage_ms.get("backproject_filter_boundary", 0.0)
-
-    def allreduce(x, op):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=op)
-        return float(t.item())
-
-    ms_step = allreduce(ms_step, dist.ReduceOp.MAX if dist else None)
-    n_valid = int(allreduce(float(n_valid_local), dist.ReduceOp.SUM if dist else None))
-    n_kept = int(allreduce(float(n_kept_local), dist.ReduceOp.SUM if dist else None))
-    n_vox = int(allreduce(float(n_vox_local), dist.ReduceOp.SUM if dist else None))
-    k4_ms = allreduce(k4_local_ms, dist.ReduceOp.MAX if dist else None)
-    value = n_valid / (ms_step / 1e3)
+    main_run = run_workload(ctx, args.workload, args.scaling, args.steps, args.warmup, e2e=not args.no_e2e,
+                            sample_mode=args.sample_mode, pixel_layout=args.pixel_layout)
+    K, H, W = main_run["K"], main_run["H"], main_run["W"]
+    n_valid_local, k4_local_ms = main_run["n_valid_local"], main_run["k4_local_ms"]
+    stage_ms = main_run["stages_ms"]
 
     # ---- roofline of the judged kernel (K4 back-project + consistency), algorithmic bytes ----
     peaks_file = ROOT / "MEASURED_PEAKS.json"
@@ -298,83 +383,64 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     bytes_per_px = 29 + 4 * K
-    k4_bytes = bytes_per_px * n_valid_local
-    achieved = k4_bytes / (k4_local_ms * 1e-3) / 1e9
+    achieved = bytes_per_px * n_valid_local / (k4_local_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "backproject_filter_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": None, "achieved_dram": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_pixel": bytes_per_px, "pixels_per_launch": n_valid_local,
-                "kernel_ms": k4_local_ms}
+                "kernel_ms": k4_local_ms,
+                "note": "achieved = algorithmic bytes (SURVEY 8d: 29 + 4K per valid pixel) / CUDA-event time; achieved_dram = ncu "
+                        "dram bytes of the same launch / the same time: the kernel reads normals only for vote candidates and "
+                        "its neighbour taps hit L2, so it moves far fewer bytes than the algorithmic figure counts"}
     traffic_file = ROOT / "profiles" / "k4_traffic.json"
     if traffic_file.exists():
         try:
             roofline["traffic"] = json.loads(traffic_file.read_text()).get(args.workload)
+            if roofline["traffic"]:
+                roofline["achieved_dram"] = roofline["traffic"] / (k4_local_ms * 1e-3) / 1e9
         except (ValueError, OSError):
             pass
 
-    # ---- end to end through the public engine call with host buffers ----
-    e2e = None
-    if not args.no_e2e:
-        del res
-        torch.cuda.empty_cache()
-        host = sharded.pin_host_inputs(*[t.cpu() for t in dev_inputs])
-
-        def time_e2e(**kw):
-            for _ in range(2):
-                out_host = sharded.run_host(*host, **kw)
-            barrier()
-            t0 = time.perf_counter()
-            e_steps = max(2, min(args.steps, 5))
-            for _ in range(e_steps):
-                out_host = sharded.run_host(*host, **kw)
-            barrier()
-            e_ms = (time.perf_counter() - t0) * 1e3 / e_steps
-            e_ms = allreduce(e_ms, dist.ReduceOp.MAX if dist else None)
-            return e_ms, int(out_host["h2d_bytes"]), int(out_host["d2h_bytes"])
-
-        e_ms, h2d, d2h = time_e2e()
-        f_ms, f_h2d, _ = time_e2e(normals_in_place=False)
-        tot = lambda x: int(allreduce(float(x), dist.ReduceOp.SUM if dist else None))
-        e2e = {"value": n_valid / (e_ms / 1e3), "unit": UNIT, "ms_per_step": e_ms,
-               "h2d_bytes_per_step": tot(h2d), "d2h_bytes_per_step": tot(d2h),
-               "api": "ShardedDensifier.run_host (pinned host arrays in, fused cloud out through pinned buffers)",
-               "note": "depth, mask, colours and sparse points are copied to the device every step; the normal maps "
-                       "stay in pinned host memory and the consistency kernel reads only the normals of its vote "
-                       "candidates over PCIe (not counted in h2d_bytes_per_step)",
-               "all_inputs_copied": {"value": n_valid / (f_ms / 1e3), "ms_per_step": f_ms, "h2d_bytes_per_step": tot(f_h2d)}}
+    # ---- strong scaling block: cfg3 (200 views at 1920x1080, K=8) split over the ranks, at every N ----
+    strong = None
+    if not args.no_strong and args.workload == "cfg2" and args.scaling == "weak":
+        sr = run_workload(ctx, "cfg3", "strong", steps=max(5, min(args.steps, 10)), warmup=3, e2e=False, clocks=False)
+        strong = {"workload": "cfg3", "scaling": "strong", "ms_per_step": sr["ms_per_step"], "value": sr["value"], "unit": UNIT,
+                  "steps": sr["steps"], "stages_ms": sr["stages_ms"], "path": sr["path"], "workload_stats": sr["stats"],
+                  "config": workload_config("cfg3", world, "strong"),
+                  "note": "total work fixed (200 views), divide the n_gpus=1 ms_per_step by this one for the speed-up"}
 
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only) ----
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        px, times, sample, _k = cpu_port_sample(args.workload, args.cpu_views, repeats=1)
+        px, times, sample, used = cpu_port_sample(args.workload, args.cpu_views, repeats=1)
         cpu_baseline = {"value": px / times[0], "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                        "seconds": times[0]}
+                        "sample_config": used, "seconds": times[0]}
 
     if rank == 0:
+        views_local = main_run["views_local"]
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "metric": METRIC, "value": main_run["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": main_run["ms_per_step"], "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "description": desc, "views_total": V_total, "views_per_gpu": hi - lo,
-                       "width": W, "height": H, "k_neighbours": K, "vote_threshold": thr, "voxel": VOXEL,
-                       "sparse_per_view": C, "align_mode": "pwl", "sample_mode": "nearest",
-                       "l2": "inputs per step (>= 3.9 GB at cfg2) are far larger than the 126 MB L2; no explicit flush",
-                       "valid_pixels": n_valid, "kept_points": n_kept, "voxels": n_vox},
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+            "config": workload_config(args.workload, world, args.scaling, args.sample_mode),
+            "workload_stats": main_run["stats"], "limits": main_run["limits"], "path": main_run["path"],
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": main_run.get("e2e"), "gpu_launches": main_run["launches"],
+            "multi_gpu_check": multi_gpu, "strong": strong,
             "host_cpus_rank0": (f"{numa_cpus[0]}-{numa_cpus[-1]} ({len(numa_cpus)})" if numa_cpus else None),
-            "clocks": clocks, "stages_ms": stage_ms,
+            "clocks": main_run["clocks"], "stages_ms": stage_ms,
             "stage_GBps_algorithmic": {
-                "align_remap": 9 * (hi - lo) * H * W / (stage_ms.get("align", float("nan")) * 1e-3) / 1e9,
+                "align_remap": 9 * views_local * H * W / (stage_ms.get("align", float("nan")) * 1e-3) / 1e9,
                 "backproject_filter": achieved,
                 # compulsory bytes of the fusion: 16 B per kept point in, 28 B per voxel out
-                "voxel_fuse": (16 * n_kept_local + 28 * n_vox_local) / (stage_ms.get("voxel_fuse", float("nan")) * 1e-3) / 1e9,
+                "voxel_fuse": (16 * main_run["n_kept_local"] + 28 * main_run["n_vox_local"]) / (stage_ms.get("voxel_fuse", float("nan")) * 1e-3) / 1e9,
             },
         }
         print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    if ctx.dist is not None:
+        ctx.dist.barrier()
+        ctx.dist.destroy_process_group()
     return 0
 
 

@@ -56,6 +56,7 @@ class FilterConfig(C.Structure):
         ("two_sided_tau", C.c_float),
         ("stride", C.c_int32),
         ("normals_in_world", C.c_int32),
+        ("pixel_layout", C.c_int32),
     ]
 
 
@@ -63,6 +64,22 @@ class VoxelGrid(C.Structure):
     _fields_ = [("voxel", C.c_float), ("origin", C.c_float * 3), ("bits", C.c_int32 * 3), ("dims", C.c_int32 * 3)]
 
 
+class GridState(C.Structure):
+    """ddn_grid_state: the device-resident grid of a fusion session (64 bytes)."""
+
+    _fields_ = [("voxel", C.c_float), ("origin", C.c_float * 3), ("bits", C.c_int32 * 3), ("dims", C.c_int32 * 3),
+                ("n_units", C.c_int64), ("status", C.c_int32), ("reserved", C.c_int32), ("cells", C.c_int64)]
+
+
+class FuseSession(C.Structure):
+    """ddn_fuse_session: host struct of device pointers."""
+
+    _fields_ = [("grid", C.c_void_p), ("units", C.c_void_p), ("cap_units", C.c_int64), ("dirty", C.c_void_p),
+                ("tile_sums", C.c_void_p), ("tile_prefix", C.c_void_p), ("counts", C.c_void_p)]
+
+
+GRID_OK, GRID_EMPTY, GRID_TOO_LARGE, GRID_TOO_MANY_BITS = 0, 1, 2, 3
+MAX_PEERS = 16
 PAIR_TABLE_FLOATS = 24
 RECORD_WORDS = 6  # DDN_RECORD_WORDS
 
@@ -77,12 +94,13 @@ SYMBOLS = {
     "ddn_align_workspace_bytes": (C.c_int, [_i64, _i64, C.POINTER(_i64)]),
     "ddn_align_views": (
         C.c_int,
-        [C.POINTER(AlignConfig), _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp],
+        [C.POINTER(AlignConfig), _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp],
     ),
-    "ddn_build_pair_tables": (C.c_int, [_i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ddn_build_pair_tables": (C.c_int, [_i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ddn_backproject_filter": (
         C.c_int,
-        [C.POINTER(FilterConfig), _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp],
+        [C.POINTER(FilterConfig), _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp,
+         C.POINTER(FuseSession), _vp],
     ),
     "ddn_bbox_init": (C.c_int, [_vp, _vp]),
     "ddn_pchip_workspace_bytes": (C.c_int, [_i64, _i64, C.POINTER(_i64)]),
@@ -113,6 +131,21 @@ SYMBOLS = {
         [C.POINTER(VoxelGrid), _i64, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     ),
     "ddn_voxel_keys": (C.c_int, [C.POINTER(VoxelGrid), _i64, _vp, _vp, _vp]),
+    "ddn_fuse_session_sizes": (C.c_int, [_i64] + [C.POINTER(_i64)] * 5),
+    "ddn_fuse_session_reset": (C.c_int, [C.POINTER(FuseSession), _vp]),
+    "ddn_fuse_begin": (C.c_int, [C.POINTER(FuseSession), C.POINTER(_vp), _i32, C.c_float, _vp]),
+    "ddn_fuse_begin_grid": (C.c_int, [C.POINTER(FuseSession), C.POINTER(VoxelGrid), _vp]),
+    "ddn_fuse_mark_points": (C.c_int, [C.POINTER(FuseSession), _i64, _vp, _vp, _i32, _vp]),
+    "ddn_fuse_finish": (
+        C.c_int,
+        [C.POINTER(FuseSession), _i64, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp],
+    ),
+    "ddn_fuse_finish_partial": (C.c_int, [C.POINTER(FuseSession), _i64, _i64, _vp, _vp, _vp, _i32, _vp, _i64, _vp]),
+    "ddn_fuse_merge_peers": (
+        C.c_int,
+        [C.POINTER(FuseSession), _i32, _i32, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp,
+         _i64, _vp, _i64, _vp],
+    ),
 }
 
 _lib = None
@@ -133,7 +166,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.ddn_version() != 100:
+    if lib.ddn_version() != 200:
         raise DDNError(f"libddn_b200.so version mismatch: {lib.ddn_version()}")
     _lib = lib
     return lib

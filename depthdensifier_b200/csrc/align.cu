@@ -456,16 +456,64 @@ __device__ __forceinline__ float pwl_eval_bucketed(float d, const float* __restr
   return pwl_interp(d, xs[i - 1], xs[i], ys[i - 1], ys[i]);
 }
 
+// Bounding-box epilogue of K3 (called by every thread of the CTA, after a block barrier that made the
+// s_dmin / s_dmax initialisation visible).  Every pixel (x, y) of the tile with refined depth d > 0 back-projects
+// to X = d * (a x + b y + c) + t per axis - affine in d for a fixed pixel and affine in (x, y) for a fixed d - so all
+// points of the tile lie inside the box of the 8 corners {x0, x1} x {y0, y1} x {dmin, dmax}.  The tile's points cost
+// two min/max per pixel instead of a full back-projection; the box is a superset of the true one by at most the
+// tile's own extent at its largest depth.
+__device__ __forceinline__ void tile_bbox_epilogue(int* __restrict__ bbox, const float* __restrict__ src_table, int v, int tx0,
+                                                   int ty0, int W, int H, int t_dmin, int t_dmax, int* s_dmin, int* s_dmax) {
+  if (bbox == nullptr) return;  // uniform
+  const int lo = __reduce_min_sync(0xffffffffu, t_dmin), hi = __reduce_max_sync(0xffffffffu, t_dmax);
+  if ((threadIdx.x & 31) == 0 && hi > 0) {
+    atomicMin(s_dmin, lo);
+    atomicMax(s_dmax, hi);
+  }
+  __syncthreads();
+  if (threadIdx.x != 0 || *s_dmax <= 0) return;
+  const float* s = src_table + (size_t)v * 16;
+  float row[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) row[i] = __ldg(s + i);
+  const float dlim[2] = {__int_as_float(*s_dmin), __int_as_float(*s_dmax)};
+  const float xs[2] = {(float)tx0, (float)(min(tx0 + kTileW, W) - 1)};
+  const float ys[2] = {(float)ty0, (float)(min(ty0 + kTileH, H) - 1)};
+  float bmin[3] = {INFINITY, INFINITY, INFINITY}, bmax[3] = {-INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float d = dlim[c & 1], x = xs[(c >> 1) & 1], y = ys[c >> 2];
+    float p[3];
+    backproject_pqd(row, d * x, d * y, d, p[0], p[1], p[2]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) bmin[i] = fminf(bmin[i], p[i]), bmax[i] = fmaxf(bmax[i], p[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    atomicMin(bbox + i, float_to_ordered(bmin[i]));
+    atomicMax(bbox + 3 + i, float_to_ordered(bmax[i]));
+  }
+}
+
 #ifndef DDN_K3_MINB
 #define DDN_K3_MINB 8
 #endif
 __global__ void __launch_bounds__(kRemapThreads, DDN_K3_MINB)
 remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y, const float* __restrict__ depth,
                     const uint8_t* __restrict__ mask, const ddn_view_stats* __restrict__ stats, AlignWorkspace ws,
-                    float* __restrict__ refined, int lut_cap) {
+                    float* __restrict__ refined, int lut_cap, const float* __restrict__ src_table, int* __restrict__ bbox) {
   extern __shared__ __align__(16) float s_dyn[];  // LUT xs | ys | bucket index (when the table fits)
   __shared__ float s_val[kHaloH][kHaloW];
   __shared__ uint8_t s_msk[kHaloH][kHaloW + 2];
+  // bounding-box epilogue: smallest / largest positive refined depth of the tile (bits of positive floats order as ints)
+  __shared__ int s_dmin, s_dmax;
+  int t_dmin = 0x7f800000, t_dmax = 0;
+  auto fold_depth = [&](float v) {
+    const int b = __float_as_int(v);
+    t_dmax = max(t_dmax, b);
+    t_dmin = min(t_dmin, v > 0.f ? b : 0x7f800000);
+  };
+  if (threadIdx.x == 0) s_dmin = 0x7f800000, s_dmax = 0;
 
   const int tid = threadIdx.x;
   const int tile = blockIdx.x;
@@ -487,8 +535,11 @@ remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y
         if (st.status == DDN_VIEW_NO_SPARSE) d = 0.f;
         else if (cfg.zero_unmasked_passthrough && !(mmap ? mmap[g] != 0 : d > 0.f)) d = 0.f;
         out[g] = d;
+        fold_depth(d);
       }
     }
+    __syncthreads();
+    tile_bbox_epilogue(bbox, src_table, v, tx0, ty0, W, H, t_dmin, t_dmax, &s_dmin, &s_dmax);
     return;
   }
 
@@ -539,36 +590,41 @@ remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y
   // phase 2: column lx, rows [ly0, ly0 + 16)
   const int lx = tid & (kHaloW - 1);
   const int x = tx0 + lx;
-  if (lx >= kTileW || x >= W) return;
+  const bool active = lx < kTileW && x < W;
   constexpr int kRowsPerThread = kTileH / (kRemapThreads / kHaloW);
   const int ly0 = (tid / kHaloW) * kRowsPerThread;
-  if (cfg.skip_smoothing) {
+  if (active && cfg.skip_smoothing) {
 #pragma unroll 4
     for (int r = 0; r < kRowsPerThread; ++r) {
       const int y = ty0 + ly0 + r;
       if (y >= H) break;
-      out[(size_t)y * W + x] = s_msk[ly0 + r + 1][lx + 1] ? s_val[ly0 + r + 1][lx + 1] : 0.f;
+      const float o = s_msk[ly0 + r + 1][lx + 1] ? s_val[ly0 + r + 1][lx + 1] : 0.f;
+      out[(size_t)y * W + x] = o;
+      fold_depth(o);
     }
-    return;
-  }
-  float lo[3], mi[3], hi[3];
-  auto load_row = [&](int hy, int slot) {
-    float a = s_val[hy][lx], b = s_val[hy][lx + 1], c = s_val[hy][lx + 2];
-    const float ab_lo = fminf(a, b), ab_hi = fmaxf(a, b);
-    lo[slot] = fminf(ab_lo, c);
-    hi[slot] = fmaxf(ab_hi, c);
-    mi[slot] = fmaxf(ab_lo, fminf(ab_hi, c));
-  };
-  load_row(ly0, 0);
-  load_row(ly0 + 1, 1);
+  } else if (active) {
+    float lo[3], mi[3], hi[3];
+    auto load_row = [&](int hy, int slot) {
+      float a = s_val[hy][lx], b = s_val[hy][lx + 1], c = s_val[hy][lx + 2];
+      const float ab_lo = fminf(a, b), ab_hi = fmaxf(a, b);
+      lo[slot] = fminf(ab_lo, c);
+      hi[slot] = fmaxf(ab_hi, c);
+      mi[slot] = fmaxf(ab_lo, fminf(ab_hi, c));
+    };
+    load_row(ly0, 0);
+    load_row(ly0 + 1, 1);
 #pragma unroll
-  for (int r = 0; r < kRowsPerThread; ++r) {
-    const int y = ty0 + ly0 + r;
-    if (y >= H) break;
-    load_row(ly0 + r + 2, (r + 2) % 3);
-    const float o = med3(fmaxf(fmaxf(lo[0], lo[1]), lo[2]), med3(mi[0], mi[1], mi[2]), fminf(fminf(hi[0], hi[1]), hi[2]));
-    out[(size_t)y * W + x] = s_msk[ly0 + r + 1][lx + 1] ? o : 0.f;
+    for (int r = 0; r < kRowsPerThread; ++r) {
+      const int y = ty0 + ly0 + r;
+      if (y >= H) break;
+      load_row(ly0 + r + 2, (r + 2) % 3);
+      float o = med3(fmaxf(fmaxf(lo[0], lo[1]), lo[2]), med3(mi[0], mi[1], mi[2]), fminf(fminf(hi[0], hi[1]), hi[2]));
+      o = s_msk[ly0 + r + 1][lx + 1] ? o : 0.f;
+      out[(size_t)y * W + x] = o;
+      fold_depth(o);
+    }
   }
+  tile_bbox_epilogue(bbox, src_table, v, tx0, ty0, W, H, t_dmin, t_dmax, &s_dmin, &s_dmax);
 }
 
 }  // namespace ddn
@@ -587,9 +643,10 @@ int ddn_align_views(const ddn_align_config* cfg, int64_t n_views, int64_t height
                     const float* depth, const uint8_t* mask, const double* cam_from_world,
                     const double* kmat, const double* sparse_xyz, const int64_t* sparse_offsets,
                     int64_t max_sparse_per_view, float* refined, ddn_view_stats* stats,
-                    void* workspace, int64_t workspace_bytes, void* stream) {
+                    void* workspace, int64_t workspace_bytes, const float* src_table, float* bbox, void* stream) {
   using namespace ddn;
   DDN_REQUIRE(cfg != nullptr, "null config");
+  DDN_REQUIRE((src_table == nullptr) == (bbox == nullptr), "src_table and bbox go together");
   DDN_REQUIRE(n_views >= 0 && height > 1 && width > 1, "shape");
   DDN_REQUIRE(height * width < (1ll << 31), "image too large");
   DDN_REQUIRE(cfg->mode == 0 || cfg->mode == 1, "mode");
@@ -622,7 +679,7 @@ int ddn_align_views(const ddn_align_config* cfg, int64_t n_views, int64_t height
                      "cudaFuncSetAttribute(remap_median)"));
   dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)n_views);
   remap_median_kernel<<<grid, kRemapThreads, smem_lut, st>>>(*cfg, (int)height, (int)width, tiles_x, tiles_y, depth, mask,
-                                                            stats, ws, refined, (int)lut);
+                                                            stats, ws, refined, (int)lut, src_table, reinterpret_cast<int*>(bbox));
   return after_launch("remap_median_kernel");
 }
 

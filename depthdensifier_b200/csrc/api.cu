@@ -48,6 +48,7 @@ void ddn_filter_config_default(ddn_filter_config* cfg) {
   cfg->two_sided_tau = 0.0f;
   cfg->stride = 1;
   cfg->normals_in_world = 0;
+  cfg->pixel_layout = 0;
 }
 
 }  // extern "C"

@@ -55,4 +55,14 @@ __device__ __forceinline__ float ordered_to_float(int i) {
   return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff);
 }
 
+// World position of a pixel from P = d*x, Q = d*y, d and the view's 16-float src_table row (rows of
+// R_s^T Kinv_s with the camera centre appended; scripts/test.py:79-90 then :233).  K4 (filter.cu) and the
+// bounding-box epilogue of K3 (align.cu) both call this, so the box encloses K4's points bit for bit.
+__device__ __forceinline__ void backproject_pqd(const float* __restrict__ s, float P, float Q, float d, float& X, float& Y,
+                                                float& Z) {
+  X = fmaf(s[0], P, fmaf(s[1], Q, fmaf(s[2], d, s[3])));
+  Y = fmaf(s[4], P, fmaf(s[5], Q, fmaf(s[6], d, s[7])));
+  Z = fmaf(s[8], P, fmaf(s[9], Q, fmaf(s[10], d, s[11])));
+}
+
 }  // namespace ddn

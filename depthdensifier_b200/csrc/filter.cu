@@ -19,7 +19,7 @@
 //     one MUFU.RCP and one MUFU.SQRT per pair).
 #include <string.h>
 
-#include "common.cuh"
+#include "fuse_common.cuh"
 
 namespace ddn {
 
@@ -37,13 +37,14 @@ constexpr int kFilterChunk = kFilterThreads * kFilterPX;
 // Table set-up (float64, one thread per (source view, neighbour))
 // pair_table[s][k][24]: rows 0..2 of K_t [M | t_ts], M = R_t R_s^T Kinv_s (12 floats) - i.e. the pixel
 //   (x, y) at depth d maps to (U, V, Z) = rows * (d x, d y, d, 1) and lands at u = U/Z, v = V/Z;
-//   camera centre of t (3), target view index (int bits), fx_t fy_t cx_t cy_t, own-view flag, pad.
+//   camera centre of t (3), target view index (int bits), fx_t fy_t cx_t cy_t, own-view flag, and (float 21,
+//   uint bits) K4's gather offset of the entry: t*H*W - 0x4B000000*(W+1) mod 2^32 (see pair_gather).
 //   The entries of a source view are COMPACTED: valid neighbours other than the view itself first
 //   (n_hot of them, in table order), then the n_own entries of the view itself (only the
 //   reference-parity table K = V lists it); entry 0 carries n_hot and n_own in floats 22, 23 (int bits).  K4's hot loop therefore runs over n_hot entries without any validity test.
 // src_table[s][16]: rows of R_s^T Kinv_s with c_s appended (12 floats), cx_s, cy_s, fx_s, fy_s.
 // ------------------------------------------------------------------------------------------------
-__global__ void build_pair_tables_kernel(int n_total, int src_begin, int n_src, int k_nbr,
+__global__ void build_pair_tables_kernel(int n_total, int src_begin, int n_src, int k_nbr, unsigned hw, unsigned width,
                                          const double* __restrict__ poses,
                                          const double* __restrict__ intr,
                                          const int32_t* __restrict__ nbr, float* __restrict__ pair_table,
@@ -127,7 +128,7 @@ __global__ void build_pair_tables_kernel(int n_total, int src_begin, int n_src, 
   o[18] = (float)intr[t * 4 + 2];
   o[19] = (float)intr[t * 4 + 3];
   o[20] = (t == s) ? 1.f : 0.f;
-  o[21] = 0.f;
+  o[21] = __uint_as_float((unsigned)t * hw - 0x4B000000u * (width + 1u));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -141,6 +142,7 @@ struct FilterParams {
   float* xyz;                // [n_src,Hs,Ws,3]
   uint8_t* votes;            // [n_src,Hs,Ws]
   int* bbox;                 // [6] ordered-int encoded, or nullptr
+  FuseDev mark;              // occupancy marking of kept points (mark.units == nullptr: off)
   int src_begin, n_src, H, W, Hs, Ws, K, stride;
   int vote_threshold;
   float depth_threshold, grazing_cos, two_sided_tau;
@@ -161,48 +163,6 @@ __device__ __forceinline__ float sqrt_approx(float x) {
 // trunc(u) for 0 <= u < 2^22, biased by 0x4B000000, on the FMA pipe (no F2I).
 __device__ __forceinline__ int trunc_biased(float u) { return __float_as_int(__fadd_rz(u, 8388608.0f)); }
 constexpr int kTruncBias = 0x4B000000;
-
-// Cooperative global<->shared copy of n floats, float4 when the global address is 16 B aligned.  The
-// common case (full chunk, aligned) is three straight-line float4 moves per thread.
-template <bool kLoad>
-__device__ __forceinline__ void stage_floats(float* smem, float* gptr, int n) {
-  const int tid = threadIdx.x;
-  const bool aligned = (reinterpret_cast<uintptr_t>(gptr) & 15) == 0;
-  float4* g4 = reinterpret_cast<float4*>(gptr);
-  float4* s4 = reinterpret_cast<float4*>(smem);
-  if (aligned && n == kFilterChunk * 3) {
-    static_assert((kFilterChunk * 3 / 4) % kFilterThreads == 0, "pixels per thread must be a multiple of 4");
-    constexpr int kV = kFilterChunk * 3 / 4 / kFilterThreads;  // float4 moves per thread
-    float4 v[kV];
-    if (kLoad) {
-#pragma unroll
-      for (int q = 0; q < kV; ++q) v[q] = __ldcs(g4 + tid + q * kFilterThreads);
-#pragma unroll
-      for (int q = 0; q < kV; ++q) s4[tid + q * kFilterThreads] = v[q];
-    } else {
-#pragma unroll
-      for (int q = 0; q < kV; ++q) v[q] = s4[tid + q * kFilterThreads];
-#pragma unroll
-      for (int q = 0; q < kV; ++q) __stcs(g4 + tid + q * kFilterThreads, v[q]);
-    }
-    return;
-  }
-  const int n4 = aligned ? (n >> 2) : 0;
-#pragma unroll 1
-  for (int i = tid; i < n4; i += kFilterThreads) {
-    if (kLoad)
-      s4[i] = __ldcs(g4 + i);
-    else
-      __stcs(g4 + i, s4[i]);
-  }
-#pragma unroll 1
-  for (int i = (n4 << 2) + tid; i < n; i += kFilterThreads) {
-    if (kLoad)
-      smem[i] = __ldcs(gptr + i);
-    else
-      __stcs(gptr + i, smem[i]);
-  }
-}
 
 // One (pixel, neighbour) evaluation, in two steps so that the gathers of a thread's four pixels are all in
 // flight before the first one is consumed.  pair_gather: project, bounds test, issue the depth lookup.
@@ -279,78 +239,85 @@ __device__ __forceinline__ void load_normal(const float* __restrict__ normal_vie
   }
 }
 
-template <bool kBilinear, bool kStride1, bool kTwoSided>
+// Pixel ownership.  A CTA owns kFilterChunk consecutive source-grid pixels of one view, a warp 128 of them.
+//   layout 0 ("strided"):  thread pixel j = warp base + j*32 + lane.  Every load, gather and byte store of a
+//                          warp instruction covers 32 consecutive pixels; xyz leaves through a per-warp
+//                          shared staging buffer as float4 (no block barrier).
+//   layout 1 ("adjacent"): thread pixel j = warp base + lane*4 + j.  One LDG.128 for the depths, one STG.32
+//                          for the votes, three STG.128 for xyz straight from registers, no shared staging;
+//                          the gathers of one instruction are 4 pixels apart.
+// -DDDN_K4_LAYOUT selects the default; both produce identical results.
+#ifndef DDN_K4_LAYOUT
+#define DDN_K4_LAYOUT 0
+#endif
+constexpr int kWarpPix = 32 * kFilterPX;
+static_assert(kFilterPX == 4, "the layouts below are written for 4 pixels per thread");
+
+template <bool kBilinear, bool kStride1, bool kTwoSided, int kLayout>
 __global__ void __launch_bounds__(kFilterThreads, kBilinear ? 3 : DDN_K4_MINBLOCKS) backproject_filter_kernel(const FilterParams p) {
   extern __shared__ __align__(16) float smem[];
-  float* s_xyz = smem;                      // kFilterChunk*3 floats: world xyz (staged out)
-  float* s_src = s_xyz + kFilterChunk * 3;  // 16 floats
-  float* s_pair = s_src + 16;               // K*24 floats
+  float* s_src = smem;                     // 16 floats
+  float* s_pair = s_src + 16;              // K*24 floats
+  float* s_stage = s_pair + p.K * DDN_PAIR_TABLE_FLOATS;  // layout 0: 8 warps x 128 px x 3 floats
   __shared__ int s_bbox[6];
+  __shared__ int s_marked;
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int sl = blockIdx.y;
   const int s = p.src_begin + sl;
   const int Ps = p.Hs * p.Ws;  // source-grid pixels per view
   const int chunk0 = blockIdx.x * kFilterChunk;
-  const int n_here = min(kFilterChunk, Ps - chunk0);
   const size_t HW = (size_t)p.H * p.W;
   const float* __restrict__ depth_s = p.refined_all + (size_t)s * HW;
   const float* __restrict__ normal_s = p.normal + (size_t)sl * HW * 3;
 
-  // pair entries -> shared memory; float 16 of every entry (unused by this kernel) is replaced by the
-  // entry's gather offset t*H*W - bias*(W+1) (see pair_candidate)
-  const unsigned idx_bias = (unsigned)kTruncBias * (unsigned)(p.W + 1);
-  for (int i = tid; i < p.K * DDN_PAIR_TABLE_FLOATS; i += kFilterThreads) {
-    const int f = i % DDN_PAIR_TABLE_FLOATS;
-    const float val = __ldg(p.pair_table + (size_t)sl * p.K * DDN_PAIR_TABLE_FLOATS + i);
-    if (f == 16) continue;
-    s_pair[i] = val;
-    if (f == 15) s_pair[i + 1] = __uint_as_float((unsigned)__float_as_int(val) * (unsigned)HW - idx_bias);
+  // tables -> shared memory, as float4 (entries are 96 bytes; the gather offset t*H*W - bias*(W+1) of every
+  // entry was put into float 21 by build_pair_tables_kernel)
+  {
+    const float4* g4 = reinterpret_cast<const float4*>(p.pair_table + (size_t)sl * p.K * DDN_PAIR_TABLE_FLOATS);
+    float4* s4 = reinterpret_cast<float4*>(s_pair);
+    for (int i = tid; i < p.K * (DDN_PAIR_TABLE_FLOATS / 4); i += kFilterThreads) s4[i] = __ldg(g4 + i);
+    if (tid < 4) reinterpret_cast<float4*>(s_src)[tid] = __ldg(reinterpret_cast<const float4*>(p.src_table + (size_t)sl * 16) + tid);
+    if (tid < 6) s_bbox[tid] = tid < 3 ? 0x7fffffff : (int)0x80000000;
+    if (tid == 6) s_marked = 0;
   }
-  if (tid < 16) s_src[tid] = __ldg(p.src_table + (size_t)sl * 16 + tid);
-  if (tid < 6) s_bbox[tid] = tid < 3 ? 0x7fffffff : (int)0x80000000;
+
+  // first pixel of the thread on the source grid: q0 = y0 * Ws + x0 (one integer division per thread)
+  const int wbase = chunk0 + warp * kWarpPix;
+  const int q0 = wbase + (kLayout == 1 ? lane * kFilterPX : lane);
+  constexpr int kStep = kLayout == 1 ? 1 : 32;
+  int ys_run = q0 / p.Ws;
+  int xs_run = q0 - ys_run * p.Ws;
 
   // Per-pixel state kept in registers: depth d (NaN = no point), P = d*x, Q = d*y, vote count.
   float d[kFilterPX], P[kFilterPX], Q[kFilterPX];
   int nvotes[kFilterPX];
   unsigned src_pix[kFilterPX];  // element index of the pixel in its own full-resolution map
   const float qnan = __int_as_float(0x7fc00000);
-
-  // (row, column) of the thread's first pixel: one integer division per thread, then +256 steps
-  int ys_run = (chunk0 + tid) / p.Ws;
-  int xs_run = (chunk0 + tid) - ys_run * p.Ws;
-  float dd[kFilterPX];
   {
+    float dd[kFilterPX];
     int px[kFilterPX], py[kFilterPX];
 #pragma unroll
     for (int j = 0; j < kFilterPX; ++j) {
-      const int l = j * kFilterThreads + tid;
       px[j] = kStride1 ? xs_run : xs_run * p.stride;
       py[j] = kStride1 ? ys_run : ys_run * p.stride;
-      src_pix[j] = kStride1 ? (unsigned)(chunk0 + l) : (unsigned)py[j] * (unsigned)p.W + (unsigned)px[j];
-      dd[j] = l < n_here ? __ldg(depth_s + src_pix[j]) : 0.f;
-      xs_run += kFilterThreads;
+      src_pix[j] = kStride1 ? (unsigned)(q0 + j * kStep) : (unsigned)py[j] * (unsigned)p.W + (unsigned)px[j];
+      xs_run += kStep;
       while (xs_run >= p.Ws) {
         xs_run -= p.Ws;
         ++ys_run;
       }
     }
-    __syncthreads();  // tables visible
+    if (kLayout == 1 && kStride1 && q0 + kFilterPX <= Ps && ((reinterpret_cast<uintptr_t>(depth_s + q0) & 15) == 0)) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(depth_s + q0));
+      dd[0] = v.x, dd[1] = v.y, dd[2] = v.z, dd[3] = v.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < kFilterPX; ++j) dd[j] = (q0 + j * kStep) < Ps ? __ldg(depth_s + src_pix[j]) : 0.f;
+    }
 #pragma unroll
     for (int j = 0; j < kFilterPX; ++j) {
-      const int l = j * kFilterThreads + tid;
       const bool valid = dd[j] > 0.f;
-      const float dv = valid ? dd[j] : 0.f;
-      const float Pv = dv * (float)px[j], Qv = dv * (float)py[j];
-      // world position (scripts/test.py:79-90 then :233), fp32 with float64-precomputed rows
-      const float X = fmaf(s_src[0], Pv, fmaf(s_src[1], Qv, fmaf(s_src[2], dv, s_src[3])));
-      const float Y = fmaf(s_src[4], Pv, fmaf(s_src[5], Qv, fmaf(s_src[6], dv, s_src[7])));
-      const float Z = fmaf(s_src[8], Pv, fmaf(s_src[9], Qv, fmaf(s_src[10], dv, s_src[11])));
-      if (l < n_here) {
-        s_xyz[l * 3 + 0] = valid ? X : 0.f;
-        s_xyz[l * 3 + 1] = valid ? Y : 0.f;
-        s_xyz[l * 3 + 2] = valid ? Z : 0.f;
-      }
       d[j] = valid ? dd[j] : qnan;
       asm volatile("" : "+f"(d[j]));  // keep the NaN-tagged depth in a register (no per-neighbour recompute)
       P[j] = d[j] * (float)px[j];
@@ -358,6 +325,7 @@ __global__ void __launch_bounds__(kFilterThreads, kBilinear ? 3 : DDN_K4_MINBLOC
       nvotes[j] = 0;
     }
   }
+  __syncthreads();  // tables visible
   // warp-uniform flags: pixel group j of this warp has at least one point (sky / masked regions are
   // contiguous, so whole groups drop out of the pair loop)
   bool live[kFilterPX];
@@ -372,6 +340,10 @@ __global__ void __launch_bounds__(kFilterThreads, kBilinear ? 3 : DDN_K4_MINBLOC
   const float thr = p.depth_threshold, gcos = p.grazing_cos, tau = p.two_sided_tau;
   const bool in_world = p.normals_in_world != 0;
   const int n_hot = __float_as_int(s_pair[22]), n_own = __float_as_int(s_pair[23]);
+
+  // world position of pixel j (scripts/test.py:79-90 then :233), fp32 with float64-precomputed rows;
+  // the same expression ddn_align_views' bounding-box epilogue evaluates (backproject_px)
+  auto world_of = [&](int j, float& X, float& Y, float& Z) { backproject_pqd(s_src, P[j], Q[j], d[j], X, Y, Z); };
 
   // Hot loop: branch-free candidate test for every (pixel, neighbour); the four gathers of a thread
   // issue back to back.  Candidates ("would vote if the grazing gate passes") are only recorded as a
@@ -390,7 +362,7 @@ __global__ void __launch_bounds__(kFilterThreads, kBilinear ? 3 : DDN_K4_MINBLOC
       for (int k = k0; k < k1; ++k, bit <<= 1) {
         const float4* t4 = reinterpret_cast<const float4*>(s_pair + k * DDN_PAIR_TABLE_FLOATS);
         const float4 r0 = t4[0], r1 = t4[1], r2 = t4[2];
-        const unsigned off_k = __float_as_uint(s_pair[k * DDN_PAIR_TABLE_FLOATS + 16]);
+        const unsigned off_k = __float_as_uint(s_pair[k * DDN_PAIR_TABLE_FLOATS + 21]);
         float Z[kFilterPX], D[kFilterPX];
         bool inb[kFilterPX];
         if (all_live) {
@@ -421,10 +393,9 @@ __global__ void __launch_bounds__(kFilterThreads, kBilinear ? 3 : DDN_K4_MINBLOC
 #pragma unroll
       for (int j = 0; j < kFilterPX; ++j) {
         if (cm[j]) {
-          const int l = j * kFilterThreads + tid;
-          float n0, n1, n2;
+          float n0, n1, n2, wx, wy, wz;
           load_normal(normal_s, src_pix[j], in_world, s_src, n0, n1, n2);
-          const float wx = s_xyz[l * 3 + 0], wy = s_xyz[l * 3 + 1], wz = s_xyz[l * 3 + 2];
+          world_of(j, wx, wy, wz);
           unsigned m = cm[j];
           while (m) {
             const int k = k0 + __ffs(m) - 1;
@@ -451,16 +422,16 @@ __global__ void __launch_bounds__(kFilterThreads, kBilinear ? 3 : DDN_K4_MINBLOC
       const float4 cc = t4[3];
 #pragma unroll
       for (int j = 0; j < kFilterPX; ++j) {
-        const int l = j * kFilterThreads + tid;
-        if (l < n_here && d[j] > 0.f) {
+        if (d[j] > 0.f) {
           const int py = (int)(src_pix[j] / (unsigned)p.W), px = (int)(src_pix[j] - (unsigned)py * (unsigned)p.W);
           const int ux = max(px - 1, 0), vy = max(py - 1, 0);
           const float D = __ldg(depth_s + (size_t)vy * p.W + ux);
           const bool bad = kTwoSided ? (fabsf(d[j] - D) > tau * D) : (d[j] < __fmul_rn(thr, D));
           if (D > 0.f && bad) {
-            float n0, n1, n2;
+            float n0, n1, n2, wx, wy, wz;
             load_normal(normal_s, src_pix[j], in_world, s_src, n0, n1, n2);
-            const float ex = cc.x - s_xyz[l * 3 + 0], ey = cc.y - s_xyz[l * 3 + 1], ez = cc.z - s_xyz[l * 3 + 2];
+            world_of(j, wx, wy, wz);
+            const float ex = cc.x - wx, ey = cc.y - wy, ez = cc.z - wz;
             const float dn = fmaf(n0, ex, fmaf(n1, ey, n2 * ez));
             const float len = sqrt_approx(fmaf(ex, ex, fmaf(ey, ey, ez * ez)));
             nvotes[j] += (dn > gcos * len) ? 1 : 0;
@@ -470,42 +441,122 @@ __global__ void __launch_bounds__(kFilterThreads, kBilinear ? 3 : DDN_K4_MINBLOC
     }
   }
 
-  float bmin[3] = {INFINITY, INFINITY, INFINITY}, bmax[3] = {-INFINITY, -INFINITY, -INFINITY};
+  // ---- epilogue: world positions (recomputed from the registers), votes, bounding box, occupancy ----
+  float X[kFilterPX], Y[kFilterPX], Zw[kFilterPX];
+  bool keep[kFilterPX];
+  unsigned vote_bytes = 0;
 #pragma unroll
   for (int j = 0; j < kFilterPX; ++j) {
-    const int l = j * kFilterThreads + tid;
-    if (l < n_here) {
-      const bool valid = d[j] > 0.f;
-      p.votes[(size_t)sl * Ps + chunk0 + l] = valid ? (uint8_t)min(nvotes[j], 254) : (uint8_t)255;
-      if (p.bbox != nullptr && valid && nvotes[j] < p.vote_threshold) {
+    const bool valid = d[j] > 0.f;
+    world_of(j, X[j], Y[j], Zw[j]);
+    if (!valid) X[j] = 0.f, Y[j] = 0.f, Zw[j] = 0.f;
+    keep[j] = valid && nvotes[j] < p.vote_threshold;
+    vote_bytes |= (valid ? (unsigned)min(nvotes[j], 254) : 255u) << (8 * j);
+  }
+  const size_t out0 = (size_t)sl * Ps;  // first pixel of the view in the outputs
+  if (kLayout == 1) {
+    uint8_t* vo = p.votes + out0 + q0;
+    if (q0 + kFilterPX <= Ps && ((reinterpret_cast<uintptr_t>(vo) & 3) == 0)) {
+      *reinterpret_cast<unsigned*>(vo) = vote_bytes;
+    } else {
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          const float c = s_xyz[l * 3 + i];
-          bmin[i] = fminf(bmin[i], c);
-          bmax[i] = fmaxf(bmax[i], c);
+      for (int j = 0; j < kFilterPX; ++j)
+        if (q0 + j < Ps) vo[j] = (uint8_t)(vote_bytes >> (8 * j));
+    }
+    float* xo = p.xyz + (out0 + q0) * 3;
+    if (q0 + kFilterPX <= Ps && ((reinterpret_cast<uintptr_t>(xo) & 15) == 0)) {
+      float4* x4 = reinterpret_cast<float4*>(xo);
+      __stcs(x4 + 0, make_float4(X[0], Y[0], Zw[0], X[1]));
+      __stcs(x4 + 1, make_float4(Y[1], Zw[1], X[2], Y[2]));
+      __stcs(x4 + 2, make_float4(Zw[2], X[3], Y[3], Zw[3]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < kFilterPX; ++j)
+        if (q0 + j < Ps) {
+          __stcs(xo + j * 3 + 0, X[j]);
+          __stcs(xo + j * 3 + 1, Y[j]);
+          __stcs(xo + j * 3 + 2, Zw[j]);
         }
-      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < kFilterPX; ++j)
+      if (q0 + j * 32 < Ps) p.votes[out0 + q0 + j * 32] = (uint8_t)(vote_bytes >> (8 * j));
+    // xyz through the warp's staging slice: stride-3 STS (conflict free), float4 out (16 B per lane, coalesced)
+    float* sw = s_stage + warp * (kWarpPix * 3);
+#pragma unroll
+    for (int j = 0; j < kFilterPX; ++j) {
+      const int l = j * 32 + lane;
+      sw[l * 3 + 0] = X[j];
+      sw[l * 3 + 1] = Y[j];
+      sw[l * 3 + 2] = Zw[j];
+    }
+    __syncwarp();
+    const int n_w = min(kWarpPix, Ps - wbase);  // pixels of this warp that exist (<= 0: none)
+    float* xo = p.xyz + (out0 + wbase) * 3;
+    if (n_w == kWarpPix && ((reinterpret_cast<uintptr_t>(xo) & 15) == 0)) {
+      const float4* s4 = reinterpret_cast<const float4*>(sw);
+      float4* g4 = reinterpret_cast<float4*>(xo);
+#pragma unroll
+      for (int q = 0; q < 3; ++q) __stcs(g4 + q * 32 + lane, s4[q * 32 + lane]);
+    } else {
+      for (int i = lane; i < n_w * 3; i += 32) __stcs(xo + i, sw[i]);
     }
   }
+
   if (p.bbox != nullptr && any_live) {
+    float bmin[3] = {INFINITY, INFINITY, INFINITY}, bmax[3] = {-INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int j = 0; j < kFilterPX; ++j) {
+      if (keep[j]) {
+        bmin[0] = fminf(bmin[0], X[j]), bmax[0] = fmaxf(bmax[0], X[j]);
+        bmin[1] = fminf(bmin[1], Y[j]), bmax[1] = fmaxf(bmax[1], Y[j]);
+        bmin[2] = fminf(bmin[2], Zw[j]), bmax[2] = fmaxf(bmax[2], Zw[j]);
+      }
+    }
     // warp reduction with REDUX on the order-preserving int encoding, then one shared atomic per warp
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       const int lo = __reduce_min_sync(0xffffffffu, float_to_ordered(bmin[i]));
       const int hi = __reduce_max_sync(0xffffffffu, float_to_ordered(bmax[i]));
-      if ((tid & 31) == 0 && lo <= hi) {
+      if (lane == 0 && lo <= hi) {
         atomicMin(&s_bbox[i], lo);
         atomicMax(&s_bbox[3 + i], hi);
       }
     }
   }
-  __syncthreads();
-  if (kStride1) {
-    stage_floats<false>(s_xyz, p.xyz + ((size_t)sl * Ps + chunk0) * 3, n_here * 3);
-  } else {
-    float* o = p.xyz + ((size_t)sl * Ps + chunk0) * 3;
-    for (int i = tid; i < n_here * 3; i += kFilterThreads) __stcs(o + i, s_xyz[i]);
+
+  // Stage 4's mark pass, fused: the occupancy bit of every kept point.  A cell equal to that of the pixel
+  // to the left (same thread, or the neighbouring lane) is already set by that pixel.
+  if (p.mark.units != nullptr && any_live) {
+    const GridDev g = *p.mark.grid;
+    if (g.n_units != 0) {
+      const float rv = 1.0f / g.voxel;
+      uint64_t cell[kFilterPX];
+      int mine = 0;
+#pragma unroll
+      for (int j = 0; j < kFilterPX; ++j) {
+        cell[j] = kNoCell;
+        if (keep[j]) {
+          uint32_t kx, ky, kz;
+          cell[j] = cell_of_point(g, rv, X[j], Y[j], Zw[j], kx, ky, kz);
+        }
+        mine += cell[j] != kNoCell ? 1 : 0;
+      }
+#pragma unroll
+      for (int j = 0; j < kFilterPX; ++j) {
+        // left neighbour: layout 1 - previous pixel of the thread, or the last pixel of the previous lane;
+        // layout 0 - the same group in the previous lane
+        uint64_t left = __shfl_up_sync(0xffffffffu, kLayout == 1 ? cell[kFilterPX - 1] : cell[j], 1);
+        if (lane == 0) left = kNoCell;
+        if (kLayout == 1 && j > 0) left = cell[j - 1];
+        if (cell[j] != kNoCell && cell[j] != left) set_cell_bit(p.mark.units, p.mark.dirty, cell[j]);
+      }
+      mine = __reduce_add_sync(0xffffffffu, mine);
+      if (lane == 0 && mine) atomicAdd(&s_marked, mine);
+    }
   }
+  __syncthreads();
   if (p.bbox != nullptr && tid < 6) {
     if (tid < 3) {
       if (s_bbox[tid] != 0x7fffffff) atomicMin(p.bbox + tid, s_bbox[tid]);
@@ -513,6 +564,7 @@ __global__ void __launch_bounds__(kFilterThreads, kBilinear ? 3 : DDN_K4_MINBLOC
       if (s_bbox[tid] != (int)0x80000000) atomicMax(p.bbox + tid, s_bbox[tid]);
     }
   }
+  if (tid == 6 && s_marked) atomicAdd(p.mark.counts, (unsigned long long)s_marked);
 }
 
 __global__ void bbox_init_kernel(int* bbox) {
@@ -524,17 +576,19 @@ __global__ void bbox_init_kernel(int* bbox) {
 
 extern "C" {
 
-int ddn_build_pair_tables(int64_t n_views_total, int64_t src_begin, int64_t n_src, int64_t k_nbr,
-                          const double* cam_from_world, const double* intr, const int32_t* nbr,
+int ddn_build_pair_tables(int64_t n_views_total, int64_t src_begin, int64_t n_src, int64_t k_nbr, int64_t height,
+                          int64_t width, const double* cam_from_world, const double* intr, const int32_t* nbr,
                           float* pair_table, float* src_table, void* stream) {
   using namespace ddn;
   DDN_REQUIRE(n_views_total > 0 && n_src >= 0 && k_nbr > 0, "view counts");
+  DDN_REQUIRE(height > 0 && width > 0 && height * width < (1ll << 31), "image size");
   DDN_REQUIRE(src_begin >= 0 && src_begin + n_src <= n_views_total, "source range");
   DDN_REQUIRE(cam_from_world && intr && nbr && pair_table && src_table, "null pointer");
   if (n_src == 0) return DDN_OK;
   const int total = (int)(n_src * k_nbr + n_src);
   build_pair_tables_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-      (int)n_views_total, (int)src_begin, (int)n_src, (int)k_nbr, cam_from_world, intr, nbr, pair_table, src_table);
+      (int)n_views_total, (int)src_begin, (int)n_src, (int)k_nbr, (unsigned)(height * width), (unsigned)width, cam_from_world, intr,
+      nbr, pair_table, src_table);
   return after_launch("build_pair_tables_kernel");
 }
 
@@ -549,17 +603,20 @@ int ddn_backproject_filter(const ddn_filter_config* cfg, int64_t n_views_total, 
                            int64_t n_src, int64_t height, int64_t width, int64_t k_nbr,
                            const float* refined_all, const float* normal, const int32_t* nbr,
                            const float* pair_table, const float* src_table, int32_t vote_threshold,
-                           float* xyz, uint8_t* votes, float* bbox, void* stream) {
+                           float* xyz, uint8_t* votes, float* bbox, const ddn_fuse_session* mark, void* stream) {
   using namespace ddn;
   (void)nbr;
   DDN_REQUIRE(cfg != nullptr, "null config");
-  DDN_REQUIRE(n_views_total > 0 && n_src >= 0 && k_nbr > 0 && k_nbr <= 1024, "view counts");
+  DDN_REQUIRE(n_views_total > 0 && n_src >= 0 && k_nbr > 0 && k_nbr <= 1024, "view counts (at most 1024 neighbours per view)");
   DDN_REQUIRE(src_begin >= 0 && src_begin + n_src <= n_views_total, "source range");
   DDN_REQUIRE(height > 0 && width > 0 && height * width < (1ll << 31), "image size");
   DDN_REQUIRE(n_views_total * height * width < (1ll << 32), "refined_all must hold fewer than 2^32 pixels (32-bit gather offsets)");
   DDN_REQUIRE(width < (1 << 22) && height < (1 << 22), "image side too large for the truncation trick");
   DDN_REQUIRE(cfg->stride >= 1, "stride");
+  DDN_REQUIRE(cfg->pixel_layout == 0 || cfg->pixel_layout == 1, "pixel_layout");
   DDN_REQUIRE(refined_all && normal && pair_table && src_table && xyz && votes, "null pointer");
+  DDN_REQUIRE((reinterpret_cast<uintptr_t>(pair_table) & 15) == 0 && (reinterpret_cast<uintptr_t>(src_table) & 15) == 0,
+              "pair_table / src_table must be 16-byte aligned");
   if (n_src == 0) return DDN_OK;
   FilterParams p;
   p.refined_all = refined_all;
@@ -569,6 +626,14 @@ int ddn_backproject_filter(const ddn_filter_config* cfg, int64_t n_views_total, 
   p.xyz = xyz;
   p.votes = votes;
   p.bbox = reinterpret_cast<int*>(bbox);
+  p.mark.grid = nullptr, p.mark.units = nullptr, p.mark.dirty = nullptr, p.mark.counts = nullptr;
+  if (mark != nullptr) {
+    DDN_REQUIRE(mark->grid && mark->units && mark->counts, "mark session: null buffer");
+    p.mark.grid = reinterpret_cast<const GridDev*>(mark->grid);
+    p.mark.units = reinterpret_cast<uint32_t*>(mark->units);
+    p.mark.dirty = mark->dirty;
+    p.mark.counts = reinterpret_cast<unsigned long long*>(mark->counts);
+  }
   p.src_begin = (int)src_begin;
   p.n_src = (int)n_src;
   p.H = (int)height;
@@ -577,7 +642,7 @@ int ddn_backproject_filter(const ddn_filter_config* cfg, int64_t n_views_total, 
   p.Hs = (p.H + p.stride - 1) / p.stride;
   p.Ws = (p.W + p.stride - 1) / p.stride;
   p.K = (int)k_nbr;
-  p.vote_threshold = vote_threshold;
+  p.vote_threshold = vote_threshold < 255 ? vote_threshold : 255;
   p.depth_threshold = cfg->depth_threshold;
   p.grazing_cos = cfg->grazing_cos;
   p.two_sided_tau = cfg->two_sided_tau;
@@ -590,30 +655,37 @@ int ddn_backproject_filter(const ddn_filter_config* cfg, int64_t n_views_total, 
   const int Ps = p.Hs * p.Ws;
   dim3 grid((Ps + kFilterChunk - 1) / kFilterChunk, (unsigned)n_src);
   DDN_REQUIRE(n_src <= 65535, "too many source views per call");
-  const size_t smem = (size_t)(kFilterChunk * 3 + 16 + p.K * DDN_PAIR_TABLE_FLOATS) * sizeof(float);
+  const int layout = cfg->pixel_layout;
+  const size_t smem = (size_t)(16 + p.K * DDN_PAIR_TABLE_FLOATS + (layout == 0 ? kFilterChunk * 3 : 0)) * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
   const bool bil = cfg->sample_mode == 1;
   const bool s1 = cfg->stride == 1;
   const bool two = cfg->two_sided_tau > 0.f;
   DDN_REQUIRE(two || cfg->depth_threshold > 0.f, "depth_threshold must be positive");
-#define DDN_LAUNCH_FILTER(B, S, T)                                                                         \
+#define DDN_LAUNCH_FILTER(B, S, T, L)                                                                      \
   do {                                                                                                     \
-    DDN_TRY(check_cuda(cudaFuncSetAttribute(backproject_filter_kernel<B, S, T>,                            \
+    DDN_TRY(check_cuda(cudaFuncSetAttribute(backproject_filter_kernel<B, S, T, L>,                         \
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),       \
                        "cudaFuncSetAttribute"));                                                           \
-    backproject_filter_kernel<B, S, T><<<grid, kFilterThreads, smem, st>>>(p);                             \
+    backproject_filter_kernel<B, S, T, L><<<grid, kFilterThreads, smem, st>>>(p);                          \
+  } while (0)
+#define DDN_LAUNCH_FILTER_L(B, S, T)       \
+  do {                                     \
+    if (layout == 1) DDN_LAUNCH_FILTER(B, S, T, 1); \
+    else DDN_LAUNCH_FILTER(B, S, T, 0);    \
   } while (0)
   if (two) {
-    if (bil && s1) DDN_LAUNCH_FILTER(true, true, true);
-    else if (bil) DDN_LAUNCH_FILTER(true, false, true);
-    else if (s1) DDN_LAUNCH_FILTER(false, true, true);
-    else DDN_LAUNCH_FILTER(false, false, true);
+    if (bil && s1) DDN_LAUNCH_FILTER_L(true, true, true);
+    else if (bil) DDN_LAUNCH_FILTER_L(true, false, true);
+    else if (s1) DDN_LAUNCH_FILTER_L(false, true, true);
+    else DDN_LAUNCH_FILTER_L(false, false, true);
   } else {
-    if (bil && s1) DDN_LAUNCH_FILTER(true, true, false);
-    else if (bil) DDN_LAUNCH_FILTER(true, false, false);
-    else if (s1) DDN_LAUNCH_FILTER(false, true, false);
-    else DDN_LAUNCH_FILTER(false, false, false);
+    if (bil && s1) DDN_LAUNCH_FILTER_L(true, true, false);
+    else if (bil) DDN_LAUNCH_FILTER_L(true, false, false);
+    else if (s1) DDN_LAUNCH_FILTER_L(false, true, false);
+    else DDN_LAUNCH_FILTER_L(false, false, false);
   }
+#undef DDN_LAUNCH_FILTER_L
 #undef DDN_LAUNCH_FILTER
   return after_launch("backproject_filter_kernel");
 }

@@ -7,55 +7,37 @@
 // replaces the radix sort of 168 M (key, index) pairs by streaming passes:
 //
 //   mark        every participating point sets the bit of its cell (RED.OR; a cell equal to the
-//               previous point's is skipped)
+//               previous point's is skipped).  In the pipeline this happens in K4's epilogue
+//               (filter.cu) while the point is still in registers; mark_points_kernel is the
+//               stand-alone form.
 //   rank        popcount scan over the occupancy: one exclusive prefix per 96-bit unit, stored in the
 //               unit's fourth word; the pass also emits the sorted keys
 //   accumulate  integer fixed-point sums per voxel with 64-bit RED.ADD.  The L2 atomic units bound this
 //               pass, so a warp first merges the points of its 16 x 2 pixel tile that share a cell
-//               (MATCH.ANY + shuffles); the group's first lane looks the slot up (ONE 16 B load:
-//               96 bits + prefix) and issues the atomics.
+//               (MATCH.ANY + REDUX over the peer mask); the group's first lane looks the slot up (ONE
+//               16 B load: 96 bits + prefix) and issues the atomics.
 //   finalize    one thread per voxel: mean = centre + sum/count, colour = round-half-up
 //
 // Integer sums make the result independent of the order of points and of how they are split over
-// ranks (ddn_voxel_partials / ddn_voxel_merge use the same passes with a different output / input).
-// Grids with more than 2^35 cells take the sort path in fuse_sort.cu.
+// ranks.  THE GRID LIVES IN DEVICE MEMORY (GridDev behind a pointer): a fusion session derives it from
+// bounding boxes on the device, every grid-sized pass is a persistent kernel that reads the actual
+// extent, so a whole step - and the multi-GPU exchange + merge over peer memory at the end of this
+// file - runs without the host looking at any intermediate result.
+// Grids with more than 2^35 cells take the sort path in fuse_sort.cu (host-grid entry points only).
 #include <algorithm>
 
 #include "fuse_common.cuh"
 
 namespace ddn {
 
-// Occupancy + rank live in ONE array of 16-byte units: words x, y, z = 96 occupancy bits, word w = the
-// exclusive rank prefix of the unit (written by the rank pass).  A slot lookup is a single LDG.128.
-constexpr int kUnitBits = 96;
-constexpr int kUnitsPerThread = 8;
-constexpr int kScanThreads = 256;
-constexpr int kTileUnits = kScanThreads * kUnitsPerThread;  // units per CTA in the rank passes (32 KB)
-// Ownership granularity of the multi-GPU form: a "tile" of the C ABI is kOwnUnits consecutive units
-// (24,576 cells in key order), fine enough to cut a dense z-layer of the grid into balanced shares.
-constexpr int kOwnUnits = kScanThreads;
-constexpr int kOwnPerScanTile = kTileUnits / kOwnUnits;
-constexpr int kAccWords = 5;                                // sx, sy, sz, r:g, b:count (u64 each)
+constexpr int kAccWords = 5;  // sx, sy, sz, r:g, b:count (u64 each)
 // Partial-sum RECORD exchanged between ranks: {key, sx, sy, sz, r:g, b:count} = DDN_RECORD_WORDS u64.  In
 // partial mode the accumulators ARE words 1..5 of the output records (stride 6), so there is no
 // finalisation pass and a destination's share of the sorted records is one contiguous slice.
 constexpr int kRecWords = DDN_RECORD_WORDS;
 static_assert(kRecWords == kAccWords + 1, "record = key + accumulators");
-constexpr uint64_t kDenseMaxCells = 1ull << 35;             // 5.7 GB of units
-constexpr uint64_t kNoCell = ~0ull;
-
-__device__ __forceinline__ uint64_t cell_of_point(const GridDev& g, float rv, float x, float y, float z, uint32_t& kx,
-                                                  uint32_t& ky, uint32_t& kz) {
-  const float fx = voxel_coord(x, g.ox, g.voxel, rv);
-  const float fy = voxel_coord(y, g.oy, g.voxel, rv);
-  const float fz = voxel_coord(z, g.oz, g.voxel, rv);
-  const bool inside = fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)g.nx && fy < (float)g.ny && fz < (float)g.nz;
-  if (!inside) return kNoCell;
-  kx = (uint32_t)fx;
-  ky = (uint32_t)fy;
-  kz = (uint32_t)fz;
-  return (uint64_t)kx + (uint64_t)g.nx * ((uint64_t)ky + (uint64_t)g.ny * (uint64_t)kz);
-}
+constexpr uint64_t kDenseMaxCells = 1ull << 35;  // 5.7 GB of units
+constexpr int kPersistentCtas = kNumSMs * 8;
 
 __device__ __forceinline__ uint64_t cell_of_key(const GridDev& g, uint64_t key) {
   const uint64_t kx = key & 0x1fffff, ky = (key >> 21) & 0x1fffff, kz = (key >> 42) & 0x1fffff;
@@ -63,22 +45,103 @@ __device__ __forceinline__ uint64_t cell_of_key(const GridDev& g, uint64_t key) 
   return kx + (uint64_t)g.nx * (ky + (uint64_t)g.ny * kz);
 }
 
-__device__ __forceinline__ void set_cell_bit(uint32_t* __restrict__ units, uint64_t cell) {
-  const uint32_t w32 = (uint32_t)(cell >> 5);  // word index in a plain bitmap
-  const uint32_t unit = w32 / 3u;
-  atomicOr(units + (size_t)unit * 4 + (w32 - unit * 3u), 1u << (cell & 31));
+// ---- session set-up -------------------------------------------------------------------------------
+struct BoxPtrs {
+  const int* p[DDN_MAX_PEERS];
+  int n;
+};
+
+// Grid from the union of n encoded bounding boxes (possibly in peer memory).  origin = (floor(min / voxel)
+// - 1) * voxel, dims = floor((max - origin) / voxel) + 2: one cell of slack on either side, so float32
+// rounding of the origin can never push a boxed point out of the grid.
+__global__ void grid_from_bbox_kernel(BoxPtrs boxes, float voxel, long long cap_units, GridDev* __restrict__ out,
+                                      unsigned long long* __restrict__ counts) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int lo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, hi[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
+  for (int b = 0; b < boxes.n; ++b)
+    for (int i = 0; i < 3; ++i) {
+      lo[i] = min(lo[i], __ldcv(boxes.p[b] + i));
+      hi[i] = max(hi[i], __ldcv(boxes.p[b] + 3 + i));
+    }
+  GridDev g;
+  g.voxel = voxel;
+  g.status = DDN_GRID_OK;
+  g.reserved = 0;
+  float o[3] = {0.f, 0.f, 0.f};
+  int dims[3] = {0, 0, 0}, bits[3] = {1, 1, 1};
+  for (int i = 0; i < 3; ++i) {
+    float flo = ordered_to_float(lo[i]), fhi = ordered_to_float(hi[i]);
+    if (!(fabsf(flo) < INFINITY) || !(fabsf(fhi) < INFINITY) || flo > fhi) {
+      g.status = DDN_GRID_EMPTY;
+      continue;
+    }
+    // the box may come from another kernel's float32 arithmetic (K3's tile corners): widen it by ~32 ulp
+    const float slack = 4e-6f * fmaxf(fabsf(flo), fabsf(fhi));
+    flo -= slack, fhi += slack;
+    o[i] = __fmul_rn(floorf(__fdiv_rn(flo, voxel)) - 1.f, voxel);
+    const float c = floorf(__fdiv_rn(__fsub_rn(fhi, o[i]), voxel)) + 2.f;
+    if (!(c <= 2097152.f)) {
+      if (g.status == DDN_GRID_OK) g.status = DDN_GRID_TOO_MANY_BITS;
+      continue;
+    }
+    dims[i] = (int)c;
+    int bb = 1;
+    while ((1 << bb) < dims[i]) ++bb;
+    bits[i] = bb;
+  }
+  g.ox = o[0], g.oy = o[1], g.oz = o[2];
+  g.nx = dims[0], g.ny = dims[1], g.nz = dims[2];
+  g.bx = bits[0], g.by = bits[1], g.bz = bits[2];
+  g.cells = (long long)dims[0] * (long long)dims[1] * (long long)dims[2];
+  g.n_units = (g.cells + kUnitBits - 1) / kUnitBits;
+  if (g.status == DDN_GRID_OK && g.n_units > cap_units) g.status = DDN_GRID_TOO_LARGE;
+  if (g.status != DDN_GRID_OK) g.n_units = 0;
+  *out = g;
+  counts[0] = 0ull;
+  counts[1] = 0ull;
 }
 
+__global__ void grid_store_kernel(GridDev g, long long cap_units, GridDev* __restrict__ out, unsigned long long* __restrict__ counts) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (g.n_units > cap_units) g.status = DDN_GRID_TOO_LARGE, g.n_units = 0;
+  *out = g;
+  counts[0] = 0ull;
+  counts[1] = 0ull;
+}
+
+// Clears the occupancy for a new step.  With dirty flags only the scan tiles the previous step touched are
+// cleared (and their flags reset); without, the units the new grid uses.
+__global__ void __launch_bounds__(256)
+clear_units_kernel(const GridDev* __restrict__ gp, uint4* __restrict__ units, uint8_t* __restrict__ dirty, long long cap_units) {
+  if (dirty != nullptr) {
+    const long long cap_tiles = (cap_units + kTileUnits - 1) / kTileUnits;
+    for (long long t = blockIdx.x; t < cap_tiles; t += gridDim.x) {
+      if (dirty[t] == 0) continue;  // CTA-uniform
+      const long long u0 = t * kTileUnits, u1 = min(u0 + (long long)kTileUnits, cap_units);
+      for (long long u = u0 + threadIdx.x; u < u1; u += blockDim.x) units[u] = make_uint4(0, 0, 0, 0);
+      __syncthreads();
+      if (threadIdx.x == 0) dirty[t] = 0;
+    }
+    return;
+  }
+  const long long n = gp->n_units;
+  for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < n; u += (long long)gridDim.x * blockDim.x)
+    units[u] = make_uint4(0, 0, 0, 0);
+}
+
+// ---- mark (stand-alone form) -----------------------------------------------------------------------
 constexpr int kMarkPX = 4;  // consecutive points per thread
 
-// mark: a thread owns 4 consecutive points; a cell equal to its predecessor (in the thread, or the last
-// cell of the previous lane) is not marked again.  Consecutive pixels of a depth map fall into the same
-// or neighbouring voxels, so this removes most of the atomics.
+// A thread owns 4 consecutive points; a cell equal to its predecessor (in the thread, or the last cell
+// of the previous lane) is not marked again.  Consecutive pixels of a depth map fall into the same or
+// neighbouring voxels, so this removes most of the atomics.
 template <bool kVec>
 __global__ void __launch_bounds__(256)
-mark_points_kernel(GridDev g, float rv, int64_t n, const float* __restrict__ xyz, const uint8_t* __restrict__ votes, int thr,
-                   uint32_t* __restrict__ units, unsigned long long* __restrict__ n_in) {
+mark_points_kernel(FuseDev f, int64_t n, const float* __restrict__ xyz, const uint8_t* __restrict__ votes, int thr) {
   __shared__ int s_count;
+  const GridDev g = *f.grid;
+  if (g.n_units == 0) return;
+  const float rv = 1.0f / g.voxel;
   if (threadIdx.x == 0) s_count = 0;
   __syncthreads();
   const int64_t base = ((int64_t)blockIdx.x * 256 + threadIdx.x) * kMarkPX;
@@ -119,65 +182,94 @@ mark_points_kernel(GridDev g, float rv, int64_t n, const float* __restrict__ xyz
   for (int j = 0; j < kMarkPX; ++j) {
     if (cell[j] != kNoCell) {
       ++mine;
-      if (cell[j] != prev) set_cell_bit(units, cell[j]);
+      if (cell[j] != prev) set_cell_bit(f.units, f.dirty, cell[j]);
     }
     prev = cell[j];
   }
   mine = __reduce_add_sync(0xffffffffu, mine);
   if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_count, mine);
   __syncthreads();
-  if (threadIdx.x == 0 && s_count) atomicAdd(n_in, (unsigned long long)s_count);
+  if (threadIdx.x == 0 && s_count) atomicAdd(f.counts, (unsigned long long)s_count);
 }
 
+// records source (legacy merge): cells outside [cell_begin, cell_end) are not owned by this call
 __global__ void __launch_bounds__(256)
-mark_records_kernel(GridDev g, int64_t n, const uint64_t* __restrict__ records, uint32_t* __restrict__ units,
-                    uint64_t cell_begin, uint64_t cell_end, unsigned long long* __restrict__ n_in) {
+mark_records_kernel(FuseDev f, int64_t n, const uint64_t* __restrict__ records, uint64_t cell_begin, uint64_t cell_end) {
   __shared__ int s_count;
+  const GridDev g = *f.grid;
+  if (g.n_units == 0) return;
   if (threadIdx.x == 0) s_count = 0;
   __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   uint64_t cell = i < n ? cell_of_key(g, __ldg(records + i * kRecWords)) : kNoCell;
-  if (cell < cell_begin || cell >= cell_end) cell = kNoCell;  // not owned by this call's tile range
-  if (cell != kNoCell) set_cell_bit(units, cell);
+  if (cell < cell_begin || cell >= cell_end) cell = kNoCell;
+  if (cell != kNoCell) set_cell_bit(f.units, f.dirty, cell);
   const int c = __popc(__ballot_sync(0xffffffffu, cell != kNoCell));
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_count, c);
   __syncthreads();
-  if (threadIdx.x == 0 && s_count) atomicAdd(n_in, (unsigned long long)s_count);
+  if (threadIdx.x == 0 && s_count) atomicAdd(f.counts, (unsigned long long)s_count);
 }
 
 // ---- rank: popcount scan over the units --------------------------------------------------------
 __device__ __forceinline__ int popc3(const uint4& u) { return __popc(u.x) + __popc(u.y) + __popc(u.z); }
 
-__global__ void __launch_bounds__(kScanThreads)
-tile_count_kernel(const uint4* __restrict__ units, uint32_t n_units, uint32_t tile_begin, uint32_t* __restrict__ tile_sums) {
-  __shared__ int s_warp[kScanThreads / 32];
-  const uint32_t base = (tile_begin + blockIdx.x) * kTileUnits;
-  int sum = 0;
-#pragma unroll
-  for (int j = 0; j < kUnitsPerThread; ++j) {
-    const uint32_t ui = base + j * kScanThreads + threadIdx.x;
-    if (ui < n_units) sum += popc3(__ldg(units + ui));
-  }
-  sum = __reduce_add_sync(0xffffffffu, sum);
-  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = sum;
+// Range of scan tiles a rank pass covers: [tile_begin, tile_begin + n_tiles); n_tiles < 0 = every tile of
+// the device grid.
+struct ScanRange {
+  long long tile_begin, n_tiles;
+};
+__device__ __forceinline__ long long scan_tiles(const ScanRange& r, long long n_units) {
+  return r.n_tiles >= 0 ? r.n_tiles : (n_units + kTileUnits - 1) / kTileUnits;
+}
+
+__device__ __forceinline__ int block_sum_256(int v, int* s_warp) {
+  v = __reduce_add_sync(0xffffffffu, v);
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = v;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int t = 0;
+  int t = 0;
 #pragma unroll
-    for (int w = 0; w < kScanThreads / 32; ++w) t += s_warp[w];
-    tile_sums[blockIdx.x] = (uint32_t)t;
+  for (int w = 0; w < kScanThreads / 32; ++w) t += s_warp[w];
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+tile_count_kernel(const GridDev* __restrict__ gp, const uint4* __restrict__ units, const uint8_t* __restrict__ dirty,
+                  ScanRange range, uint32_t* __restrict__ tile_sums) {
+  __shared__ int s_warp[kScanThreads / 32];
+  const long long n_units = gp->n_units;
+  const long long tiles = scan_tiles(range, n_units);
+  for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const long long tile = range.tile_begin + t;
+    if (dirty != nullptr && dirty[tile] == 0) {  // untouched since the last clean-up: empty (CTA-uniform)
+      if (threadIdx.x == 0) tile_sums[t] = 0u;
+      continue;
+    }
+    const long long base = tile * kTileUnits;
+    int sum = 0;
+#pragma unroll
+    for (int j = 0; j < kUnitsPerThread; ++j) {
+      const long long ui = base + j * kScanThreads + threadIdx.x;
+      if (ui < n_units) sum += popc3(__ldg(units + ui));
+    }
+    const int total = block_sum_256(sum, s_warp);
+    if (threadIdx.x == 0) tile_sums[t] = (uint32_t)total;
   }
 }
 
-// exclusive scan of the tile sums in place (one CTA), total -> counts_out[1]
-__global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t* __restrict__ tile_sums, int tiles, int64_t* __restrict__ counts_out) {
+// exclusive scan of the tile sums in place (one CTA), total -> counts[1] and tile_sums[tiles].
+// n_from_plan: the number of entries is plan[1] - plan[0] (merge over a device-side tile range).
+__global__ void __launch_bounds__(1024)
+tile_scan_kernel(const GridDev* __restrict__ gp, ScanRange range, const long long* __restrict__ plan,
+                 uint32_t* __restrict__ tile_sums, unsigned long long* __restrict__ counts) {
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_carry;
+  const long long tiles = plan != nullptr ? plan[1] - plan[0] : scan_tiles(range, gp->n_units);
   if (threadIdx.x == 0) s_carry = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int base = 0; base < tiles; base += 1024) {
-    const int i = base + threadIdx.x;
+  for (long long base = 0; base < tiles; base += 1024) {
+    const long long i = base + threadIdx.x;
     const uint32_t v = i < tiles ? tile_sums[i] : 0u;
     uint32_t inc = v;
 #pragma unroll
@@ -205,91 +297,105 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t* __restrict__ 
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    counts_out[1] = (int64_t)s_carry;
+    counts[1] = (unsigned long long)s_carry;
     tile_sums[tiles] = s_carry;  // exclusive prefix with the total appended: [tiles + 1] entries
   }
 }
 
-// Per unit: exclusive rank prefix -> word w of the unit.  Per set bit: canonical key of the cell ->
-// keys[slot].  The cell coordinates are decoded once per non-empty unit and then stepped along x.
-__global__ void __launch_bounds__(kScanThreads)
-unit_prefix_kernel(GridDev g, uint4* __restrict__ units, uint32_t n_units, uint32_t tile_begin,
-                   const uint32_t* __restrict__ tile_excl, uint64_t* __restrict__ keys, int key_stride,
-                   uint32_t* __restrict__ own_prefix, uint32_t own_tiles) {
-  __shared__ uint32_t s_warp[kScanThreads / 32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t base = (tile_begin + blockIdx.x) * kTileUnits;
-  uint32_t carry = tile_excl[blockIdx.x];
-  const uint32_t own0 = (tile_begin + blockIdx.x) * kOwnPerScanTile;
-  // empty tile (most of the grid is): its units keep the zero prefix word of the memset and are never
-  // looked up, nothing to emit
-  if (tile_excl[blockIdx.x + 1] == carry) {
-    if (own_prefix != nullptr && threadIdx.x <= kOwnPerScanTile && own0 + threadIdx.x <= own_tiles &&
-        (threadIdx.x < kOwnPerScanTile || blockIdx.x == gridDim.x - 1))
-      own_prefix[own0 + threadIdx.x] = carry;
-    return;
-  }
-  const uint64_t nxy = (uint64_t)g.nx * (uint64_t)g.ny;
-#pragma unroll 1
-  for (int j = 0; j < kUnitsPerThread; ++j) {
-    const uint32_t ui = base + j * kScanThreads + threadIdx.x;
-    uint4 u = make_uint4(0, 0, 0, 0);
-    if (ui < n_units) u = __ldg(units + ui);
-    const uint32_t cnt = (uint32_t)popc3(u);
-    uint32_t inc = cnt;
+// canonical keys of the set bits of one unit -> keys[slot...] (slots >= cap are dropped)
+__device__ __forceinline__ void emit_unit_keys(const GridDev& g, uint64_t nxy, long long ui, const uint4& u, uint32_t slot,
+                                               uint64_t* __restrict__ keys, int key_stride, long long cap) {
+  const uint64_t cell0 = (uint64_t)ui * kUnitBits;
+  uint32_t kz = (uint32_t)(cell0 / nxy);
+  const uint64_t rem = cell0 - (uint64_t)kz * nxy;
+  uint32_t ky = (uint32_t)(rem / (uint64_t)g.nx);
+  const uint32_t kx0 = (uint32_t)(rem - (uint64_t)ky * (uint64_t)g.nx);
+  const uint32_t w[3] = {u.x, u.y, u.z};
+  uint32_t row_off = 0;  // bits of this unit that belong to earlier rows
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
-      if (lane >= d) inc += t;
-    }
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    uint32_t before = 0, total = 0;
-#pragma unroll
-    for (int q = 0; q < kScanThreads / 32; ++q) {
-      const uint32_t s = s_warp[q];
-      before += q < warp ? s : 0u;
-      total += s;
-    }
-    __syncthreads();
-    uint32_t slot = carry + before + inc - cnt;
-    if (own_prefix != nullptr && threadIdx.x == 0 && own0 + j <= own_tiles) own_prefix[own0 + j] = carry;
-    carry += total;
-    if (ui < n_units) units[ui].w = slot;
-    if (cnt) {
-      const uint64_t cell0 = (uint64_t)ui * kUnitBits;
-      uint32_t kz = (uint32_t)(cell0 / nxy);
-      const uint64_t rem = cell0 - (uint64_t)kz * nxy;
-      uint32_t ky = (uint32_t)(rem / (uint64_t)g.nx);
-      const uint32_t kx0 = (uint32_t)(rem - (uint64_t)ky * (uint64_t)g.nx);
-      const uint32_t w[3] = {u.x, u.y, u.z};
-      uint32_t row_off = 0;  // bits of this unit that belong to earlier rows
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        uint32_t bits = w[i];
-        while (bits) {
-          const int b = __ffs(bits) - 1;
-          bits &= bits - 1;
-          uint32_t kx = kx0 + (uint32_t)(i * 32 + b) - row_off;
-          while (kx >= (uint32_t)g.nx) {  // the unit straddles a row end
-            kx -= (uint32_t)g.nx;
-            row_off += (uint32_t)g.nx;
-            if (++ky >= (uint32_t)g.ny) ky = 0, ++kz;
-          }
-          keys[(size_t)(slot++) * key_stride] = (uint64_t)kx | ((uint64_t)ky << 21) | ((uint64_t)kz << 42);
-        }
+  for (int i = 0; i < 3; ++i) {
+    uint32_t bits = w[i];
+    while (bits) {
+      const int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      uint32_t kx = kx0 + (uint32_t)(i * 32 + b) - row_off;
+      while (kx >= (uint32_t)g.nx) {  // the unit straddles a row end
+        kx -= (uint32_t)g.nx;
+        row_off += (uint32_t)g.nx;
+        if (++ky >= (uint32_t)g.ny) ky = 0, ++kz;
       }
+      if ((long long)slot < cap) keys[(size_t)slot * key_stride] = (uint64_t)kx | ((uint64_t)ky << 21) | ((uint64_t)kz << 42);
+      ++slot;
     }
   }
-  if (own_prefix != nullptr && threadIdx.x == 0 && blockIdx.x == gridDim.x - 1 && own0 + kOwnPerScanTile <= own_tiles)
-    own_prefix[own0 + kOwnPerScanTile] = carry;  // total, when the ownership tiles end exactly at this scan tile
 }
 
-// accumulators of the counts[1] voxels -> 0 (device-side count, no host round trip)
+// Per unit: exclusive rank prefix -> word w of the unit.  Per set bit: canonical key of the cell ->
+// keys[slot].  own_prefix (optional): record index at every ownership-tile boundary, [own_tiles + 1].
+__global__ void __launch_bounds__(kScanThreads)
+unit_prefix_kernel(const GridDev* __restrict__ gp, uint4* __restrict__ units, ScanRange range,
+                   const uint32_t* __restrict__ tile_excl, uint64_t* __restrict__ keys, int key_stride, long long cap,
+                   uint32_t* __restrict__ own_prefix) {
+  __shared__ uint32_t s_warp[kScanThreads / 32];
+  const GridDev g = *gp;
+  const long long n_units = g.n_units;
+  const long long tiles = scan_tiles(range, n_units);
+  const long long own_tiles = (n_units + kOwnUnits - 1) / kOwnUnits;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t nxy = (uint64_t)g.nx * (uint64_t)g.ny;
+  for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const long long tile = range.tile_begin + t;
+    const long long base = tile * kTileUnits;
+    uint32_t carry = tile_excl[t];
+    const long long own0 = tile * kOwnPerScanTile;
+    const bool last = t == tiles - 1;
+    // empty tile (most of the grid is): its units keep the zero prefix word of the clean-up and are never
+    // looked up, nothing to emit
+    if (tile_excl[t + 1] == carry) {
+      if (own_prefix != nullptr && threadIdx.x <= kOwnPerScanTile && own0 + threadIdx.x <= own_tiles &&
+          (threadIdx.x < kOwnPerScanTile || last))
+        own_prefix[own0 + threadIdx.x] = carry;
+      continue;
+    }
+#pragma unroll 1
+    for (int j = 0; j < kUnitsPerThread; ++j) {
+      const long long ui = base + j * kScanThreads + threadIdx.x;
+      uint4 u = make_uint4(0, 0, 0, 0);
+      if (ui < n_units) u = __ldg(units + ui);
+      const uint32_t cnt = (uint32_t)popc3(u);
+      uint32_t inc = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t tt = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += tt;
+      }
+      if (lane == 31) s_warp[warp] = inc;
+      __syncthreads();
+      uint32_t before = 0, total = 0;
+#pragma unroll
+      for (int q = 0; q < kScanThreads / 32; ++q) {
+        const uint32_t s = s_warp[q];
+        before += q < warp ? s : 0u;
+        total += s;
+      }
+      __syncthreads();
+      const uint32_t slot = carry + before + inc - cnt;
+      if (own_prefix != nullptr && threadIdx.x == 0 && own0 + j <= own_tiles) own_prefix[own0 + j] = carry;
+      carry += total;
+      if (ui < n_units) units[ui].w = slot;
+      if (cnt) emit_unit_keys(g, nxy, ui, u, slot, keys, key_stride, cap);
+    }
+    if (own_prefix != nullptr && threadIdx.x == 0 && last && own0 + kOwnPerScanTile <= own_tiles)
+      own_prefix[own0 + kOwnPerScanTile] = carry;  // total, when the ownership tiles end exactly at this scan tile
+  }
+}
+
+// accumulators of the min(counts[1], cap) voxels -> 0 (device-side count, no host round trip)
 __global__ void __launch_bounds__(256)
-zero_accum_kernel(ulonglong2* __restrict__ accum2, const int64_t* __restrict__ counts, int words_per_voxel) {
-  const int64_t n2 = (counts[1] * words_per_voxel + 1) / 2;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x)
+zero_accum_kernel(ulonglong2* __restrict__ accum2, const unsigned long long* __restrict__ counts, int words_per_voxel, long long cap) {
+  const long long mv = min((long long)counts[1], cap);
+  const long long n2 = (mv * words_per_voxel + 1) / 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x)
     accum2[i] = make_ulonglong2(0ull, 0ull);
 }
 
@@ -308,10 +414,11 @@ __device__ __forceinline__ uint32_t slot_of_cell(uint64_t cell, const uint4* __r
 
 // accumulate: one point per lane, aggregated ACROSS THE WARP before touching memory.  With a row length
 // (points are pixels of [rows, row_len] images) a warp covers a 16 x 2 pixel tile, otherwise 32
-// consecutive points (the tile shape is kAccTileW).  Lanes whose points fall into the same cell are found with MATCH.ANY; every lane
-// walks its peer mask with shuffles (32-bit partial sums: at most 32 points of |offset| <= 2^19), and
-// the lowest lane of each group looks the slot up and issues the five 64-bit REDs.  The L2 atomic units
-// are the bound of this pass, so points per RED group is what matters: ~2 at cfg 2.
+// consecutive points.  Lanes whose points fall into the same cell are found with MATCH.ANY and summed
+// with REDUX over that peer mask (32-bit partial sums: at most 32 points of |offset| <= 2^19); the
+// lowest lane of each group looks the slot up and issues the five 64-bit REDs.  The L2 atomic units are
+// the bound of this pass, so points per RED group is what matters: ~2 at cfg 2.
+// (-DDDN_ACC_SHFL: the round-1 aggregation, a shuffle walk over the peer mask.)
 #ifndef DDN_ACC_TPW
 #define DDN_ACC_TPW 8
 #endif
@@ -320,9 +427,12 @@ constexpr int kAccTileW = 16;  // pixel tile of a warp: 16 x 2 (measured at cfg 
 
 template <int kTW>  // tile width in pixels (tile = kTW x 32/kTW); 0 = no row structure, 32 consecutive points
 __global__ void __launch_bounds__(256)
-accumulate_points_kernel(GridDev g, float rv, int64_t n, int row_len, const float* __restrict__ xyz,
+accumulate_points_kernel(const GridDev* __restrict__ gp, int64_t n, int row_len, const float* __restrict__ xyz,
                          const uint8_t* __restrict__ rgb, const uint8_t* __restrict__ votes, int thr,
-                         const uint4* __restrict__ units, unsigned long long* __restrict__ accum, int stride) {
+                         const uint4* __restrict__ units, unsigned long long* __restrict__ accum, int stride, long long cap) {
+  const GridDev g = *gp;
+  if (g.n_units == 0) return;
+  const float rv = 1.0f / g.voxel;
   const int lane = threadIdx.x & 31;
   const float fix_scale = voxel_fix_scale(g.voxel);
   // n < 2^31, so tile indices fit 32 bits
@@ -397,9 +507,10 @@ accumulate_points_kernel(GridDev g, float rv, int64_t n, int row_len, const floa
     uint32_t peers = __match_any_sync(0xffffffffu, cell);
     if (!valid) peers = 0;
     const bool leader = valid && (__ffs(peers) - 1) == lane;
-    const int iters = __reduce_max_sync(0xffffffffu, __popc(peers));
     int sx = 0, sy = 0, sz = 0;
     uint32_t srg = 0, sb = 0;
+#ifdef DDN_ACC_SHFL
+    const int iters = __reduce_max_sync(0xffffffffu, __popc(peers));
     uint32_t rest = peers;
 #pragma unroll 1
     for (int k = 0; k < iters; ++k) {
@@ -411,38 +522,56 @@ accumulate_points_kernel(GridDev g, float rv, int64_t n, int row_len, const floa
       const uint32_t arg = __shfl_sync(0xffffffffu, rg, src), ab = __shfl_sync(0xffffffffu, bb, src);
       if (has) sx += ax, sy += ay, sz += az, srg += arg, sb += ab;
     }
+#else
+    if (valid) {  // every lane of a group passes the same mask: REDUX over the group only
+      sx = __reduce_add_sync(peers, ox);
+      sy = __reduce_add_sync(peers, oy);
+      sz = __reduce_add_sync(peers, oz);
+      srg = __reduce_add_sync(peers, rg);
+      sb = __reduce_add_sync(peers, bb);
+    }
+#endif
     if (leader) {
-      unsigned long long* a = accum + (size_t)slot_of_cell(cell, units) * stride;
-      atomicAdd(a + 0, (unsigned long long)(long long)sx);
-      atomicAdd(a + 1, (unsigned long long)(long long)sy);
-      atomicAdd(a + 2, (unsigned long long)(long long)sz);
-      atomicAdd(a + 3, ((unsigned long long)(srg >> 16) << 32) | (srg & 0xffffu));
-      atomicAdd(a + 4, ((unsigned long long)sb << 32) | (unsigned)__popc(peers));
+      const uint32_t slot = slot_of_cell(cell, units);
+      if ((long long)slot < cap) {
+        unsigned long long* a = accum + (size_t)slot * stride;
+        atomicAdd(a + 0, (unsigned long long)(long long)sx);
+        atomicAdd(a + 1, (unsigned long long)(long long)sy);
+        atomicAdd(a + 2, (unsigned long long)(long long)sz);
+        atomicAdd(a + 3, ((unsigned long long)(srg >> 16) << 32) | (srg & 0xffffu));
+        atomicAdd(a + 4, ((unsigned long long)sb << 32) | (unsigned)__popc(peers));
+      }
     }
   }
 }
 
 __global__ void __launch_bounds__(256)
-accumulate_records_kernel(GridDev g, int64_t n, const unsigned long long* __restrict__ records, const uint4* __restrict__ units,
-                          uint64_t cell_begin, uint64_t cell_end, unsigned long long* __restrict__ accum) {
+accumulate_records_kernel(const GridDev* __restrict__ gp, int64_t n, const unsigned long long* __restrict__ records,
+                          const uint4* __restrict__ units, uint64_t cell_begin, uint64_t cell_end,
+                          unsigned long long* __restrict__ accum, long long cap) {
+  const GridDev g = *gp;
+  if (g.n_units == 0) return;
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
   const unsigned long long* r = records + i * kRecWords;
   const uint64_t cell = cell_of_key(g, __ldg(r));
   if (cell == kNoCell || cell < cell_begin || cell >= cell_end) return;
-  unsigned long long* a = accum + (size_t)slot_of_cell(cell, units) * kAccWords;
+  const uint32_t slot = slot_of_cell(cell, units);
+  if ((long long)slot >= cap) return;
+  unsigned long long* a = accum + (size_t)slot * kAccWords;
 #pragma unroll
   for (int q = 0; q < kAccWords; ++q) atomicAdd(a + q, __ldg(r + 1 + q));
 }
 
 // One thread per voxel.  The colour fields are 32 bits wide: a voxel with 2^24 or more points could
-// have overflowed them, which is reported (counts_out[0] = -1) instead of returned as a wrong colour.
+// have overflowed them, which is reported (counts[0] = -1) instead of returned as a wrong colour.
 __global__ void __launch_bounds__(256)
-finalize_kernel(GridDev g, const unsigned long long* __restrict__ accum, const uint64_t* __restrict__ keys,
-                int64_t* __restrict__ counts, float* __restrict__ out_xyz, uint8_t* __restrict__ out_rgb,
+finalize_kernel(const GridDev* __restrict__ gp, const unsigned long long* __restrict__ accum, const uint64_t* __restrict__ keys,
+                long long* __restrict__ counts, long long cap, float* __restrict__ out_xyz, uint8_t* __restrict__ out_rgb,
                 int32_t* __restrict__ out_count) {
-  const int64_t mv = counts[1];
-  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < mv; r += (int64_t)gridDim.x * blockDim.x) {
+  const GridDev g = *gp;
+  const long long mv = min(counts[1], cap);
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < mv; r += (long long)gridDim.x * blockDim.x) {
     const unsigned long long* a = accum + (size_t)r * kAccWords;
     const long long sx = (long long)a[0], sy = (long long)a[1], sz = (long long)a[2];
     const unsigned long long rg = a[3], bn = a[4];
@@ -467,14 +596,269 @@ __global__ void canonical_key_kernel(GridDev g, int64_t n, const float* __restri
   keys[i] = ok ? ((uint64_t)kx | ((uint64_t)ky << 21) | ((uint64_t)kz << 42)) : ~0ull;
 }
 
-// ---- host side ---------------------------------------------------------------------------------
-struct DenseLayout {
-  uint64_t cells, n_units, tiles, own_tiles;
-  size_t units, units_bytes, tile_sums, accum, total;
+// ====================================================================================================
+// Multi-GPU: owner-side exchange + merge over peer memory
+// ====================================================================================================
+// plan (device, i64): [0] first owned tile, [1] end of owned tiles, [2] records to receive, [3] own tiles,
+// [4 + q] first record of this rank's share in rank q's records, [4 + P + q] its length, [4 + 2P + q] exclusive
+// prefix of the lengths (P = DDN_MAX_PEERS).
+constexpr int kPlanWords = 4 + 3 * DDN_MAX_PEERS;
+static_assert(kPlanWords <= 64, "plan scratch is 64 words");
+
+struct PeerPtrs {
+  const void* p[DDN_MAX_PEERS];
 };
 
+// The R ranks cut the ownership tiles into R contiguous ranges that balance the GLOBAL record count:
+// cum[t] = sum over ranks of tile_prefix_q[t] is the number of records in tiles [0, t); boundary b is the
+// first t with cum[t] >= total * b / R.  Every rank runs the same search on the same (peer-visible) arrays,
+// so all agree without communicating.  One warp per boundary, one lane per rank per probe.
+__global__ void __launch_bounds__(32 * DDN_MAX_PEERS)
+merge_plan_kernel(const GridDev* __restrict__ gp, PeerPtrs prefix, int rank, int R, long long* __restrict__ plan) {
+  __shared__ long long s_bnd[DDN_MAX_PEERS + 1];
+  const long long n_own = (gp->n_units + kOwnUnits - 1) / kOwnUnits;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  auto cum_at = [&](long long t) -> long long {  // warp-collective
+    long long v = 0;
+    if (lane < R) v = (long long)__ldcv(reinterpret_cast<const uint32_t*>(prefix.p[lane]) + t);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+  };
+  if (warp >= 1 && warp < R) {
+    const long long total = cum_at(n_own);
+    const long long target = total * warp / R;
+    long long lo = 0, hi = n_own + 1;
+    while (lo < hi) {
+      const long long mid = (lo + hi) >> 1;
+      if (cum_at(mid) < target) lo = mid + 1;
+      else hi = mid;
+    }
+    if (lane == 0) s_bnd[warp] = min(lo, n_own);
+  }
+  if (threadIdx.x == 0) s_bnd[0] = 0, s_bnd[R] = n_own;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int b = 1; b <= R; ++b) s_bnd[b] = max(s_bnd[b], s_bnd[b - 1]);  // monotone
+    plan[0] = s_bnd[rank];
+    plan[1] = s_bnd[rank + 1];
+    plan[3] = n_own;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    long long begin = 0, count = 0;
+    if (lane < R) {
+      const uint32_t* pq = reinterpret_cast<const uint32_t*>(prefix.p[lane]);
+      begin = (long long)__ldcv(pq + s_bnd[rank]);
+      count = (long long)__ldcv(pq + s_bnd[rank + 1]) - begin;
+    }
+    long long inc = count;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const long long t = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += t;
+    }
+    if (lane < DDN_MAX_PEERS) {
+      plan[4 + lane] = begin;
+      plan[4 + DDN_MAX_PEERS + lane] = count;
+      plan[4 + 2 * DDN_MAX_PEERS + lane] = inc - count;
+    }
+    const long long total = __shfl_sync(0xffffffffu, inc, 31);
+    if (lane == 0) plan[2] = total;
+  }
+}
+
+// local copy of every rank's tile prefix over the owned range [t0, t1]: local[q * stride + (t - t0)]
+__global__ void __launch_bounds__(256)
+merge_copy_prefix_kernel(PeerPtrs prefix, int R, const long long* __restrict__ plan, uint32_t* __restrict__ local, long long stride) {
+  const long long t0 = plan[0], n = plan[1] - t0 + 1;
+  for (int q = 0; q < R; ++q) {
+    const uint32_t* pq = reinterpret_cast<const uint32_t*>(prefix.p[q]);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      local[q * stride + i] = __ldcv(pq + t0 + i);
+  }
+}
+
+// OR of all ranks' occupancy over the owned tiles -> this rank's units (in place: peers only read the units
+// of THEIR ranges), count per tile.  A tile a rank has no record in is not read from that rank.
+__global__ void __launch_bounds__(kOwnUnits)
+merge_or_kernel(FuseDev f, PeerPtrs peer_units, int rank, int R, const long long* __restrict__ plan,
+                const uint32_t* __restrict__ prefix_local, long long stride, uint32_t* __restrict__ tile_sums) {
+  __shared__ int s_warp[kScanThreads / 32];
+  const long long n_units = f.grid->n_units;
+  const long long t0 = plan[0], t1 = plan[1];
+  uint4* my_units = reinterpret_cast<uint4*>(f.units);
+  for (long long t = t0 + blockIdx.x; t < t1; t += gridDim.x) {
+    const long long ui = t * kOwnUnits + threadIdx.x;
+    uint4 m = make_uint4(0, 0, 0, 0);
+    for (int q = 0; q < R; ++q) {
+      const uint32_t* pl = prefix_local + q * stride + (t - t0);
+      if (pl[1] == pl[0]) continue;  // CTA-uniform
+      if (ui < n_units) {
+        const uint4 u = q == rank ? my_units[ui] : __ldcv(reinterpret_cast<const uint4*>(peer_units.p[q]) + ui);
+        m.x |= u.x, m.y |= u.y, m.z |= u.z;
+      }
+    }
+    const int total = block_sum_256(popc3(m), s_warp);
+    // an untouched tile stays untouched; a touched one gets the merged bits (its prefix word follows)
+    if (ui < n_units && total > 0) my_units[ui] = m;
+    if (threadIdx.x == 0) {
+      tile_sums[t - t0] = (uint32_t)total;
+      if (total > 0 && f.dirty != nullptr) f.dirty[(t * kOwnUnits) / kTileUnits] = 1;
+    }
+  }
+}
+
+// rank prefix of the merged units + keys of the merged voxels (one ownership tile per CTA iteration)
+__global__ void __launch_bounds__(kOwnUnits)
+merge_prefix_kernel(FuseDev f, const long long* __restrict__ plan, const uint32_t* __restrict__ tile_excl,
+                    uint64_t* __restrict__ keys, long long cap) {
+  __shared__ uint32_t s_warp[kScanThreads / 32];
+  const GridDev g = *f.grid;
+  const long long n_units = g.n_units;
+  const long long t0 = plan[0], t1 = plan[1];
+  uint4* my_units = reinterpret_cast<uint4*>(f.units);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t nxy = (uint64_t)g.nx * (uint64_t)g.ny;
+  for (long long t = t0 + blockIdx.x; t < t1; t += gridDim.x) {
+    const uint32_t carry = tile_excl[t - t0];
+    if (tile_excl[t - t0 + 1] == carry) continue;  // CTA-uniform
+    const long long ui = t * kOwnUnits + threadIdx.x;
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (ui < n_units) u = my_units[ui];
+    const uint32_t cnt = (uint32_t)popc3(u);
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t tt = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += tt;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t before = 0;
+#pragma unroll
+    for (int q = 0; q < kScanThreads / 32; ++q) before += q < warp ? s_warp[q] : 0u;
+    __syncthreads();
+    const uint32_t slot = carry + before + inc - cnt;
+    if (ui < n_units) my_units[ui].w = slot;
+    if (cnt) emit_unit_keys(g, nxy, ui, u, slot, keys, 1, cap);
+  }
+}
+
+// pull + add: thread i handles one record of this rank's share, read straight out of its owner's HBM
+// (48 contiguous bytes per thread, 1536 per warp: fully coalesced NVLink reads), looked up in the merged
+// units and added with 64-bit REDs.
+__global__ void __launch_bounds__(256)
+merge_accumulate_kernel(FuseDev f, PeerPtrs peer_records, int R, const long long* __restrict__ plan,
+                        unsigned long long* __restrict__ accum, long long cap) {
+  const GridDev g = *f.grid;
+  if (g.n_units == 0) return;
+  const long long total = plan[2];
+  const uint4* units = reinterpret_cast<const uint4*>(f.units);
+  const uint64_t cell_begin = (uint64_t)plan[0] * kOwnUnits * kUnitBits, cell_end = (uint64_t)plan[1] * kOwnUnits * kUnitBits;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int q = 0;
+#pragma unroll
+    for (int k = 1; k < DDN_MAX_PEERS; ++k) q += (k < R && i >= plan[4 + 2 * DDN_MAX_PEERS + k]) ? 1 : 0;
+    const long long j = plan[4 + q] + (i - plan[4 + 2 * DDN_MAX_PEERS + q]);
+    const ulonglong2* r = reinterpret_cast<const ulonglong2*>(reinterpret_cast<const unsigned long long*>(peer_records.p[q]) + j * kRecWords);
+    const ulonglong2 a = __ldcv(r), b = __ldcv(r + 1), c = __ldcv(r + 2);
+    const uint64_t cell = cell_of_key(g, a.x);
+    if (cell == kNoCell || cell < cell_begin || cell >= cell_end) continue;
+    const uint32_t slot = slot_of_cell(cell, units);
+    if ((long long)slot >= cap) continue;
+    unsigned long long* o = accum + (size_t)slot * kAccWords;
+    atomicAdd(o + 0, a.y);
+    atomicAdd(o + 1, b.x);
+    atomicAdd(o + 2, b.y);
+    atomicAdd(o + 3, c.x);
+    atomicAdd(o + 4, c.y);
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
 static uint64_t grid_cells(const GridDev& g) { return (uint64_t)g.nx * (uint64_t)g.ny * (uint64_t)g.nz; }
 static bool use_dense(const GridDev& g) { return grid_cells(g) <= kDenseMaxCells; }
+
+static int session_check(const ddn_fuse_session* s) {
+  DDN_REQUIRE(s != nullptr, "null session");
+  DDN_REQUIRE(s->grid && s->units && s->tile_sums && s->counts, "session: null buffer");
+  DDN_REQUIRE(s->cap_units > 0 && s->cap_units <= (int64_t)(kDenseMaxCells / kUnitBits) + 1, "session: cap_units");
+  DDN_REQUIRE((uintptr_t)s->units % 16 == 0 && (uintptr_t)s->grid % 8 == 0, "session: alignment");
+  return DDN_OK;
+}
+
+static FuseDev fuse_dev(const ddn_fuse_session* s) {
+  FuseDev f;
+  f.grid = reinterpret_cast<const GridDev*>(s->grid);
+  f.units = reinterpret_cast<uint32_t*>(s->units);
+  f.dirty = s->dirty;
+  f.counts = reinterpret_cast<unsigned long long*>(s->counts);
+  return f;
+}
+
+static int launch_clear(const ddn_fuse_session* s, cudaStream_t st) {
+  clear_units_kernel<<<kPersistentCtas, 256, 0, st>>>(reinterpret_cast<const GridDev*>(s->grid), reinterpret_cast<uint4*>(s->units),
+                                                      s->dirty, (long long)s->cap_units);
+  return after_launch("clear_units_kernel");
+}
+
+static int launch_mark_points(const ddn_fuse_session* s, int64_t n, const float* xyz, const uint8_t* votes, int thr, cudaStream_t st) {
+  const bool vec = ((uintptr_t)xyz % 16 == 0) && (votes == nullptr || (uintptr_t)votes % 4 == 0);
+  const unsigned mblocks = (unsigned)((n + 256 * kMarkPX - 1) / (256 * kMarkPX));
+  if (vec) mark_points_kernel<true><<<mblocks, 256, 0, st>>>(fuse_dev(s), n, xyz, votes, thr);
+  else mark_points_kernel<false><<<mblocks, 256, 0, st>>>(fuse_dev(s), n, xyz, votes, thr);
+  return after_launch("mark_points_kernel");
+}
+
+// rank passes over `range` (whole device grid when range.n_tiles < 0): tile counts -> scan -> accumulators
+// cleared -> unit prefixes + keys
+static int launch_rank(const ddn_fuse_session* s, ScanRange range, uint64_t* keys, int key_stride, unsigned long long* zero_base,
+                       int zero_stride, long long cap, uint32_t* own_prefix, cudaStream_t st) {
+  const GridDev* gp = reinterpret_cast<const GridDev*>(s->grid);
+  uint4* units = reinterpret_cast<uint4*>(s->units);
+  unsigned long long* counts = reinterpret_cast<unsigned long long*>(s->counts);
+  const unsigned ctas = range.n_tiles >= 0 ? (unsigned)std::max<long long>(1, std::min<long long>(range.n_tiles, kPersistentCtas))
+                                            : (unsigned)kPersistentCtas;
+  tile_count_kernel<<<ctas, kScanThreads, 0, st>>>(gp, units, s->dirty, range, s->tile_sums);
+  DDN_TRY(after_launch("tile_count_kernel"));
+  tile_scan_kernel<<<1, 1024, 0, st>>>(gp, range, nullptr, s->tile_sums, counts);
+  DDN_TRY(after_launch("tile_scan_kernel"));
+  zero_accum_kernel<<<kPersistentCtas, 256, 0, st>>>((ulonglong2*)zero_base, counts, zero_stride, cap);
+  DDN_TRY(after_launch("zero_accum_kernel"));
+  unit_prefix_kernel<<<ctas, kScanThreads, 0, st>>>(gp, units, range, s->tile_sums, keys, key_stride, cap, own_prefix);
+  return after_launch("unit_prefix_kernel");
+}
+
+static int launch_accumulate_points(const ddn_fuse_session* s, int64_t n, int64_t row_len, const float* xyz, const uint8_t* rgb,
+                                    const uint8_t* votes, int thr, unsigned long long* accum, int stride, long long cap,
+                                    cudaStream_t st) {
+  const GridDev* gp = reinterpret_cast<const GridDev*>(s->grid);
+  const uint4* units = reinterpret_cast<const uint4*>(s->units);
+  const bool tiled = row_len >= 32 && row_len < (1 << 30);
+  const int tw = tiled ? kAccTileW : 0;
+  const int th = tw ? 32 / tw : 1, twe = tw ? tw : 32;
+  const int64_t n_tiles = tiled ? ((row_len + twe - 1) / twe) * (((n + row_len - 1) / row_len + th - 1) / th) : (n + 31) / 32;
+  const unsigned ablocks = (unsigned)((n_tiles + 8 * kAccTilesPerWarp - 1) / (8 * kAccTilesPerWarp));
+  if (tiled)
+    accumulate_points_kernel<kAccTileW><<<ablocks, 256, 0, st>>>(gp, n, (int)row_len, xyz, rgb, votes, thr, units, accum, stride, cap);
+  else
+    accumulate_points_kernel<0><<<ablocks, 256, 0, st>>>(gp, n, (int)row_len, xyz, rgb, votes, thr, units, accum, stride, cap);
+  return after_launch("accumulate_points_kernel");
+}
+
+static int launch_finalize(const ddn_fuse_session* s, const unsigned long long* accum, const uint64_t* keys, long long cap,
+                           float* out_xyz, uint8_t* out_rgb, int32_t* out_count, cudaStream_t st) {
+  finalize_kernel<<<kPersistentCtas, 256, 0, st>>>(reinterpret_cast<const GridDev*>(s->grid), accum, keys,
+                                                   reinterpret_cast<long long*>(s->counts), cap, out_xyz, out_rgb, out_count);
+  return after_launch("finalize_kernel");
+}
+
+// ---- legacy host-grid entry points: a session carved out of the caller's workspace -----------------
+struct DenseLayout {
+  uint64_t cells, n_units, tiles, own_tiles;
+  size_t grid, units, tile_sums, accum, total;
+};
 
 static void dense_layout(const GridDev& g, int64_t n, DenseLayout* L) {  // sized for the non-partial form
   L->cells = grid_cells(g);
@@ -488,108 +872,37 @@ static void dense_layout(const GridDev& g, int64_t n, DenseLayout* L) {  // size
     off += (size_t)align_up((int64_t)bytes, 256);
     return o;
   };
-  L->units_bytes = (size_t)L->n_units * 16;
-  L->units = take(L->units_bytes);
-  L->tile_sums = take((size_t)(L->tiles + 1) * 4);
+  L->grid = take(sizeof(GridDev));
+  L->units = take((size_t)L->n_units * 16);
+  L->tile_sums = take((size_t)(L->own_tiles + 2) * 4);
   L->accum = take((size_t)max_vox * kAccWords * 8 + 16);
   L->total = off + 256;
 }
 
-struct DenseSource {
-  // points
-  const float* xyz = nullptr;
-  const uint8_t* rgb = nullptr;
-  const uint8_t* votes = nullptr;
-  int thr = 0;
-  int64_t row_len = 0;
-  // records
-  const unsigned long long* records = nullptr;
-};
-
-// records_out != nullptr: partial mode (output = records, no finalisation); else final voxels.
-// tile range [tile_begin, tile_end) (records source only; 0, 0 = whole grid): only that slice of the occupancy
-// array is cleared / scanned and records outside it are ignored - an owner rank merges its key range at a
-// cost proportional to its share of the grid.  tile_prefix_out (optional): [tiles + 1] exclusive prefix of
-// the voxel count per tile, i.e. where each tile's records start in the sorted output.
-static int dense_fuse(const GridDev& g, int64_t n, const DenseSource& src, uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb,
-                      int32_t* out_count, unsigned long long* records_out, int64_t* counts_out, void* workspace,
-                      int64_t workspace_bytes, cudaStream_t st, int64_t tile_begin = 0, int64_t tile_end = 0,
-                      uint32_t* tile_prefix_out = nullptr) {
-  DenseLayout L;
-  dense_layout(g, n, &L);
-  // ownership tiles -> owned cell range and the scan tiles that enclose it
-  if (tile_end <= 0) tile_begin = 0, tile_end = (int64_t)L.own_tiles;
-  DDN_REQUIRE(tile_begin >= 0 && tile_begin <= tile_end && tile_end <= (int64_t)L.own_tiles, "tile range");
-  const uint64_t cell_begin = (uint64_t)tile_begin * kOwnUnits * kUnitBits;
-  const uint64_t cell_end = (uint64_t)tile_end * kOwnUnits * kUnitBits;
-  const int64_t own_begin = tile_begin, own_end = tile_end;
-  tile_begin = own_begin / kOwnPerScanTile;
-  tile_end = (own_end + kOwnPerScanTile - 1) / kOwnPerScanTile;
-  const uint32_t n_tiles = own_end > own_begin ? (uint32_t)(tile_end - tile_begin) : 0u;
-  if ((int64_t)L.total > workspace_bytes) {
-    set_error("fuse workspace too small: %lld < %lld", (long long)workspace_bytes, (long long)L.total);
+static int carve_session(const GridDev& g, int64_t n, void* workspace, int64_t workspace_bytes, ddn_fuse_session* s,
+                         int64_t* counts_out, unsigned long long** accum, DenseLayout* L) {
+  dense_layout(g, n, L);
+  if ((int64_t)L->total > workspace_bytes) {
+    set_error("fuse workspace too small: %lld < %lld", (long long)workspace_bytes, (long long)L->total);
     return DDN_ERR_WORKSPACE_TOO_SMALL;
   }
   char* base = reinterpret_cast<char*>(align_up((int64_t)(uintptr_t)workspace, 256));
-  uint4* units = (uint4*)(base + L.units);
-  uint32_t* tile_sums = (uint32_t*)(base + L.tile_sums);
-  const bool partial = records_out != nullptr;
-  // accumulators: words 1..5 of the output records (partial mode) or a workspace array
-  unsigned long long* accum = partial ? records_out + 1 : (unsigned long long*)(base + L.accum);
-  const int stride = partial ? kRecWords : kAccWords;
-  unsigned long long* zero_base = partial ? records_out : accum;
-  uint64_t* keys = partial ? (uint64_t*)records_out : out_keys;
-  const float rv = 1.0f / g.voxel;
-  const unsigned blocks = (unsigned)((n + 255) / 256);
-  const bool points = src.records == nullptr;
-  const bool vec = points && ((uintptr_t)src.xyz % 16 == 0) && (src.votes == nullptr || (uintptr_t)src.votes % 4 == 0);
-  DDN_REQUIRE((uintptr_t)zero_base % 16 == 0, "record / accumulator buffer must be 16-byte aligned");
+  s->grid = reinterpret_cast<ddn_grid_state*>(base + L->grid);
+  s->units = base + L->units;
+  s->cap_units = (int64_t)L->n_units;
+  s->dirty = nullptr;
+  s->tile_sums = reinterpret_cast<uint32_t*>(base + L->tile_sums);
+  s->tile_prefix = nullptr;
+  s->counts = counts_out;
+  *accum = reinterpret_cast<unsigned long long*>(base + L->accum);
+  return DDN_OK;
+}
 
-  DDN_TRY(check_cuda(cudaMemsetAsync(counts_out, 0, 16, st), "memset counts"));
-  if (n_tiles == 0) return DDN_OK;
-  {
-    const size_t ub = (size_t)tile_begin * kTileUnits, ue = std::min((size_t)tile_end * kTileUnits, (size_t)L.n_units);
-    DDN_TRY(check_cuda(cudaMemsetAsync(units + ub, 0, (ue - ub) * 16, st), "memset occupancy"));
-  }
-  if (points) {
-    const unsigned mblocks = (unsigned)((n + 256 * kMarkPX - 1) / (256 * kMarkPX));
-    if (vec)
-      mark_points_kernel<true><<<mblocks, 256, 0, st>>>(g, rv, n, src.xyz, src.votes, src.thr, (uint32_t*)units,
-                                                        (unsigned long long*)counts_out);
-    else
-      mark_points_kernel<false><<<mblocks, 256, 0, st>>>(g, rv, n, src.xyz, src.votes, src.thr, (uint32_t*)units,
-                                                         (unsigned long long*)counts_out);
-  } else {
-    mark_records_kernel<<<blocks, 256, 0, st>>>(g, n, (const uint64_t*)src.records, (uint32_t*)units, cell_begin, cell_end,
-                                                (unsigned long long*)counts_out);
-  }
-  DDN_TRY(after_launch("mark_kernel"));
-  tile_count_kernel<<<n_tiles, kScanThreads, 0, st>>>(units, (uint32_t)L.n_units, (uint32_t)tile_begin, tile_sums);
-  DDN_TRY(after_launch("tile_count_kernel"));
-  tile_scan_kernel<<<1, 1024, 0, st>>>(tile_sums, (int)n_tiles, counts_out);
-  DDN_TRY(after_launch("tile_scan_kernel"));
-  zero_accum_kernel<<<kNumSMs * 8, 256, 0, st>>>((ulonglong2*)zero_base, counts_out, stride);
-  DDN_TRY(after_launch("zero_accum_kernel"));
-  unit_prefix_kernel<<<n_tiles, kScanThreads, 0, st>>>(g, units, (uint32_t)L.n_units, (uint32_t)tile_begin, tile_sums, keys,
-                                                       partial ? kRecWords : 1, tile_prefix_out, (uint32_t)L.own_tiles);
-  DDN_TRY(after_launch("unit_prefix_kernel"));
-  if (points) {
-    const bool tiled = src.row_len >= 32 && src.row_len < (1 << 30);
-    const int tw = tiled ? kAccTileW : 0;
-    const int th = tw ? 32 / tw : 1, twe = tw ? tw : 32;
-    const int64_t n_tiles = tiled ? ((src.row_len + twe - 1) / twe) * (((n + src.row_len - 1) / src.row_len + th - 1) / th) : (n + 31) / 32;
-    const unsigned ablocks = (unsigned)((n_tiles + 8 * kAccTilesPerWarp - 1) / (8 * kAccTilesPerWarp));
-#define DDN_ACC(TW) accumulate_points_kernel<TW><<<ablocks, 256, 0, st>>>(g, rv, n, (int)src.row_len, src.xyz, src.rgb, src.votes, src.thr, units, accum, stride)
-    if (tw == kAccTileW) DDN_ACC(kAccTileW);
-    else DDN_ACC(0);
-#undef DDN_ACC
-  } else {
-    accumulate_records_kernel<<<blocks, 256, 0, st>>>(g, n, src.records, units, cell_begin, cell_end, accum);
-  }
-  DDN_TRY(after_launch("accumulate_kernel"));
-  if (partial) return DDN_OK;
-  finalize_kernel<<<kNumSMs * 8, 256, 0, st>>>(g, accum, out_keys, counts_out, out_xyz, out_rgb, out_count);
-  return after_launch("finalize_kernel");
+static int begin_with_grid(const ddn_fuse_session* s, const GridDev& g, cudaStream_t st) {
+  grid_store_kernel<<<1, 32, 0, st>>>(g, (long long)s->cap_units, reinterpret_cast<GridDev*>(s->grid),
+                                      reinterpret_cast<unsigned long long*>(s->counts));
+  DDN_TRY(after_launch("grid_store_kernel"));
+  return launch_clear(s, st);
 }
 
 }  // namespace ddn
@@ -625,14 +938,22 @@ int ddn_voxel_fuse(const ddn_voxel_grid* grid_host, int64_t n_points, int64_t ro
   DDN_REQUIRE(row_len >= 0, "row_len");
   DDN_REQUIRE(counts_out != nullptr, "null counts_out");
   cudaStream_t st = (cudaStream_t)stream;
+  vote_threshold = std::min(vote_threshold, 255);
   if (n_points == 0) return check_cuda(cudaMemsetAsync(counts_out, 0, 16, st), "memset counts");
   DDN_REQUIRE(xyz && rgb && out_keys && out_xyz && out_rgb && out_count && workspace, "null pointer");
   if (!use_dense(g))
     return sort_fuse_points(g, n_points, xyz, rgb, votes, vote_threshold, out_keys, out_xyz, out_rgb, out_count, counts_out,
                             workspace, workspace_bytes, st, nullptr);
-  DenseSource src;
-  src.xyz = xyz, src.rgb = rgb, src.votes = votes, src.thr = vote_threshold, src.row_len = row_len;
-  return dense_fuse(g, n_points, src, out_keys, out_xyz, out_rgb, out_count, nullptr, counts_out, workspace, workspace_bytes, st);
+  ddn_fuse_session s;
+  unsigned long long* accum;
+  DenseLayout L;
+  DDN_TRY(carve_session(g, n_points, workspace, workspace_bytes, &s, counts_out, &accum, &L));
+  DDN_TRY(begin_with_grid(&s, g, st));
+  DDN_TRY(launch_mark_points(&s, n_points, xyz, votes, vote_threshold, st));
+  const long long cap = (long long)std::min<uint64_t>((uint64_t)n_points, L.cells);
+  DDN_TRY(launch_rank(&s, ScanRange{0, -1}, out_keys, 1, accum, kAccWords, cap, nullptr, st));
+  DDN_TRY(launch_accumulate_points(&s, n_points, row_len, xyz, rgb, votes, vote_threshold, accum, kAccWords, cap, st));
+  return launch_finalize(&s, accum, out_keys, cap, out_xyz, out_rgb, out_count, st);
 }
 
 int ddn_fuse_tile_info(const ddn_voxel_grid* grid_host, int64_t* n_tiles, int64_t* cells_per_tile) {
@@ -660,6 +981,7 @@ int ddn_voxel_partials(const ddn_voxel_grid* grid_host, int64_t n_points, int64_
   DDN_REQUIRE(row_len >= 0, "row_len");
   DDN_REQUIRE(counts_out != nullptr, "null counts_out");
   cudaStream_t st = (cudaStream_t)stream;
+  vote_threshold = std::min(vote_threshold, 255);
   if (n_points == 0) {
     if (tile_prefix != nullptr && use_dense(g)) {
       DenseLayout L;
@@ -669,13 +991,20 @@ int ddn_voxel_partials(const ddn_voxel_grid* grid_host, int64_t n_points, int64_
     return check_cuda(cudaMemsetAsync(counts_out, 0, 16, st), "memset counts");
   }
   DDN_REQUIRE(xyz && rgb && records && workspace, "null pointer");
+  DDN_REQUIRE((uintptr_t)records % 16 == 0, "records must be 16-byte aligned");
   if (!use_dense(g))
     return sort_fuse_points(g, n_points, xyz, rgb, votes, vote_threshold, nullptr, nullptr, nullptr, nullptr, counts_out, workspace,
                             workspace_bytes, st, (unsigned long long*)records);
-  DenseSource src;
-  src.xyz = xyz, src.rgb = rgb, src.votes = votes, src.thr = vote_threshold, src.row_len = row_len;
-  return dense_fuse(g, n_points, src, nullptr, nullptr, nullptr, nullptr, (unsigned long long*)records, counts_out, workspace,
-                    workspace_bytes, st, 0, 0, tile_prefix);
+  ddn_fuse_session s;
+  unsigned long long* accum;
+  DenseLayout L;
+  DDN_TRY(carve_session(g, n_points, workspace, workspace_bytes, &s, counts_out, &accum, &L));
+  DDN_TRY(begin_with_grid(&s, g, st));
+  DDN_TRY(launch_mark_points(&s, n_points, xyz, votes, vote_threshold, st));
+  unsigned long long* rec = (unsigned long long*)records;
+  const long long cap = (long long)n_points;
+  DDN_TRY(launch_rank(&s, ScanRange{0, -1}, (uint64_t*)rec, kRecWords, rec, kRecWords, cap, tile_prefix, st));
+  return launch_accumulate_points(&s, n_points, row_len, xyz, rgb, votes, vote_threshold, rec + 1, kRecWords, cap, st);
 }
 
 int ddn_voxel_merge(const ddn_voxel_grid* grid_host, int64_t n_records, const uint64_t* records, int64_t tile_begin,
@@ -692,10 +1021,37 @@ int ddn_voxel_merge(const ddn_voxel_grid* grid_host, int64_t n_records, const ui
   if (!use_dense(g))
     return sort_merge_records(g, n_records, (const unsigned long long*)records, out_keys, out_xyz, out_rgb, out_count, counts_out,
                               workspace, workspace_bytes, st);
-  DenseSource src;
-  src.records = (const unsigned long long*)records;
-  return dense_fuse(g, n_records, src, out_keys, out_xyz, out_rgb, out_count, nullptr, counts_out, workspace, workspace_bytes, st,
-                    tile_begin, tile_end);
+  ddn_fuse_session s;
+  unsigned long long* accum;
+  DenseLayout L;
+  DDN_TRY(carve_session(g, n_records, workspace, workspace_bytes, &s, counts_out, &accum, &L));
+  // ownership tiles -> owned cell range and the scan tiles that enclose it
+  if (tile_end <= 0) tile_begin = 0, tile_end = (int64_t)L.own_tiles;
+  DDN_REQUIRE(tile_begin >= 0 && tile_begin <= tile_end && tile_end <= (int64_t)L.own_tiles, "tile range");
+  const uint64_t cell_begin = (uint64_t)tile_begin * kOwnUnits * kUnitBits;
+  const uint64_t cell_end = (uint64_t)tile_end * kOwnUnits * kUnitBits;
+  ScanRange range;
+  range.tile_begin = tile_begin / kOwnPerScanTile;
+  range.n_tiles = tile_end > tile_begin ? (tile_end + kOwnPerScanTile - 1) / kOwnPerScanTile - range.tile_begin : 0;
+  grid_store_kernel<<<1, 32, 0, st>>>(g, (long long)s.cap_units, reinterpret_cast<GridDev*>(s.grid),
+                                      reinterpret_cast<unsigned long long*>(s.counts));
+  DDN_TRY(after_launch("grid_store_kernel"));
+  if (range.n_tiles == 0) return DDN_OK;
+  {
+    const size_t ub = (size_t)range.tile_begin * kTileUnits;
+    const size_t ue = std::min((size_t)(range.tile_begin + range.n_tiles) * kTileUnits, (size_t)L.n_units);
+    DDN_TRY(check_cuda(cudaMemsetAsync(reinterpret_cast<uint4*>(s.units) + ub, 0, (ue - ub) * 16, st), "memset occupancy"));
+  }
+  const unsigned blocks = (unsigned)((n_records + 255) / 256);
+  mark_records_kernel<<<blocks, 256, 0, st>>>(fuse_dev(&s), n_records, records, cell_begin, cell_end);
+  DDN_TRY(after_launch("mark_records_kernel"));
+  const long long cap = (long long)std::min<uint64_t>((uint64_t)n_records, L.cells);
+  DDN_TRY(launch_rank(&s, range, out_keys, 1, accum, kAccWords, cap, nullptr, st));
+  accumulate_records_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const GridDev*>(s.grid), n_records,
+                                                    (const unsigned long long*)records, reinterpret_cast<const uint4*>(s.units),
+                                                    cell_begin, cell_end, accum, cap);
+  DDN_TRY(after_launch("accumulate_records_kernel"));
+  return launch_finalize(&s, accum, out_keys, cap, out_xyz, out_rgb, out_count, st);
 }
 
 int ddn_voxel_keys(const ddn_voxel_grid* grid_host, int64_t n_points, const float* xyz, uint64_t* keys, void* stream) {
@@ -713,6 +1069,146 @@ int ddn_voxel_keys(const ddn_voxel_grid* grid_host, int64_t n_points, const floa
   g.nx = g.ny = g.nz = 1 << 21;
   canonical_key_kernel<<<(unsigned)((n_points + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g, n_points, xyz, keys);
   return after_launch("canonical_key_kernel");
+}
+
+// ---- fusion session ------------------------------------------------------------------------------
+int ddn_fuse_session_sizes(int64_t max_cells, int64_t* cap_units, int64_t* units_bytes, int64_t* dirty_bytes,
+                           int64_t* tile_sums_bytes, int64_t* tile_prefix_bytes) {
+  using namespace ddn;
+  DDN_REQUIRE(max_cells > 0 && (uint64_t)max_cells <= kDenseMaxCells, "max_cells must be in (0, 2^35]");
+  DDN_REQUIRE(cap_units && units_bytes && dirty_bytes && tile_sums_bytes && tile_prefix_bytes, "null output");
+  const int64_t cu = align_up((max_cells + kUnitBits - 1) / kUnitBits, kTileUnits);
+  *cap_units = cu;
+  *units_bytes = cu * 16;
+  *dirty_bytes = align_up(cu / kTileUnits + 1, 256);
+  *tile_sums_bytes = align_up((cu / kOwnUnits + 2) * 4, 256);
+  *tile_prefix_bytes = align_up((cu / kOwnUnits + 2) * 4, 256);
+  return DDN_OK;
+}
+
+int ddn_fuse_session_reset(const ddn_fuse_session* s, void* stream) {
+  using namespace ddn;
+  DDN_TRY(session_check(s));
+  cudaStream_t st = (cudaStream_t)stream;
+  DDN_TRY(check_cuda(cudaMemsetAsync(s->units, 0, (size_t)s->cap_units * 16, st), "memset units"));
+  if (s->dirty != nullptr) DDN_TRY(check_cuda(cudaMemsetAsync(s->dirty, 0, (size_t)(s->cap_units / kTileUnits + 1), st), "memset flags"));
+  DDN_TRY(check_cuda(cudaMemsetAsync(s->grid, 0, sizeof(ddn_grid_state), st), "memset grid"));
+  return check_cuda(cudaMemsetAsync(s->counts, 0, 16, st), "memset counts");
+}
+
+int ddn_fuse_begin(const ddn_fuse_session* s, const void* const* bbox_ptrs_host, int32_t n_boxes, float voxel, void* stream) {
+  using namespace ddn;
+  DDN_TRY(session_check(s));
+  DDN_REQUIRE(bbox_ptrs_host != nullptr && n_boxes >= 1 && n_boxes <= DDN_MAX_PEERS, "bounding boxes");
+  DDN_REQUIRE(voxel > 0.f, "voxel size");
+  cudaStream_t st = (cudaStream_t)stream;
+  BoxPtrs boxes;
+  boxes.n = n_boxes;
+  for (int i = 0; i < DDN_MAX_PEERS; ++i) boxes.p[i] = i < n_boxes ? reinterpret_cast<const int*>(bbox_ptrs_host[i]) : nullptr;
+  for (int i = 0; i < n_boxes; ++i) DDN_REQUIRE(boxes.p[i] != nullptr, "null bounding box");
+  grid_from_bbox_kernel<<<1, 32, 0, st>>>(boxes, voxel, (long long)s->cap_units, reinterpret_cast<GridDev*>(s->grid),
+                                          reinterpret_cast<unsigned long long*>(s->counts));
+  DDN_TRY(after_launch("grid_from_bbox_kernel"));
+  return launch_clear(s, st);
+}
+
+int ddn_fuse_begin_grid(const ddn_fuse_session* s, const ddn_voxel_grid* grid_host, void* stream) {
+  using namespace ddn;
+  DDN_TRY(session_check(s));
+  GridDev g;
+  DDN_TRY(grid_from_host(grid_host, &g));
+  DDN_REQUIRE(use_dense(g), "grid too large for a fusion session (more than 2^35 cells)");
+  return begin_with_grid(s, g, (cudaStream_t)stream);
+}
+
+int ddn_fuse_mark_points(const ddn_fuse_session* s, int64_t n_points, const float* xyz, const uint8_t* votes,
+                         int32_t vote_threshold, void* stream) {
+  using namespace ddn;
+  DDN_TRY(session_check(s));
+  DDN_REQUIRE(n_points >= 0 && n_points < (1ll << 31) - 1024, "n_points");
+  if (n_points == 0) return DDN_OK;
+  DDN_REQUIRE(xyz != nullptr, "null pointer");
+  return launch_mark_points(s, n_points, xyz, votes, std::min(vote_threshold, 255), (cudaStream_t)stream);
+}
+
+int ddn_fuse_finish(const ddn_fuse_session* s, int64_t n_points, int64_t row_len, const float* xyz, const uint8_t* rgb,
+                    const uint8_t* votes, int32_t vote_threshold, uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb,
+                    int32_t* out_count, int64_t cap_out, void* accum, int64_t accum_bytes, void* stream) {
+  using namespace ddn;
+  DDN_TRY(session_check(s));
+  DDN_REQUIRE(n_points >= 0 && n_points < (1ll << 31) - 1024, "n_points");
+  DDN_REQUIRE(row_len >= 0, "row_len");
+  DDN_REQUIRE(cap_out > 0 && cap_out < (1ll << 31), "cap_out");
+  DDN_REQUIRE(out_keys && out_xyz && out_rgb && out_count && accum, "null pointer");
+  DDN_REQUIRE(accum_bytes >= cap_out * kAccWords * 8 + 16 && (uintptr_t)accum % 16 == 0, "accumulator scratch");
+  DDN_REQUIRE(n_points == 0 || (xyz && rgb), "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  vote_threshold = std::min(vote_threshold, 255);
+  unsigned long long* acc = (unsigned long long*)accum;
+  DDN_TRY(launch_rank(s, ScanRange{0, -1}, out_keys, 1, acc, kAccWords, cap_out, nullptr, st));
+  if (n_points > 0)
+    DDN_TRY(launch_accumulate_points(s, n_points, row_len, xyz, rgb, votes, vote_threshold, acc, kAccWords, cap_out, st));
+  return launch_finalize(s, acc, out_keys, cap_out, out_xyz, out_rgb, out_count, st);
+}
+
+int ddn_fuse_finish_partial(const ddn_fuse_session* s, int64_t n_points, int64_t row_len, const float* xyz, const uint8_t* rgb,
+                            const uint8_t* votes, int32_t vote_threshold, uint64_t* records, int64_t cap_records, void* stream) {
+  using namespace ddn;
+  DDN_TRY(session_check(s));
+  DDN_REQUIRE(n_points >= 0 && n_points < (1ll << 31) - 1024, "n_points");
+  DDN_REQUIRE(row_len >= 0, "row_len");
+  DDN_REQUIRE(cap_records > 0 && cap_records < (1ll << 31), "cap_records");
+  DDN_REQUIRE(records != nullptr && (uintptr_t)records % 16 == 0, "records must be 16-byte aligned");
+  DDN_REQUIRE(n_points == 0 || (xyz && rgb), "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  vote_threshold = std::min(vote_threshold, 255);
+  unsigned long long* rec = (unsigned long long*)records;
+  DDN_TRY(launch_rank(s, ScanRange{0, -1}, (uint64_t*)rec, kRecWords, rec, kRecWords, cap_records, s->tile_prefix, st));
+  if (n_points == 0) return DDN_OK;
+  return launch_accumulate_points(s, n_points, row_len, xyz, rgb, votes, vote_threshold, rec + 1, kRecWords, cap_records, st);
+}
+
+int ddn_fuse_merge_peers(const ddn_fuse_session* s, int32_t rank, int32_t n_ranks, const void* const* peer_units_host,
+                         const void* const* peer_records_host, const void* const* peer_tile_prefix_host, int64_t* plan,
+                         uint32_t* prefix_scratch, uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb,
+                         int32_t* out_count, int64_t cap_out, void* accum, int64_t accum_bytes, void* stream) {
+  using namespace ddn;
+  DDN_TRY(session_check(s));
+  DDN_REQUIRE(n_ranks >= 1 && n_ranks <= DDN_MAX_PEERS && rank >= 0 && rank < n_ranks, "rank / n_ranks");
+  DDN_REQUIRE(peer_units_host && peer_records_host && peer_tile_prefix_host && plan && prefix_scratch, "null pointer");
+  DDN_REQUIRE(cap_out > 0 && cap_out < (1ll << 31), "cap_out");
+  DDN_REQUIRE(out_keys && out_xyz && out_rgb && out_count && accum, "null pointer");
+  DDN_REQUIRE(accum_bytes >= cap_out * kAccWords * 8 + 16 && (uintptr_t)accum % 16 == 0, "accumulator scratch");
+  PeerPtrs pu, pr, pp;
+  for (int q = 0; q < DDN_MAX_PEERS; ++q) {
+    pu.p[q] = q < n_ranks ? peer_units_host[q] : nullptr;
+    pr.p[q] = q < n_ranks ? peer_records_host[q] : nullptr;
+    pp.p[q] = q < n_ranks ? peer_tile_prefix_host[q] : nullptr;
+    if (q < n_ranks) DDN_REQUIRE(pu.p[q] && pr.p[q] && pp.p[q], "null peer pointer");
+  }
+  DDN_REQUIRE(pu.p[rank] == s->units && pp.p[rank] == (const void*)s->tile_prefix, "entry `rank` must be the session's own buffers");
+  cudaStream_t st = (cudaStream_t)stream;
+  const GridDev* gp = reinterpret_cast<const GridDev*>(s->grid);
+  const FuseDev f = fuse_dev(s);
+  unsigned long long* counts = reinterpret_cast<unsigned long long*>(s->counts);
+  long long* planll = reinterpret_cast<long long*>(plan);
+  unsigned long long* acc = (unsigned long long*)accum;
+  const long long stride = (long long)(s->cap_units / kOwnUnits + 2);
+  merge_plan_kernel<<<1, 32 * DDN_MAX_PEERS, 0, st>>>(gp, pp, rank, n_ranks, planll);
+  DDN_TRY(after_launch("merge_plan_kernel"));
+  merge_copy_prefix_kernel<<<kNumSMs, 256, 0, st>>>(pp, n_ranks, planll, prefix_scratch, stride);
+  DDN_TRY(after_launch("merge_copy_prefix_kernel"));
+  merge_or_kernel<<<kPersistentCtas, kOwnUnits, 0, st>>>(f, pu, rank, n_ranks, planll, prefix_scratch, stride, s->tile_sums);
+  DDN_TRY(after_launch("merge_or_kernel"));
+  tile_scan_kernel<<<1, 1024, 0, st>>>(gp, ScanRange{0, 0}, planll, s->tile_sums, counts);
+  DDN_TRY(after_launch("tile_scan_kernel"));
+  zero_accum_kernel<<<kPersistentCtas, 256, 0, st>>>((ulonglong2*)acc, counts, kAccWords, cap_out);
+  DDN_TRY(after_launch("zero_accum_kernel"));
+  merge_prefix_kernel<<<kPersistentCtas, kOwnUnits, 0, st>>>(f, planll, s->tile_sums, out_keys, cap_out);
+  DDN_TRY(after_launch("merge_prefix_kernel"));
+  merge_accumulate_kernel<<<kPersistentCtas, 256, 0, st>>>(f, pr, n_ranks, planll, acc, cap_out);
+  DDN_TRY(after_launch("merge_accumulate_kernel"));
+  return launch_finalize(s, acc, out_keys, cap_out, out_xyz, out_rgb, out_count, st);
 }
 
 }  // extern "C"

@@ -1,17 +1,25 @@
 // Shared definitions of stage 4 (voxel-grid fusion): grid description, IEEE-exact voxel coordinates,
-// fixed-point offsets and the finalisation of one voxel.  Used by the dense-rank path (fuse.cu) and by
-// the sort path kept for grids too large for a dense occupancy bitmap (fuse_sort.cu).
+// the occupancy-unit layout, fixed-point offsets and the finalisation of one voxel.  Used by the
+// dense-rank path (fuse.cu), by K4's fused occupancy marking (filter.cu) and by the sort path kept for
+// grids too large for a dense occupancy bitmap (fuse_sort.cu).
 #pragma once
 
 #include "common.cuh"
 
 namespace ddn {
 
+// Same layout as ddn_grid_state (include/ddn_b200.h): the grid lives in DEVICE memory, so a step needs no
+// host round trip between the bounding box and the fusion passes.  Host-grid entry points fill one on
+// the host and pass it by value to a one-thread kernel that stores it.
 struct GridDev {
   float voxel, ox, oy, oz;
-  int bx, by, bz;  // significant bits per axis (sort path key packing)
-  int nx, ny, nz;  // cells per axis; a point outside [0, n) on any axis does not participate
+  int bx, by, bz;     // significant bits per axis (sort path key packing)
+  int nx, ny, nz;     // cells per axis; a point outside [0, n) on any axis does not participate
+  long long n_units;  // ceil(cells / 96); 0 when status != DDN_GRID_OK
+  int status, reserved;
+  long long cells;
 };
+static_assert(sizeof(GridDev) == sizeof(ddn_grid_state), "GridDev mirrors ddn_grid_state");
 
 inline int grid_from_host(const ddn_voxel_grid* h, GridDev* g) {
   DDN_REQUIRE(h != nullptr, "null grid");
@@ -29,6 +37,10 @@ inline int grid_from_host(const ddn_voxel_grid* h, GridDev* g) {
   g->nx = h->dims[0] > 0 ? h->dims[0] : (1 << h->bits[0]);
   g->ny = h->dims[1] > 0 ? h->dims[1] : (1 << h->bits[1]);
   g->nz = h->dims[2] > 0 ? h->dims[2] : (1 << h->bits[2]);
+  g->cells = (long long)g->nx * (long long)g->ny * (long long)g->nz;
+  g->n_units = (g->cells + 95) / 96;
+  g->status = DDN_GRID_OK;
+  g->reserved = 0;
   return DDN_OK;
 }
 
@@ -74,6 +86,52 @@ __device__ __forceinline__ void finalize_voxel(const GridDev& g, float cx, float
   orgb[1] = (uint8_t)((2 * sg + cnt) / c2);
   orgb[2] = (uint8_t)((2 * sb + cnt) / c2);
 }
+
+// ---- occupancy units (dense-rank path) --------------------------------------------------------------
+// Occupancy + rank live in ONE array of 16-byte units: words x, y, z = 96 occupancy bits, word w = the
+// exclusive rank prefix of the unit (written by the rank pass).  A slot lookup is a single LDG.128.
+constexpr int kUnitBits = 96;
+constexpr int kUnitsPerThread = 8;
+constexpr int kScanThreads = 256;
+constexpr int kTileUnits = kScanThreads * kUnitsPerThread;  // units per "scan tile" (32 KB of units)
+// Ownership granularity of the multi-GPU form: a "tile" of the C ABI is kOwnUnits consecutive units
+// (24,576 cells in key order), fine enough to cut a dense z-layer of the grid into balanced shares.
+constexpr int kOwnUnits = kScanThreads;
+constexpr int kOwnPerScanTile = kTileUnits / kOwnUnits;
+constexpr uint64_t kNoCell = ~0ull;
+
+__device__ __forceinline__ uint64_t cell_of_point(const GridDev& g, float rv, float x, float y, float z, uint32_t& kx,
+                                                  uint32_t& ky, uint32_t& kz) {
+  const float fx = voxel_coord(x, g.ox, g.voxel, rv);
+  const float fy = voxel_coord(y, g.oy, g.voxel, rv);
+  const float fz = voxel_coord(z, g.oz, g.voxel, rv);
+  const bool inside = fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)g.nx && fy < (float)g.ny && fz < (float)g.nz;
+  if (!inside) return kNoCell;
+  kx = (uint32_t)fx;
+  ky = (uint32_t)fy;
+  kz = (uint32_t)fz;
+  return (uint64_t)kx + (uint64_t)g.nx * ((uint64_t)ky + (uint64_t)g.ny * (uint64_t)kz);
+}
+
+// Sets the occupancy bit of `cell`.  `dirty` (optional): one byte per scan tile, set when a tile receives
+// its first bit - the rank passes and the clean-up then only touch the tiles a step has actually used.
+__device__ __forceinline__ void set_cell_bit(uint32_t* __restrict__ units, uint8_t* __restrict__ dirty, uint64_t cell) {
+  const uint32_t w32 = (uint32_t)(cell >> 5);  // word index in a plain bitmap
+  const uint32_t unit = w32 / 3u;
+  atomicOr(units + (size_t)unit * 4 + (w32 - unit * 3u), 1u << (cell & 31));
+  if (dirty != nullptr) {
+    uint8_t* d = dirty + unit / (uint32_t)kTileUnits;
+    if (*reinterpret_cast<volatile uint8_t*>(d) == 0) *reinterpret_cast<volatile uint8_t*>(d) = 1;
+  }
+}
+
+// The device buffers of one fusion session, as the kernels see them (host struct: ddn_fuse_session).
+struct FuseDev {
+  const GridDev* grid;
+  uint32_t* units;
+  uint8_t* dirty;                   // may be nullptr
+  unsigned long long* counts;       // [0] participating points, [1] voxels
+};
 
 // ---- sort path (fuse_sort.cu) -------------------------------------------------------------------
 // records != nullptr: partial mode, output = records [.,DDN_RECORD_WORDS] (see include/ddn_b200.h)

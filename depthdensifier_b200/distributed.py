@@ -8,9 +8,20 @@ depth of each source view's K neighbours, stage 4 is a global group-by on the vo
   neighbour table reference (with ring-ordered cameras that is <= K maps per shard boundary instead
   of the all-gather of all V maps), as one NCCL all-to-all-v;
 * voxel exchange: every rank fuses its own points into per-voxel PARTIAL SUMS (integer fixed point,
-  so the result does not depend on how points are split over ranks), the sorted partials are cut at
-  R-1 sampled splitter keys - each rank owns one disjoint key range, so the cut is R contiguous slices
-  and needs no pack kernel - and exchanged with an all-to-all-v; the owner merges its R sorted runs.
+  so the result does not depend on how points are split over ranks); the grid's tiles are cut into R
+  contiguous ranges that balance the global record count - each rank owns one disjoint key range, so a
+  destination's share of a rank's sorted records is one contiguous slice and needs no pack kernel - and
+  the owner adds up what the R ranks hold for its range.
+
+Two implementations of the same steps:
+
+* the DEVICE path (CUDA): no host round trip anywhere in a step.  The grid is derived on the device from
+  the bounding boxes the alignment kernels produce (all ranks' boxes are read through NVLink peer
+  memory), the consistency kernel marks the occupancy of the points it keeps, and the owner-side merge
+  reads the peers' occupancy units and partial records straight out of their HBM inside its kernels
+  (ddn_fuse_merge_peers) - no staging copy, no host-side plan;
+* the COLLECTIVE path (all-to-all-v over torch.distributed; host-side grid and plan): what the gloo tests
+  drive on CPU with a stand-in backend, and the fallback when symmetric memory cannot be set up.
 
 With world == 1 both exchanges vanish and this is the single-GPU pipeline.
 """
@@ -23,7 +34,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .engine import DensifyConfig, DensifyResult
+from .engine import DensifyConfig, DensifyResult, clamp_vote_threshold
 from .neighbours import default_vote_threshold
 
 
@@ -139,7 +150,7 @@ class ShardedDensifier:
         self.rank, self.world, self.group = rank, world, group
         self.V, self.lo, self.hi, self.H, self.W = n_views_total, lo, hi, height, width
         self.K = nbr.shape[1]
-        self.thr = cfg.vote_threshold if cfg.vote_threshold is not None else default_vote_threshold(self.K)
+        self.thr = clamp_vote_threshold(cfg.vote_threshold if cfg.vote_threshold is not None else default_vote_threshold(self.K))
         bounds = shard_bounds(n_views_total, world) if world > 1 else [(lo, hi)]
         if world > 1 and bounds[rank] != (lo, hi):
             raise ValueError(f"rank {rank}: shard {(lo, hi)} does not match the contiguous layout {bounds[rank]}")
@@ -160,7 +171,13 @@ class ShardedDensifier:
         # remains for the gloo tests and as the fallback when symmetric memory cannot be set up
         self.peer = None
         self.bounds = bounds
-        if world > 1 and self.device.type == "cuda" and backend is ops:
+        self.device_path = self.device.type == "cuda" and backend is ops  # sync-free fusion sessions
+        self.session = None
+        self._tables = None
+        s0 = cfg.filter.stride
+        self.Hs, self.Ws = (height + s0 - 1) // s0, (width + s0 - 1) // s0
+        self._local_max = max(b - a for a, b in bounds)
+        if world > 1 and self.device_path:
             try:
                 self.peer = PeerMemory(group, self.device)
                 plans = [make_halo_plan(nbr, bounds, q) for q in range(world)]
@@ -177,11 +194,44 @@ class ShardedDensifier:
                 s_ = cfg.filter.stride
                 self.peer_records_shape = (self._local_max * ((height + s_ - 1) // s_) * ((width + s_ - 1) // s_), 6)
                 self.peer.buffer("refined", (self._slots_max, self.H, self.W), torch.float32)
+                self.peer.buffer("bbox", (64,), torch.int32)
                 if cfg.voxel is not None:
                     self.peer.buffer("records", self.peer_records_shape, torch.int64)
+                    self._make_session()
             except Exception as e:  # pragma: no cover - depends on the platform
                 print(f"[depthdensifier_b200] symmetric memory unavailable ({e!r}); using NCCL collectives")
                 self.peer = None
+                self.session = None
+            if self.peer is None:
+                self.device_path = False
+        elif self.device_path and cfg.voxel is not None:
+            self._make_session()
+
+    def _make_session(self) -> None:
+        """Fusion session of this rank; with peers its occupancy units and tile prefix live in symmetric memory so
+        the owner-side merge of every other rank can read them over NVLink."""
+        cfg = self.cfg
+        if self.peer is None:
+            self.session = ops.FuseSession(self.device, cfg.max_grid_cells)
+            return
+
+        def alloc(name, nbytes):
+            if name in ("units", "tile_prefix"):
+                return self.peer.buffer("fuse_" + name, (nbytes,), torch.uint8)[0]
+            return None
+
+        self.session = ops.FuseSession(self.device, cfg.max_grid_cells, tile_prefix=True, alloc=alloc)
+        ptrs = lambda name, shape, dt: [int(v.data_ptr()) for v in self.peer.buffer(name, shape, dt)[2]]
+        self._peer_units = ptrs("fuse_units", (self.session.units.numel(),), torch.uint8)
+        self._peer_prefix = ptrs("fuse_tile_prefix", (self.session.tile_prefix.numel(),), torch.uint8)
+        self._peer_records = ptrs("records", tuple(self.peer_records_shape), torch.int64)
+        self._peer_bbox = ptrs("bbox", (64,), torch.int32)
+        self._plan = torch.zeros(64, dtype=torch.int64, device=self.device)
+        self._prefix_scratch = torch.empty(self.session.n_own_cap * self.world, dtype=torch.int32, device=self.device)
+        # a rank's share of the merged voxels: the cuts balance the global record count, up to one tile per rank
+        n_max = self._local_max * self.Hs * self.Ws
+        self._cap_merge = n_max + 24576 * self.world + 1024
+        self._merge_out = ops.new_voxel_outputs(self._cap_merge, self.device)
 
     # -- exchange steps -------------------------------------------------------------------------------
     def _exchange_halo(self, refined_slots: torch.Tensor) -> None:
@@ -244,6 +294,8 @@ class ShardedDensifier:
 
     # -- pipeline ---------------------------------------------------------------------------------------
     def run(self, depth, normal, mask, rgb, sparse_xyz, sparse_offsets, record_events: bool = False, grid=None) -> ShardResult:
+        """One step on device-resident inputs of the rank's own views.  On the device path nothing in here waits
+        for the GPU: validate with ``ShardResult.check()`` (or read ``counts``) when the results are needed."""
         cfg = self.cfg
         ev = {}
 
@@ -260,23 +312,32 @@ class ShardedDensifier:
         if self._max_sparse is None:
             off = sparse_offsets.cpu().numpy()
             self._max_sparse = max(int(np.max(np.diff(off))) if len(off) > 1 else 1, 1)
+        fuse = cfg.voxel is not None
         refined_slots = self._new_refined_slots()
+        pair, src = mark("pair_tables", self._pair_tables)
+        box = self._new_box() if (self.device_path and fuse and grid is None) else None
         _, stats = mark("align", lambda: self.ops.align_views(
             depth, mask, self.poses_slots[: self.n_local].contiguous(), self.kmat, sparse_xyz, sparse_offsets,
-            self._max_sparse, cfg.align, out=refined_slots[: self.n_local]))
-        xyz, votes, bbox = self._halo_and_filter(refined_slots, normal, mark)
+            self._max_sparse, cfg.align, out=refined_slots[: self.n_local], **self._box_args(src, box)))
+        xyz, votes, bbox = self._halo_and_filter(refined_slots, normal, mark, pair, src, box=box, grid=grid)
         res = ShardResult(refined=refined_slots[: self.n_local], stats=stats, xyz=xyz, votes=votes, vote_threshold=self.thr,
                           bbox=bbox, events=ev)
-        if cfg.voxel is None:
+        if not fuse:
             return res
+        s = cfg.filter.stride
+        rgb_s = rgb if s == 1 else rgb[:, ::s, ::s].contiguous()
+        if self.device_path:
+            k, x, c, n, counts = mark("voxel_fuse", lambda: self._fuse_device(xyz, rgb_s, votes, mark))
+            res.session, res.grid = self.session, grid
+            res.voxel_keys, res.voxel_xyz, res.voxel_rgb, res.voxel_count, res.counts = k, x, c, n, counts
+            return res
+        # collective path: the grid is made on the host from the (all-reduced) box of the kept points
         if grid is None:
             bb = mark("bbox_sync", lambda: self._global_bbox(bbox))
             if not np.all(np.isfinite(bb)):
                 res.counts = torch.zeros(2, dtype=torch.int64, device=self.device)
                 return res
             grid = self.ops.make_grid(bb[:3], bb[3:], cfg.voxel)
-        s = cfg.filter.stride
-        rgb_s = rgb if s == 1 else rgb[:, ::s, ::s].contiguous()
         if self.world == 1:
             k, x, c, n, counts = mark("voxel_fuse", lambda: self.ops.voxel_fuse(
                 xyz.view(-1, 3), rgb_s.view(-1, 3), votes.view(-1), self.thr, grid, trim=False, row_len=xyz.shape[2]))
@@ -285,31 +346,66 @@ class ShardedDensifier:
         res.grid, res.voxel_keys, res.voxel_xyz, res.voxel_rgb, res.voxel_count, res.counts = grid, k, x, c, n, counts
         return res
 
+    def _pair_tables(self):
+        if self.device_path:
+            return self.ops.build_pair_tables(self.poses_slots, self.intr_slots, self._nbr_full(), 0, self.n_local, self.H, self.W)
+        return self.ops.build_pair_tables(self.poses_slots, self.intr_slots, self._nbr_full(), 0, self.n_local, height=self.H,
+                                          width=self.W)
+
+    def _new_box(self) -> torch.Tensor:
+        """Bounding box of this rank's back-projected pixels (filled by the alignment kernel); in peer-visible
+        memory when there are peers, whose boxes the grid kernel reads directly."""
+        if self.peer is not None:
+            buf = self.peer.buffer("bbox", (64,), torch.int32)[0]
+            return ops.init_bbox(buf[:6])
+        return self.ops.new_bbox(self.device)
+
+    @staticmethod
+    def _box_args(src, box, c0=None, c1=None):
+        if box is None:
+            return {}
+        return {"src_table": src if c0 is None else src[c0:c1], "bbox": box}
+
+    def _begin_session(self, box, grid) -> None:
+        """Opens the fusion step (stream-ordered after the barrier that made every rank's box visible)."""
+        if grid is not None:
+            self.session.begin_grid(grid)
+        elif self.peer is not None:
+            self.session.begin(self._peer_bbox, self.cfg.voxel)
+        else:
+            self.session.begin([box], self.cfg.voxel)
+
     def _new_refined_slots(self) -> torch.Tensor:
         """[n_slots,H,W] buffer for own + halo refined maps; NVLink-visible when peer memory is in use."""
         if self.peer is not None:
             buf, hdl, _ = self.peer.buffer("refined", (self._slots_max, self.H, self.W), torch.float32)
-            hdl.barrier()  # peers finished reading last step's maps before they are overwritten
+            # start of a step: every peer has finished the previous one, i.e. is done reading this rank's maps,
+            # bounding box, occupancy units and partial records, all of which are about to be overwritten
+            hdl.barrier()
             return buf[: self.n_slots]
         return torch.empty((self.n_slots, self.H, self.W), dtype=torch.float32, device=self.device)
 
-    def _halo_and_filter(self, refined_slots, normal, mark, wait_normal=None):
+    def _halo_and_filter(self, refined_slots, normal, mark, pair, src, wait_normal=None, box=None, grid=None):
         """Halo exchange + stages 2-3.  With peer memory the halo maps are pulled on a side stream while K4
-        already runs on the source views whose neighbours are all local."""
+        already runs on the source views whose neighbours are all local.  On the device path the fusion step is
+        opened in between (the grid needs every rank's box: same barrier as the halo) and K4 marks the occupancy
+        of the points it keeps."""
         cfg = self.cfg
         join_halo = None
         if self.peer is not None:
             join_halo = mark("halo_exchange", lambda: self._pull_halo_async(refined_slots))
         else:
             mark("halo_exchange", lambda: self._exchange_halo(refined_slots))
-        pair, src = mark("pair_tables", lambda: self.ops.build_pair_tables(self.poses_slots, self.intr_slots, self._nbr_full(), 0, self.n_local))
-        bbox = self.ops.new_bbox(self.device)
-        s_ = cfg.filter.stride
-        Hs, Ws = (self.H + s_ - 1) // s_, (self.W + s_ - 1) // s_
-        xyz = torch.empty((self.n_local, Hs, Ws, 3), dtype=torch.float32, device=self.device)
-        votes = torch.empty((self.n_local, Hs, Ws), dtype=torch.uint8, device=self.device)
+        sess = None
+        if self.device_path and cfg.voxel is not None:
+            mark("fuse_begin", lambda: self._begin_session(box, grid))
+            sess = self.session
+        bbox = self.ops.new_bbox(self.device) if not self.device_path or sess is None else None
+        xyz = torch.empty((self.n_local, self.Hs, self.Ws, 3), dtype=torch.float32, device=self.device)
+        votes = torch.empty((self.n_local, self.Hs, self.Ws), dtype=torch.uint8, device=self.device)
         if wait_normal is not None:
             wait_normal()
+        extra = {"mark": sess} if self.device_path else {}
 
         def k4(c0, c1):
             if c1 <= c0:
@@ -317,7 +413,7 @@ class ShardedDensifier:
             whole = c0 == 0 and c1 == self.n_local
             self.ops.backproject_filter(refined_slots, normal if whole else normal[c0:c1], self.nbr_slots,
                                         pair if whole else pair[c0:c1], src if whole else src[c0:c1], c0, self.thr, cfg.filter,
-                                        bbox=bbox, xyz_out=xyz[c0:c1], votes_out=votes[c0:c1])
+                                        bbox=bbox, xyz_out=xyz[c0:c1], votes_out=votes[c0:c1], **extra)
 
         if join_halo is not None:
             i0, i1 = self._interior_range()
@@ -327,6 +423,25 @@ class ShardedDensifier:
         else:
             mark("backproject_filter", lambda: k4(0, self.n_local))
         return xyz, votes, bbox
+
+    def _fuse_device(self, xyz, rgb, votes, mark=None):
+        """Stage 4 on the device path.  One rank: rank + accumulate + finalise.  R ranks: partial records into
+        peer-visible memory, one barrier, then the owner-side merge that reads the peers' units and records over
+        NVLink.  Returns persistent output buffers (valid until the next step) and a snapshot of the counts."""
+        if mark is None:
+            mark = lambda name, fn: fn()
+        sess = self.session
+        flat = (xyz.view(-1, 3), rgb.view(-1, 3), votes.view(-1))
+        if self.peer is None:
+            k, x, c, n, counts = self.ops.fuse_finish(sess, *flat, self.thr, row_len=xyz.shape[2])
+            return k, x, c, n, counts.clone()
+        rec, hdl, _ = self.peer.buffer("records", tuple(self.peer_records_shape), torch.int64)
+        mark("fuse_partials", lambda: self.ops.fuse_finish_partial(sess, *flat, self.thr, rec, row_len=xyz.shape[2]))
+        hdl.barrier()  # every rank's units, tile prefix and records are complete
+        k, x, c, n, counts = mark("fuse_merge", lambda: self.ops.fuse_merge_peers(
+            sess, self.rank, self.world, self._peer_units, self._peer_records, self._peer_prefix, self._plan,
+            self._prefix_scratch, self._cap_merge, out=self._merge_out))
+        return k, x, c, n, counts.clone()
 
     def _nbr_full(self) -> torch.Tensor:
         """Neighbour table padded to n_slots rows (build_pair_tables indexes it by global slot)."""
@@ -428,7 +543,8 @@ class ShardedDensifier:
 
         got = mark("fuse_alltoall", exchange)
         k, x, c, n, mcounts = mark("fuse_merge", lambda: self.ops.voxel_merge_partials(got, grid, tile_range=tile_range))
-        counts2 = torch.stack([counts[0], mcounts[1]])  # (points fused locally, voxels owned)
+        # (points fused locally, voxels owned); the owner's colour-sum overflow flag (-1) is kept
+        counts2 = torch.stack([torch.where(mcounts[0] < 0, mcounts[0], counts[0]), mcounts[1]])
         return k, x, c, n, counts2
 
     # -- end-to-end with host buffers -----------------------------------------------------------------
@@ -495,6 +611,9 @@ class ShardedDensifier:
             upload(st["sparse_offsets"], sparse_offsets)
         refined_slots = self._new_refined_slots()
         poses_local = self.poses_slots[:n]
+        fuse = cfg.voxel is not None
+        pair, src = self._pair_tables()
+        box = self._new_box() if (self.device_path and fuse) else None
         stats = []
         for c0 in range(0, n, max(int(chunk_views), 1)):
             c1 = min(c0 + max(int(chunk_views), 1), n)
@@ -506,7 +625,7 @@ class ShardedDensifier:
             comp.wait_event(ev)
             _, s_c = self.ops.align_views(st["depth"][c0:c1], st["mask"][c0:c1], poses_local[c0:c1].contiguous(),
                                           self.kmat[c0:c1].contiguous(), st["sparse_xyz"], st["sparse_offsets"][c0:c1 + 1].contiguous(),
-                                          self._max_sparse, cfg.align, out=refined_slots[c0:c1])
+                                          self._max_sparse, cfg.align, out=refined_slots[c0:c1], **self._box_args(src, box, c0, c1))
             stats.append(s_c)
         with torch.cuda.stream(copy):
             if normals_in_place and normal.is_pinned():
@@ -521,25 +640,39 @@ class ShardedDensifier:
             upload(st["rgb"], rgb)
             ev_rgb = torch.cuda.Event()
             ev_rgb.record(copy)
-        xyz, votes, bbox = self._halo_and_filter(refined_slots, normal_arg, lambda name, fn: fn(), wait_normal=lambda: comp.wait_event(ev_n))
+        xyz, votes, bbox = self._halo_and_filter(refined_slots, normal_arg, lambda name, fn: fn(), pair, src,
+                                                 wait_normal=lambda: comp.wait_event(ev_n), box=box)
         out = {"h2d_bytes": h2d, "d2h_bytes": 0, "num_points": 0, "stats": torch.cat(stats) if stats else None}
-        if cfg.voxel is None:
+        if not fuse:
             torch.cuda.synchronize(self.device)
             return out
-        bb = self._global_bbox(bbox)
-        out["d2h_bytes"] += 24
-        if not np.all(np.isfinite(bb)):
-            return out
-        grid = self.ops.make_grid(bb[:3], bb[3:], cfg.voxel)
-        comp.wait_event(ev_rgb)
         s = cfg.filter.stride
-        rgb_s = st["rgb"] if s == 1 else st["rgb"][:, ::s, ::s].contiguous()
-        if self.world == 1:
-            k, x, c, m, counts = self.ops.voxel_fuse(xyz.view(-1, 3), rgb_s.view(-1, 3), votes.view(-1), self.thr, grid,
-                                                     trim=False, row_len=xyz.shape[2])
+        grid = None
+        if self.device_path:
+            comp.wait_event(ev_rgb)
+            rgb_s = st["rgb"] if s == 1 else st["rgb"][:, ::s, ::s].contiguous()
+            k, x, c, m, counts = self._fuse_device(xyz, rgb_s, votes)
+            st_grid = self.session.grid_state()  # the one wait of the call: the host needs the voxel count to copy back
+            if st_grid.status == 1:
+                return out
+            grid = self.session.host_grid()
         else:
-            k, x, c, m, counts = self._fuse_sharded(xyz, rgb_s, votes, grid)
+            bb = self._global_bbox(bbox)
+            out["d2h_bytes"] += 24
+            if not np.all(np.isfinite(bb)):
+                return out
+            grid = self.ops.make_grid(bb[:3], bb[3:], cfg.voxel)
+            comp.wait_event(ev_rgb)
+            rgb_s = st["rgb"] if s == 1 else st["rgb"][:, ::s, ::s].contiguous()
+            if self.world == 1:
+                k, x, c, m, counts = self.ops.voxel_fuse(xyz.view(-1, 3), rgb_s.view(-1, 3), votes.view(-1), self.thr, grid,
+                                                         trim=False, row_len=xyz.shape[2])
+            else:
+                k, x, c, m, counts = self._fuse_sharded(xyz, rgb_s, votes, grid)
         mv = self.ops.checked_voxel_count(counts)
+        if mv > k.shape[0]:
+            raise ops.DDNError(f"voxel fusion: {mv} voxels exceed the output capacity {k.shape[0]}")
+        out["d2h_bytes"] += 64 + 16
         po = self._pinned_out(st, mv)
         for name, t in (("keys", k), ("xyz", x), ("rgb", c), ("count", m)):
             po[name][:mv].copy_(t[:mv], non_blocking=True)
@@ -547,6 +680,5 @@ class ShardedDensifier:
             out["d2h_bytes"] += out[name].numel() * out[name].element_size()
         torch.cuda.synchronize(self.device)
         out["num_points"] = int(counts[0].item())
-        out["d2h_bytes"] += 16
         out["grid"] = grid
         return out

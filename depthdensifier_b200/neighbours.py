@@ -50,18 +50,18 @@ def covisibility_table(observed_ids: list[np.ndarray], k: int, cam_from_world: n
     nbr = np.full((V, k), -1, dtype=np.int32)
     if V == 0:
         return nbr
-    all_ids = np.concatenate([np.unique(np.asarray(o, dtype=np.int64)) for o in observed_ids]) if V else np.zeros(0, np.int64)
-    owner = np.concatenate([np.full(len(np.unique(np.asarray(o, dtype=np.int64))), v, dtype=np.int64) for v, o in enumerate(observed_ids)])
+    # incidence matrix A [V, points] (1 where the view observes the point); shared = A A^T counts, for every pair
+    # of views, the tracks that contain both - one sparse product instead of a Python loop over the tracks
+    import scipy.sparse as sp
+
+    uniq = [np.unique(np.asarray(o, dtype=np.int64)) for o in observed_ids]
+    all_ids = np.concatenate(uniq)
     shared = np.zeros((V, V), dtype=np.int64)
     if len(all_ids):
-        order = np.argsort(all_ids, kind="stable")
-        ids_s, own_s = all_ids[order], owner[order]
-        starts = np.flatnonzero(np.r_[True, ids_s[1:] != ids_s[:-1]])
-        ends = np.r_[starts[1:], len(ids_s)]
-        for a, b in zip(starts, ends):  # one track = the views observing one 3D point
-            if b - a > 1:
-                views = own_s[a:b]
-                shared[np.ix_(views, views)] += 1
+        owner = np.concatenate([np.full(len(u), v, dtype=np.int64) for v, u in enumerate(uniq)])
+        _, col = np.unique(all_ids, return_inverse=True)
+        A = sp.csr_matrix((np.ones(len(col), dtype=np.int64), (owner, col)), shape=(V, int(col.max()) + 1))
+        shared = np.asarray((A @ A.T).todense(), dtype=np.int64)
     dist = None
     if cam_from_world is not None:
         c = camera_centers(cam_from_world)

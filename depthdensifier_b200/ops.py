@@ -89,6 +89,7 @@ class FilterOptions:
     two_sided_tau: float = 0.0
     stride: int = 1
     normals_in_world: bool = False
+    pixel_layout: int = 0  # which 4 pixels a K4 thread owns: 0 = 32 apart, 1 = adjacent (same results)
 
     def to_c(self) -> _lib.FilterConfig:
         if self.sample_mode not in ("nearest", "bilinear"):
@@ -100,14 +101,19 @@ class FilterOptions:
             float(self.two_sided_tau),
             int(self.stride),
             int(bool(self.normals_in_world)),
+            int(self.pixel_layout),
         )
 
 
 def align_views(depth, mask, cam_from_world, kmat, sparse_xyz, sparse_offsets, max_sparse_per_view: int,
-                opts: AlignOptions, out=None):
-    """Stage 1 for V views.  Returns (refined [V,H,W] f32, stats [V,8] int32 raw ddn_view_stats)."""
+                opts: AlignOptions, out=None, src_table=None, bbox=None):
+    """Stage 1 for V views.  Returns (refined [V,H,W] f32, stats [V,8] int32 raw ddn_view_stats).
+    ``src_table`` [V,16] (from build_pair_tables) + ``bbox`` [6] (new_bbox): the kernel also extends the box to
+    enclose the back-projection of every refined pixel, so the voxel grid is known before stages 2+3."""
     lib = _lib.load()
-    dev = _require_cuda(depth, mask, cam_from_world, kmat, sparse_xyz, sparse_offsets, out)
+    dev = _require_cuda(depth, mask, cam_from_world, kmat, sparse_xyz, sparse_offsets, out, src_table, bbox)
+    assert (src_table is None) == (bbox is None)
+    assert src_table is None or (src_table.dtype == torch.float32 and tuple(src_table.shape) == (depth.shape[0], 16))
     V, H, W = depth.shape
     assert depth.dtype == torch.float32 and cam_from_world.dtype == torch.float64 and kmat.dtype == torch.float64
     assert sparse_xyz.dtype == torch.float64 and sparse_offsets.dtype == torch.int64
@@ -123,7 +129,8 @@ def align_views(depth, mask, cam_from_world, kmat, sparse_xyz, sparse_offsets, m
         _lib.check(
             lib.ddn_align_views(
                 C.byref(cfg), V, H, W, _p(depth), _p(mask), _p(cam_from_world), _p(kmat), _p(sparse_xyz),
-                _p(sparse_offsets), int(max_sparse_per_view), _p(refined), _p(stats), _p(ws), nbytes.value, _stream(),
+                _p(sparse_offsets), int(max_sparse_per_view), _p(refined), _p(stats), _p(ws), nbytes.value, _p(src_table),
+                _p(bbox), _stream(),
             )
         )
     return refined, stats
@@ -149,7 +156,9 @@ def decode_stats(stats: torch.Tensor) -> list[dict]:
     return out
 
 
-def build_pair_tables(cam_from_world, intr, nbr, src_begin: int, n_src: int):
+def build_pair_tables(cam_from_world, intr, nbr, src_begin: int, n_src: int, height: int, width: int):
+    """Per-(source view, neighbour) float32 tables from the float64 poses; ``height`` / ``width``: the size of the
+    depth maps the tables will be used with (K4's gather offsets are precomputed per entry)."""
     lib = _lib.load()
     dev = _require_cuda(cam_from_world, intr, nbr)
     V = cam_from_world.shape[0]
@@ -159,16 +168,21 @@ def build_pair_tables(cam_from_world, intr, nbr, src_begin: int, n_src: int):
     pair = torch.empty((n_src, K, _lib.PAIR_TABLE_FLOATS), dtype=torch.float32, device=dev)
     src = torch.empty((n_src, 16), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.ddn_build_pair_tables(V, src_begin, n_src, K, _p(cam_from_world), _p(intr), _p(nbr), _p(pair), _p(src), _stream()))
+        _lib.check(lib.ddn_build_pair_tables(V, src_begin, n_src, K, int(height), int(width), _p(cam_from_world), _p(intr), _p(nbr),
+                                             _p(pair), _p(src), _stream()))
     return pair, src
 
 
-def new_bbox(dev) -> torch.Tensor:
+def init_bbox(bbox: torch.Tensor) -> torch.Tensor:
+    """(+inf, -inf) in the order-preserving int encoding the kernels fold points into."""
     lib = _lib.load()
-    bbox = torch.empty(6, dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(bbox.device):
         _lib.check(lib.ddn_bbox_init(_p(bbox), _stream()))
     return bbox
+
+
+def new_bbox(dev) -> torch.Tensor:
+    return init_bbox(torch.empty(6, dtype=torch.int32, device=dev))
 
 
 def decode_bbox(bbox: torch.Tensor) -> np.ndarray:
@@ -179,10 +193,11 @@ def decode_bbox(bbox: torch.Tensor) -> np.ndarray:
 
 
 def backproject_filter(refined_all, normal, nbr, pair_table, src_table, src_begin: int, vote_threshold: int,
-                       opts: FilterOptions, bbox=None, xyz_out=None, votes_out=None):
+                       opts: FilterOptions, bbox=None, xyz_out=None, votes_out=None, mark=None):
     """Stages 2+3 for the source views src_begin..src_begin+n_src (n_src = normal.shape[0]).  ``normal`` may
     be a PINNED HOST tensor: the kernel then reads the normals of its vote candidates in place over PCIe
-    (unified addressing) and the 12 B/pixel normal map never moves to the device."""
+    (unified addressing) and the 12 B/pixel normal map never moves to the device.  ``mark``: an open
+    ``FuseSession``; the kernel then also sets the occupancy bits of the kept points (stage 4's mark pass)."""
     lib = _lib.load()
     normal_on_host = not normal.is_cuda
     if normal_on_host and not (normal.is_pinned() and normal.is_contiguous()):
@@ -203,7 +218,8 @@ def backproject_filter(refined_all, normal, nbr, pair_table, src_table, src_begi
         _lib.check(
             lib.ddn_backproject_filter(
                 C.byref(cfg), V, src_begin, n_src, H, W, K, _p(refined_all), _p(normal), _p(nbr), _p(pair_table),
-                _p(src_table), int(vote_threshold), _p(xyz), _p(votes), _p(bbox), _stream(),
+                _p(src_table), int(vote_threshold), _p(xyz), _p(votes), _p(bbox),
+                C.byref(mark.c) if mark is not None else None, _stream(),
             )
         )
     return xyz, votes
@@ -235,6 +251,141 @@ def checked_voxel_count(counts: torch.Tensor) -> int:
     if n_pts < 0:
         raise DDNError("voxel fusion: a voxel collected 2^24 or more points (32-bit colour sums); use a smaller voxel")
     return mv
+
+
+GRID_STATUS = {0: "ok", 1: "empty (no finite bounding box)", 2: "grid larger than the session's capacity",
+               3: "an axis needs more than 21 bits"}
+
+
+class FuseSession:
+    """Device buffers of one fusion session (include/ddn_b200.h: ddn_fuse_session): the grid lives on the device,
+    derived there from bounding boxes, so a step runs without the host looking at an intermediate result.
+    ``alloc(name, nbytes)`` may supply a buffer from elsewhere (NVLink-visible symmetric memory for ``units`` and
+    ``tile_prefix`` in the multi-GPU path); every buffer is otherwise a plain device tensor."""
+
+    def __init__(self, device, max_cells: int = 1 << 33, tile_prefix: bool = False, dirty: bool = True, alloc=None):
+        lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise DDNError("no CUDA device available: depthdensifier_b200 has no CPU fallback")
+        self.device = torch.device(device)
+        sizes = [C.c_int64(0) for _ in range(5)]
+        _lib.check(lib.ddn_fuse_session_sizes(int(max_cells), *[C.byref(x) for x in sizes]))
+        cap_units, units_b, dirty_b, sums_b, prefix_b = (x.value for x in sizes)
+        self.max_cells, self.cap_units = int(max_cells), cap_units
+        self.n_own_cap = cap_units // 256 + 2
+
+        def get(name, nbytes):
+            t = alloc(name, nbytes) if alloc is not None else None
+            if t is None:
+                t = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            assert t.is_cuda and t.is_contiguous() and t.numel() * t.element_size() >= nbytes and t.data_ptr() % 16 == 0
+            return t
+
+        self.units = get("units", units_b)
+        self.dirty = get("dirty", dirty_b) if dirty else None
+        self.tile_sums = get("tile_sums", sums_b)
+        self.tile_prefix = get("tile_prefix", prefix_b) if tile_prefix else None
+        self.grid = torch.zeros(16, dtype=torch.int32, device=self.device)
+        self.counts = torch.zeros(2, dtype=torch.int64, device=self.device)
+        self.c = _lib.FuseSession(self.grid.data_ptr(), self.units.data_ptr(), cap_units,
+                                  self.dirty.data_ptr() if self.dirty is not None else None, self.tile_sums.data_ptr(),
+                                  self.tile_prefix.data_ptr() if self.tile_prefix is not None else None, self.counts.data_ptr())
+        self._accum = None
+        with torch.cuda.device(self.device):
+            _lib.check(lib.ddn_fuse_session_reset(C.byref(self.c), _stream()))
+
+    def begin(self, boxes, voxel: float) -> None:
+        """Opens a step on the union of ``boxes``: device tensors [6] (new_bbox encoding) or raw device addresses
+        (peer memory)."""
+        lib = _lib.load()
+        ptrs = [b if isinstance(b, int) else b.data_ptr() for b in boxes]
+        arr = (C.c_void_p * len(ptrs))(*ptrs)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.ddn_fuse_begin(C.byref(self.c), arr, len(ptrs), float(np.float32(voxel)), _stream()))
+
+    def begin_grid(self, grid: _lib.VoxelGrid) -> None:
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.ddn_fuse_begin_grid(C.byref(self.c), C.byref(grid), _stream()))
+
+    def grid_state(self) -> _lib.GridState:
+        """Host copy of the device grid (synchronises)."""
+        raw = self.grid.cpu().numpy().tobytes()
+        return _lib.GridState.from_buffer_copy(raw)
+
+    def host_grid(self) -> _lib.VoxelGrid:
+        """The device grid as the host struct the host-grid entry points and the tests take (synchronises);
+        raises when the session could not build one."""
+        st = self.grid_state()
+        if st.status != _lib.GRID_OK:
+            raise DDNError(f"fusion grid: {GRID_STATUS.get(st.status, st.status)} (dims {list(st.dims)}, "
+                           f"capacity {self.max_cells} cells); raise max_grid_cells or use a larger voxel")
+        g = _lib.VoxelGrid()
+        g.voxel = st.voxel
+        for i in range(3):
+            g.origin[i], g.bits[i], g.dims[i] = st.origin[i], st.bits[i], st.dims[i]
+        return g
+
+    def accum(self, cap_out: int) -> torch.Tensor:
+        nbytes = cap_out * 40 + 16
+        if self._accum is None or self._accum.numel() < nbytes:
+            self._accum = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self._accum
+
+    def mark_points(self, xyz, votes, vote_threshold: int) -> None:
+        lib = _lib.load()
+        _require_cuda(xyz, votes)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.ddn_fuse_mark_points(C.byref(self.c), xyz.shape[0], _p(xyz), _p(votes), int(vote_threshold), _stream()))
+
+
+def new_voxel_outputs(cap_out: int, dev):
+    return (torch.empty(cap_out, dtype=torch.int64, device=dev), torch.empty((cap_out, 3), dtype=torch.float32, device=dev),
+            torch.empty((cap_out, 3), dtype=torch.uint8, device=dev), torch.empty(cap_out, dtype=torch.int32, device=dev))
+
+
+def fuse_finish(sess: FuseSession, xyz, rgb, votes, vote_threshold: int, row_len: int = 0, cap_out: int | None = None, out=None):
+    """Rank + accumulate + finalise of the points marked in ``sess``.  Returns keys, xyz, rgb, count (capacity
+    ``cap_out``, default = the number of points) and the session's device counts [2] = (points, voxels)."""
+    lib = _lib.load()
+    dev = _require_cuda(xyz, rgb, votes)
+    N = xyz.shape[0]
+    assert xyz.dtype == torch.float32 and rgb.dtype == torch.uint8 and tuple(rgb.shape) == (N, 3)
+    cap = max(int(cap_out if cap_out is not None else N), 1)
+    k, x, c, n = out if out is not None else new_voxel_outputs(cap, dev)
+    acc = sess.accum(cap)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ddn_fuse_finish(C.byref(sess.c), N, int(row_len), _p(xyz), _p(rgb), _p(votes), int(vote_threshold), _p(k), _p(x),
+                                       _p(c), _p(n), cap, _p(acc), acc.numel(), _stream()))
+    return k, x, c, n, sess.counts
+
+
+def fuse_finish_partial(sess: FuseSession, xyz, rgb, votes, vote_threshold: int, records, row_len: int = 0):
+    """Rank + accumulate into partial ``records`` [cap, 6] i64 (and the session's tile prefix)."""
+    lib = _lib.load()
+    dev = _require_cuda(xyz, rgb, votes, records)
+    N = xyz.shape[0]
+    assert records.dtype == torch.int64 and records.shape[1] == _lib.RECORD_WORDS
+    with torch.cuda.device(dev):
+        _lib.check(lib.ddn_fuse_finish_partial(C.byref(sess.c), N, int(row_len), _p(xyz), _p(rgb), _p(votes), int(vote_threshold),
+                                               _p(records), records.shape[0], _stream()))
+    return sess.counts
+
+
+def fuse_merge_peers(sess: FuseSession, rank: int, world: int, peer_units, peer_records, peer_tile_prefix, plan, prefix_scratch,
+                     cap_out: int, out=None):
+    """Owner-side exchange + merge over peer memory.  ``peer_*``: per rank, the device address of that rank's
+    units / records / tile prefix as mapped into this process.  Returns keys, xyz, rgb, count, counts."""
+    lib = _lib.load()
+    dev = sess.device
+    k, x, c, n = out if out is not None else new_voxel_outputs(cap_out, dev)
+    acc = sess.accum(cap_out)
+    arr = lambda ptrs: (C.c_void_p * world)(*[int(v) for v in ptrs])
+    with torch.cuda.device(dev):
+        _lib.check(lib.ddn_fuse_merge_peers(C.byref(sess.c), int(rank), int(world), arr(peer_units), arr(peer_records),
+                                            arr(peer_tile_prefix), _p(plan), _p(prefix_scratch), _p(k), _p(x), _p(c), _p(n), int(cap_out),
+                                            _p(acc), acc.numel(), _stream()))
+    return k, x, c, n, sess.counts
 
 
 def voxel_fuse(xyz, rgb, votes, vote_threshold: int, grid: _lib.VoxelGrid, trim: bool = True, row_len: int = 0):

@@ -41,7 +41,7 @@ from .neighbours import covisibility_table, nearest_views_table
 # ==============================================================================================
 @dataclass
 class PathsConfig:
-    """Configuration for input and output paths."""
+    """Where the sparse model and the images are read from and where the densified model goes."""
 
     recon_path: Path = Path("data/360_v2/bicycle/sparse/0")
     image_dir: Path = Path("data/360_v2/bicycle/images")
@@ -52,29 +52,29 @@ class PathsConfig:
 
 @dataclass
 class MoGeConfig:
-    """Configuration for the MoGe model."""
+    """Monocular depth network (only used when no precomputed depth is given)."""
 
     checkpoint: Path = Path("models/moge/moge-2-vitl-normal/model.pt")
 
 
 @dataclass
 class ProcessingConfig:
-    """Parameters for processing and densification."""
+    """Resolution and sampling density of the dense points."""
 
     pipeline_downsample_factor: int = 1
-    """Factor to downsample images before processing. Larger is faster."""
+    """Images and cameras are shrunk by this integer factor before anything else (1 = full size)."""
     downsample_density: int = 32
-    """Controls final point cloud density (1=densest)."""
+    """Pixel stride of the back-projection grid: every n-th row and column yields a point."""
 
 
 @dataclass
 class FilteringConfig:
-    """Parameters for multi-view consistency filtering."""
+    """Multi-view consistency vote."""
 
     vote_threshold: int = 5
-    """Number of votes required to remove a 'floater' point."""
+    """A point is dropped once this many views have voted against it (1..254)."""
     depth_threshold: float = 0.7
-    """Threshold to identify a floater (projected_depth < T * refined_depth)."""
+    """A view votes against a point that lies in front of the view's own surface by more than this ratio (z < T * D)."""
     num_neighbours: int | None = None
     """new: test each view against its K nearest views; None = against every view (reference)."""
     neighbour_mode: str = "covisibility"
@@ -92,7 +92,7 @@ class FusionConfig:
 
 @dataclass
 class ScriptConfig:
-    """Main configuration for the densification script."""
+    """Root of the configuration tree (same field names as the reference script, so the tyro flags match)."""
 
     paths: PathsConfig = field(default_factory=PathsConfig)
     moge: MoGeConfig = field(default_factory=MoGeConfig)

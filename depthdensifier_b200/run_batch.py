@@ -1,7 +1,8 @@
 """Batch driver (reference: scripts/run_batch.py:26-110): run the densification pipeline on every scan folder
 under ``root_dir`` (each holding ``sparse/0`` and ``images``), keep going when a scan fails, print a timing
-table at the end.  Same ``BatchConfig`` fields; ``base_config`` carries the shared ScriptConfig overrides
-(e.g. ``--base-config.filtering.vote-threshold 3``)."""
+table at the end.  Same ``BatchConfig`` fields and flags: ``root_dir`` and ``output_dir`` are required, ``config``
+embeds the ScriptConfig shared by all scans (e.g. ``--config.filtering.vote-threshold 3``), and each scan's model
+goes to ``<output_dir>/<scan>/sparse/0`` (scripts/run_batch.py:63-65)."""
 
 from __future__ import annotations
 
@@ -15,20 +16,24 @@ from .pipeline import PathsConfig, ScriptConfig, main as densify_main
 
 @dataclass
 class BatchConfig:
-    """Configuration for the batch processing script."""
+    """Batch run over every scan folder of one directory."""
 
-    root_dir: Path = Path("data/360_v2")
-    """Directory containing the scan folders."""
-    output_dir: Path = Path("results/batch")
-    """Where each scan's model is written (<output_dir>/<scan>/0)."""
+    root_dir: Path
+    """Folder whose sub-folders are the scans (each with images/ and sparse/0/)."""
+    output_dir: Path
+    """Results go to <output_dir>/<scan>/sparse/0."""
+    config: ScriptConfig = field(default_factory=ScriptConfig)
+    """Settings shared by all scans; the three paths are replaced per scan."""
     depth_root: Path | None = None
     """new: <depth_root>/<scan> holds the precomputed depth .npz files (None -> MoGe)."""
-    base_config: ScriptConfig = field(default_factory=ScriptConfig)
-    """Base configuration for the densification script; the paths are overridden per scan."""
 
 
 def main(config: BatchConfig) -> dict[str, float | str]:
-    scans = sorted(p for p in Path(config.root_dir).iterdir() if p.is_dir())
+    root = Path(config.root_dir).resolve()
+    if not root.is_dir():  # scripts/run_batch.py:48-50
+        print(f"Error: Root directory not found at {root}")
+        return {}
+    scans = sorted(p for p in root.iterdir() if p.is_dir())
     if not scans:
         print(f"No scan folders found in {config.root_dir}")
         return {}
@@ -39,8 +44,8 @@ def main(config: BatchConfig) -> dict[str, float | str]:
         if not recon.is_dir() or not images.is_dir():
             print(f"Skipping {scan.name}: missing sparse/0 or images")
             continue
-        run_config = copy.deepcopy(config.base_config)
-        run_config.paths = PathsConfig(recon_path=recon, image_dir=images, output_model_dir=Path(config.output_dir) / scan.name / "0",
+        run_config = copy.deepcopy(config.config)
+        run_config.paths = PathsConfig(recon_path=recon, image_dir=images, output_model_dir=Path(config.output_dir) / scan.name / "sparse" / "0",
                                        depth_dir=(Path(config.depth_root) / scan.name) if config.depth_root is not None else None)
         t0 = time.time()
         try:

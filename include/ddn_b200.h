@@ -32,7 +32,7 @@ extern "C" {
 #define DDN_API
 #endif
 
-#define DDN_VERSION 100 /* 0.1.0, mirrors the reference package __version__ (src/depthdensifier/__init__.py:5) */
+#define DDN_VERSION 200 /* ABI revision 2 (device-resident fusion sessions); the Python package keeps the reference's __version__ 0.1.0 */
 
 enum {
   DDN_OK = 0,
@@ -96,12 +96,18 @@ DDN_API int ddn_align_workspace_bytes(int64_t n_views, int64_t max_sparse_per_vi
  * cam_from_world [V,3,4] f64 row-major; kmat [V,3,3] f64 (only the top two rows are used, :112);
  * sparse_xyz [S,3] f64 world, CSR sparse_offsets [V+1] i64; refined [V,H,W] f32 out;
  * stats [V] out.  A view with no sparse points gets status DDN_VIEW_NO_SPARSE and an all-zero map.
- * Views that the reference returns unchanged get a copy of their input depth. */
+ * Views that the reference returns unchanged get a copy of their input depth.
+ * Optional bounding-box epilogue (src_table and bbox both non-NULL): bbox [6] (ddn_bbox_init encoding)
+ * is extended to enclose the back-projection (src_table [V,16] f32 from ddn_build_pair_tables, the
+ * arithmetic of ddn_backproject_filter) of every refined pixel > 0.  It is a tile-wise bound (the 8 corners
+ * of each 126x32 pixel tile at its smallest and largest depth), i.e. a superset of the exact box, and makes
+ * the voxel grid known BEFORE stages 2+3 run. */
 DDN_API int ddn_align_views(const ddn_align_config* cfg, int64_t n_views, int64_t height, int64_t width,
                     const float* depth, const uint8_t* mask, const double* cam_from_world,
                     const double* kmat, const double* sparse_xyz, const int64_t* sparse_offsets,
                     int64_t max_sparse_per_view, float* refined, ddn_view_stats* stats,
-                    void* workspace, int64_t workspace_bytes, void* stream);
+                    void* workspace, int64_t workspace_bytes, const float* src_table, float* bbox,
+                    void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Stages 2+3 - pixel back-projection fused with the multi-view consistency vote.
@@ -116,6 +122,7 @@ typedef struct {
   float two_sided_tau;     /* <= 0: one-sided z < thr*D (reference, :319-321); > 0: |z-D| > tau*D (new) */
   int32_t stride;          /* ProcessingConfig.downsample_density (scripts/test.py:37); 1 = densest */
   int32_t normals_in_world; /* 0 = reference quirk (camera-frame normal vs world dir, :291); 1 = rotate by R_src^T */
+  int32_t pixel_layout;    /* which 4 pixels a thread owns: 0 = 32 apart (default), 1 = adjacent (vector I/O); same results */
 } ddn_filter_config;
 
 DDN_API void ddn_filter_config_default(ddn_filter_config* cfg);
@@ -125,20 +132,27 @@ DDN_API void ddn_filter_config_default(ddn_filter_config* cfg);
  * on the device from the poses (cam_from_world [V,3,4] f64) and PINHOLE intrinsics
  * (intr [V,4] f64: fx, fy, cx, cy - scripts/test.py:81) and rounded once. */
 DDN_API int ddn_build_pair_tables(int64_t n_views_total, int64_t src_begin, int64_t n_src, int64_t k_nbr,
-                          const double* cam_from_world, const double* intr, const int32_t* nbr,
-                          float* pair_table, float* src_table, void* stream);
+                          int64_t height, int64_t width, const double* cam_from_world, const double* intr,
+                          const int32_t* nbr, float* pair_table, float* src_table, void* stream);
 
 /* refined_all [V,H,W] f32 (zero outside the mask); normal [n_src,H,W,3] f32 for the source views
  * src_begin..src_begin+n_src - only the normals of vote candidates are read, so this one pointer may
  * also be PINNED HOST memory (unified addressing): the map then never moves to the device; outputs on the strided grid Hs=ceil(H/stride), Ws=ceil(W/stride):
  * xyz [n_src,Hs,Ws,3] f32 world, votes [n_src,Hs,Ws] u8 (255 = pixel has no point, i.e. depth<=0).
  * bbox [6] f32 (optional, may be NULL): running min xyz / max xyz over points with
- * votes < vote_threshold; must be initialised to +inf/-inf by ddn_bbox_init. */
+ * votes < vote_threshold; must be initialised to +inf/-inf by ddn_bbox_init.
+ * vote_threshold is clamped to 255: votes saturate at 254 and 255 marks "no point", so a threshold of 255
+ * or more keeps every point that exists and never a pixel without one.
+ * mark (optional, may be NULL): a fusion session opened by ddn_fuse_begin*; the kernel then also sets the
+ * occupancy bit of every kept point (the "mark" pass of stage 4 fused into the epilogue, where the point
+ * is still in registers) and adds their number to the session's counts[0]. */
+struct ddn_fuse_session;
 DDN_API int ddn_backproject_filter(const ddn_filter_config* cfg, int64_t n_views_total, int64_t src_begin,
                            int64_t n_src, int64_t height, int64_t width, int64_t k_nbr,
                            const float* refined_all, const float* normal, const int32_t* nbr,
                            const float* pair_table, const float* src_table, int32_t vote_threshold,
-                           float* xyz, uint8_t* votes, float* bbox, void* stream);
+                           float* xyz, uint8_t* votes, float* bbox, const struct ddn_fuse_session* mark,
+                           void* stream);
 
 DDN_API int ddn_bbox_init(float* bbox, void* stream);
 
@@ -244,6 +258,82 @@ DDN_API int ddn_voxel_merge(const ddn_voxel_grid* grid_host, int64_t n_records, 
                     int64_t tile_begin, int64_t tile_end, uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb,
                     int32_t* out_count, int64_t* counts_out, void* workspace, int64_t workspace_bytes,
                     void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage 4 without a host round trip: the FUSION SESSION.  The grid is derived ON THE DEVICE from one or
+ * more bounding boxes (ddn_bbox_init encoding; with R ranks the R boxes may sit in peer memory) and kept
+ * in device memory, launch sizes come from capacities, actual extents are read by the kernels.  A step is
+ *   ddn_fuse_begin -> ddn_backproject_filter(..., mark = session) -> ddn_fuse_finish[_partial]
+ *   [-> ddn_fuse_merge_peers]
+ * and never needs the host to look at a result in between.
+ * ------------------------------------------------------------------------------------------ */
+enum { DDN_GRID_OK = 0, DDN_GRID_EMPTY = 1, DDN_GRID_TOO_LARGE = 2, DDN_GRID_TOO_MANY_BITS = 3 };
+
+typedef struct ddn_grid_state { /* 64 bytes of DEVICE memory, written by ddn_fuse_begin* */
+  float voxel;
+  float origin[3]; /* (floor(box_min / voxel) - 1) * voxel in float32: one cell of slack below the box */
+  int32_t bits[3];
+  int32_t dims[3];
+  int64_t n_units; /* occupancy units in use: ceil(cells / 96); 0 unless status == DDN_GRID_OK */
+  int32_t status;  /* DDN_GRID_*: EMPTY = no finite box, TOO_LARGE = more cells than cap_units * 96 */
+  int32_t reserved;
+  int64_t cells;
+} ddn_grid_state;
+
+#define DDN_MAX_PEERS 16
+
+typedef struct ddn_fuse_session { /* HOST struct of DEVICE pointers, owned by the caller */
+  ddn_grid_state* grid;
+  void* units;           /* [cap_units] 16-byte units: 96 occupancy bits + the unit's rank prefix */
+  int64_t cap_units;
+  uint8_t* dirty;        /* [cap_units / 2048 + 1] one flag per 32 KB of units, or NULL.  With flags the
+                            session keeps its units clean between steps (ddn_fuse_begin clears only what the
+                            previous step touched) and the rank passes skip untouched tiles; without, every
+                            step clears and scans the whole grid. */
+  uint32_t* tile_sums;   /* [cap_units / 256 + 2] scratch */
+  uint32_t* tile_prefix; /* [cap_units / 256 + 2] or NULL: index of the first record of every ownership tile
+                            (256 units = 24,576 cells in key order); needed by ddn_fuse_merge_peers */
+  int64_t* counts;       /* [2]: participating points, voxels (the true count even when it exceeds a capacity) */
+} ddn_fuse_session;
+
+/* Sizes of the session buffers for grids of up to max_cells cells (all outputs in bytes but cap_units). */
+DDN_API int ddn_fuse_session_sizes(int64_t max_cells, int64_t* cap_units, int64_t* units_bytes, int64_t* dirty_bytes,
+                           int64_t* tile_sums_bytes, int64_t* tile_prefix_bytes);
+/* Once after allocation (and after any error): clears units and flags. */
+DDN_API int ddn_fuse_session_reset(const ddn_fuse_session* s, void* stream);
+/* Opens a step: grid from the n_boxes (<= DDN_MAX_PEERS) bounding boxes bbox_ptrs_host[i] (HOST array of
+ * device pointers to [6] encoded boxes), occupancy cleared, counts zeroed. */
+DDN_API int ddn_fuse_begin(const ddn_fuse_session* s, const void* const* bbox_ptrs_host, int32_t n_boxes, float voxel,
+                   void* stream);
+/* Same with a grid chosen on the host. */
+DDN_API int ddn_fuse_begin_grid(const ddn_fuse_session* s, const ddn_voxel_grid* grid_host, void* stream);
+/* Stand-alone mark pass for points that did not come out of ddn_backproject_filter(mark = s). */
+DDN_API int ddn_fuse_mark_points(const ddn_fuse_session* s, int64_t n_points, const float* xyz, const uint8_t* votes,
+                         int32_t vote_threshold, void* stream);
+/* Rank + accumulate + finalise of the marked points (same xyz / votes / threshold as the mark).  Outputs as
+ * ddn_voxel_fuse with capacity cap_out voxels; accum: scratch of cap_out * 40 bytes, 16-byte aligned. */
+DDN_API int ddn_fuse_finish(const ddn_fuse_session* s, int64_t n_points, int64_t row_len, const float* xyz,
+                    const uint8_t* rgb, const uint8_t* votes, int32_t vote_threshold, uint64_t* out_keys,
+                    float* out_xyz, uint8_t* out_rgb, int32_t* out_count, int64_t cap_out, void* accum,
+                    int64_t accum_bytes, void* stream);
+/* Rank + accumulate into partial RECORDS [cap_records, DDN_RECORD_WORDS] (keys ascending) and, when the session
+ * has one, the tile prefix. */
+DDN_API int ddn_fuse_finish_partial(const ddn_fuse_session* s, int64_t n_points, int64_t row_len, const float* xyz,
+                            const uint8_t* rgb, const uint8_t* votes, int32_t vote_threshold, uint64_t* records,
+                            int64_t cap_records, void* stream);
+/* Owner-side exchange + merge over PEER MEMORY (NVLink loads inside the kernels, no staging copy, no host
+ * plan).  Every rank calls it after all ranks finished ddn_fuse_finish_partial on the same grid (the caller
+ * provides that barrier).  peer_*_host: HOST arrays of n_ranks device pointers - every rank's units, records and
+ * tile_prefix as mapped into this process (entry `rank` = the local buffers).  The ranks split the tiles into
+ * n_ranks contiguous ranges balancing the global record count (each computes the same cuts from the summed
+ * prefixes); this rank ORs the occupancy of its range over all ranks, ranks it, pulls its share of every
+ * rank's records and adds them, and finalises.  plan: device scratch [64] i64 (out: [0],[1] = tile range,
+ * [2] = records received); prefix_scratch: device [(cap_units / 256 + 2) * n_ranks] u32.  Outputs as
+ * ddn_fuse_finish.  The rank-ordered concatenation of the outputs is globally key-sorted. */
+DDN_API int ddn_fuse_merge_peers(const ddn_fuse_session* s, int32_t rank, int32_t n_ranks, const void* const* peer_units_host,
+                         const void* const* peer_records_host, const void* const* peer_tile_prefix_host, int64_t* plan,
+                         uint32_t* prefix_scratch, uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb,
+                         int32_t* out_count, int64_t cap_out, void* accum, int64_t accum_bytes, void* stream);
 
 /* Stand-alone pieces of stage 4 (used by the multi-GPU path and by tests). */
 DDN_API int ddn_voxel_keys(const ddn_voxel_grid* grid_host, int64_t n_points, const float* xyz,

@@ -118,7 +118,7 @@ class OracleBackend:
             refined[v] = torch.from_numpy(ref)
         return refined, stats
 
-    def build_pair_tables(self, poses, intr, nbr, src_begin, n_src):
+    def build_pair_tables(self, poses, intr, nbr, src_begin, n_src, height=0, width=0):
         return (poses.numpy(), intr.numpy(), nbr.numpy()), None
 
     def new_bbox(self, dev):

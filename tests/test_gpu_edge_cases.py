@@ -70,7 +70,7 @@ def test_filter_padded_and_duplicate_neighbours(lib_built):
     nbr = np.array([[1, -1, 2, 2, 0, -1], [-1, -1, -1, -1, -1, -1], [3, 3, 3, 1, -1, 4], [0, 1, 2, 3, 4, -1], [4, 4, 0, -1, 1, 2]],
                    np.int32)
     d_pose, d_intr, d_nbr = _cuda(poses), _cuda(intr), _cuda(nbr)
-    pair, src = ops.build_pair_tables(d_pose, d_intr, d_nbr, 0, 5)
+    pair, src = ops.build_pair_tables(d_pose, d_intr, d_nbr, 0, 5, 90, 120)
     xyz, votes = ops.backproject_filter(_cuda(refined), _cuda(sc.normal.numpy()), d_nbr, pair, src, 0, 2, ops.FilterOptions())
     votes = votes.cpu().numpy()
     valid = refined > 0

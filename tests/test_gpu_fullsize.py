@@ -55,8 +55,8 @@ def test_cfg1_pipeline_vs_oracle(lib_built):
     # stage 4 on the GPU's kept points: keys / counts / colours bit-exact, positions within tolerance
     keep = votes[valid] < thr
     kept_xyz, kept_rgb = xyz[keep], sc.rgb.numpy()[valid][keep]
-    origin = np.array(list(res.grid.origin), np.float32)
-    assert np.array_equal(origin, R.voxel_origin(kept_xyz, voxel))
+    origin = np.array(list(res.host_grid().origin), np.float32)  # derived on the device from the alignment kernel's box
+    assert (origin <= kept_xyz.min(0)).all()
     k_ref, m_ref, c_ref, n_ref = R.voxel_fuse(kept_xyz, kept_rgb, voxel, origin)
     mv = int(res.counts[1])
     assert res.counts.cpu().tolist() == [int(keep.sum()), len(k_ref)]
@@ -87,10 +87,11 @@ def test_fullsize_properties(lib_built, V, W, H, K):
     # keys strictly ascending (sorted + unique), every axis inside the grid
     keys = res.voxel_keys[:mv]
     assert bool((keys[1:] > keys[:-1]).all())
+    grid = res.host_grid()
     for ax in range(3):
-        assert int(((keys >> (21 * ax)) & 0x1FFFFF).max()) < res.grid.dims[ax]
+        assert int(((keys >> (21 * ax)) & 0x1FFFFF).max()) < grid.dims[ax]
     # fused positions lie inside their voxel (up to float32 rounding of the centre)
-    org = torch.tensor(list(res.grid.origin), device=dev)
+    org = torch.tensor(list(grid.origin), device=dev)
     cell = torch.stack([(keys >> (21 * ax)) & 0x1FFFFF for ax in range(3)], 1).float()
     rel = (res.voxel_xyz[:mv] - org) / voxel - cell
     assert float(rel.min()) > -1e-3 and float(rel.max()) < 1 + 1e-3
@@ -98,15 +99,21 @@ def test_fullsize_properties(lib_built, V, W, H, K):
     bb = ops.decode_bbox(res.bbox)
     kept = res.xyz[keep]
     assert np.array_equal(bb[:3], kept.min(0).values.cpu().numpy()) and np.array_equal(bb[3:], kept.max(0).values.cpu().numpy())
+    # the alignment kernel's tile-wise box encloses EVERY back-projected pixel, and not by much
+    bv = ops.decode_bbox(res.bbox_valid)
+    allp = res.xyz[res.votes != 255]
+    lo, hi = allp.min(0).values.cpu().numpy(), allp.max(0).values.cpu().numpy()
+    assert (bv[:3] <= lo).all() and (bv[3:] >= hi).all()
+    assert np.prod(bv[3:] - bv[:3]) < 2.0 * np.prod(hi - lo)
     # permutation invariance (integer sums): fusing the same kept points in a random order gives the same bits
     perm = torch.randperm(kept.shape[0], device=dev, generator=torch.Generator(device=dev).manual_seed(1))
     rgb_kept = sc.rgb[keep]
-    k2, x2, c2, n2, cnt2 = ops.voxel_fuse(kept[perm].contiguous(), rgb_kept[perm].contiguous(), None, 1, res.grid)
+    k2, x2, c2, n2, cnt2 = ops.voxel_fuse(kept[perm].contiguous(), rgb_kept[perm].contiguous(), None, 1, grid)
     assert torch.equal(k2, keys) and torch.equal(n2, res.voxel_count[:mv]) and torch.equal(c2, res.voxel_rgb[:mv])
     assert torch.equal(x2, res.voxel_xyz[:mv])
     # idempotence: fusing the fused cloud reproduces it - except for the few means that float32 rounding puts
     # exactly on a voxel face (they may fall into the neighbour cell)
-    k3, x3, c3, n3, cnt3 = ops.voxel_fuse(res.voxel_xyz[:mv].contiguous(), res.voxel_rgb[:mv].contiguous(), None, 1, res.grid)
+    k3, x3, c3, n3, cnt3 = ops.voxel_fuse(res.voxel_xyz[:mv].contiguous(), res.voxel_rgb[:mv].contiguous(), None, 1, grid)
     assert int(n3.sum()) == mv and mv - len(k3) <= 1e-4 * mv
     same = torch.isin(k3, keys)
     assert float(same.float().mean()) > 1 - 1e-4
@@ -115,7 +122,7 @@ def test_fullsize_properties(lib_built, V, W, H, K):
     assert float((x3[single & same] - res.voxel_xyz[:mv][pos]).abs().max()) <= 1e-6
     # sub-scene consistency: the votes of 3 source views recomputed alone (same refined maps) are identical
     sub = [0, V // 2, V - 1]
-    pair, src = ops.build_pair_tables(sc.cam_from_world, sc.intrinsics, nbr, 0, V)
+    pair, src = ops.build_pair_tables(sc.cam_from_world, sc.intrinsics, nbr, 0, V, H, W)
     for s in sub:
         xyz_s, votes_s = ops.backproject_filter(res.refined, sc.normal[s:s + 1].contiguous(), nbr, pair[s:s + 1].contiguous(),
                                                 src[s:s + 1].contiguous(), s, thr, eng.cfg.filter)

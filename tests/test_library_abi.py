@@ -20,7 +20,7 @@ def test_exports_every_declared_symbol(lib_built):
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/ddn_b200.h but not exported"
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
-    assert _lib.load().ddn_version() == 100
+    assert _lib.load().ddn_version() == 200
 
 
 def test_argument_validation_without_gpu(lib_built):
