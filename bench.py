@@ -361,7 +361,7 @@ def main():
         # hardware equivalence before anything is timed: N ranks == 1 rank, bit for bit, on the path that is timed
         from depthdensifier_b200.selfcheck import multi_gpu_check
 
-        reports = [multi_gpu_check(dev, rank, world), multi_gpu_check(dev, rank, world, n_views=29, width=203, height=131, k=3, voxel=0.03)]
+        reports = [multi_gpu_check(dev, rank, world), multi_gpu_check(dev, rank, world, n_views=29, width=203, height=131, k=3, voxel=0.03, dedup=True)]
         multi_gpu = {"passed": all(r["passed"] for r in reports), "path": reports[0]["path"], "cases": reports}
         if not multi_gpu["passed"]:
             if rank == 0:

@@ -136,6 +136,7 @@ SYMBOLS = {
     "ddn_fuse_begin": (C.c_int, [C.POINTER(FuseSession), C.POINTER(_vp), _i32, C.c_float, _vp]),
     "ddn_fuse_begin_grid": (C.c_int, [C.POINTER(FuseSession), C.POINTER(VoxelGrid), _vp]),
     "ddn_fuse_mark_points": (C.c_int, [C.POINTER(FuseSession), _i64, _vp, _vp, _i32, _vp]),
+    "ddn_fuse_unmark_points": (C.c_int, [C.POINTER(FuseSession), _i64, _vp, _vp]),
     "ddn_fuse_finish": (
         C.c_int,
         [C.POINTER(FuseSession), _i64, _i64, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp],
@@ -143,8 +144,8 @@ SYMBOLS = {
     "ddn_fuse_finish_partial": (C.c_int, [C.POINTER(FuseSession), _i64, _i64, _vp, _vp, _vp, _i32, _vp, _i64, _vp]),
     "ddn_fuse_merge_peers": (
         C.c_int,
-        [C.POINTER(FuseSession), _i32, _i32, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp,
-         _i64, _vp, _i64, _vp],
+        [C.POINTER(FuseSession), _i32, _i32, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _vp, _i64, _vp, _vp, _vp,
+         _vp, _i64, _vp, _i64, _vp],
     ),
 }
 

@@ -14,8 +14,8 @@
 //               unit's fourth word; the pass also emits the sorted keys
 //   accumulate  integer fixed-point sums per voxel with 64-bit RED.ADD.  The L2 atomic units bound this
 //               pass, so a warp first merges the points of its 16 x 2 pixel tile that share a cell
-//               (MATCH.ANY + REDUX over the peer mask); the group's first lane looks the slot up (ONE
-//               16 B load: 96 bits + prefix) and issues the atomics.
+//               (MATCH.ANY + shuffles); the group's first lane looks the slot up (ONE 16 B load:
+//               96 bits + prefix) and issues the atomics.
 //   finalize    one thread per voxel: mean = centre + sum/count, colour = round-half-up
 //
 // Integer sums make the result independent of the order of points and of how they are split over
@@ -210,6 +210,27 @@ mark_records_kernel(FuseDev f, int64_t n, const uint64_t* __restrict__ records, 
   if (threadIdx.x == 0 && s_count) atomicAdd(f.counts, (unsigned long long)s_count);
 }
 
+// N5 (sparse-cloud merge with de-duplication): clears the occupancy bit of every cell that holds one of the
+// given points, so the dense voxel there is never created (the sparse point itself is kept by the caller).
+// Runs between the mark and the rank passes; [cell_begin, cell_end): the cells this call may touch.
+__global__ void __launch_bounds__(256)
+unmark_points_kernel(FuseDev f, int64_t n, const float* __restrict__ xyz, const long long* __restrict__ plan) {
+  const GridDev g = *f.grid;
+  if (g.n_units == 0) return;
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  uint32_t kx, ky, kz;
+  const uint64_t cell = cell_of_point(g, 1.0f / g.voxel, __ldg(xyz + i * 3 + 0), __ldg(xyz + i * 3 + 1), __ldg(xyz + i * 3 + 2), kx, ky, kz);
+  if (cell == kNoCell) return;
+  if (plan != nullptr) {
+    const uint64_t cb = (uint64_t)plan[0] * kOwnUnits * kUnitBits, ce = (uint64_t)plan[1] * kOwnUnits * kUnitBits;
+    if (cell < cb || cell >= ce) return;
+  }
+  const uint32_t w32 = (uint32_t)(cell >> 5);
+  const uint32_t unit = w32 / 3u;
+  atomicAnd(f.units + (size_t)unit * 4 + (w32 - unit * 3u), ~(1u << (cell & 31)));
+}
+
 // ---- rank: popcount scan over the units --------------------------------------------------------
 __device__ __forceinline__ int popc3(const uint4& u) { return __popc(u.x) + __popc(u.y) + __popc(u.z); }
 
@@ -399,12 +420,17 @@ zero_accum_kernel(ulonglong2* __restrict__ accum2, const unsigned long long* __r
     accum2[i] = make_ulonglong2(0ull, 0ull);
 }
 
+// slot of `cell` in the key-sorted output, or kNoSlot when its occupancy bit is not set (a cell that
+// ddn_fuse_unmark_points removed: its points do not participate)
+constexpr uint32_t kNoSlot = 0xffffffffu;
 __device__ __forceinline__ uint32_t slot_of_cell(uint64_t cell, const uint4* __restrict__ units) {
   const uint32_t w32 = (uint32_t)(cell >> 5);
   const uint32_t unit = w32 / 3u;
   const int wi = (int)(w32 - unit * 3u);
   const uint32_t below = (1u << (cell & 31)) - 1u;
   const uint4 u = __ldg(units + unit);
+  const uint32_t word = wi == 0 ? u.x : (wi == 1 ? u.y : u.z);
+  if (((word >> (cell & 31)) & 1u) == 0u) return kNoSlot;
   uint32_t s = u.w;
   s += __popc(u.x & (wi > 0 ? 0xffffffffu : below));
   s += wi > 0 ? __popc(u.y & (wi > 1 ? 0xffffffffu : below)) : 0;
@@ -414,11 +440,12 @@ __device__ __forceinline__ uint32_t slot_of_cell(uint64_t cell, const uint4* __r
 
 // accumulate: one point per lane, aggregated ACROSS THE WARP before touching memory.  With a row length
 // (points are pixels of [rows, row_len] images) a warp covers a 16 x 2 pixel tile, otherwise 32
-// consecutive points.  Lanes whose points fall into the same cell are found with MATCH.ANY and summed
-// with REDUX over that peer mask (32-bit partial sums: at most 32 points of |offset| <= 2^19); the
-// lowest lane of each group looks the slot up and issues the five 64-bit REDs.  The L2 atomic units are
-// the bound of this pass, so points per RED group is what matters: ~2 at cfg 2.
-// (-DDDN_ACC_SHFL: the round-1 aggregation, a shuffle walk over the peer mask.)
+// consecutive points.  Lanes whose points fall into the same cell are found with MATCH.ANY; every lane
+// walks its peer mask with shuffles (32-bit partial sums: at most 32 points of |offset| <= 2^19), and
+// the lowest lane of each group looks the slot up and issues the five 64-bit REDs.  The L2 atomic units
+// are the bound of this pass, so points per RED group is what matters: ~2 at cfg 2.
+// (-DDDN_ACC_REDUX sums each group with REDUX over its own peer mask instead of the shuffle walk: the
+// hardware serialises the distinct masks of a warp, measured 2.5x SLOWER - profiles/README.md, round 2.)
 #ifndef DDN_ACC_TPW
 #define DDN_ACC_TPW 8
 #endif
@@ -509,7 +536,7 @@ accumulate_points_kernel(const GridDev* __restrict__ gp, int64_t n, int row_len,
     const bool leader = valid && (__ffs(peers) - 1) == lane;
     int sx = 0, sy = 0, sz = 0;
     uint32_t srg = 0, sb = 0;
-#ifdef DDN_ACC_SHFL
+#ifndef DDN_ACC_REDUX
     const int iters = __reduce_max_sync(0xffffffffu, __popc(peers));
     uint32_t rest = peers;
 #pragma unroll 1
@@ -706,6 +733,21 @@ merge_or_kernel(FuseDev f, PeerPtrs peer_units, int rank, int R, const long long
       tile_sums[t - t0] = (uint32_t)total;
       if (total > 0 && f.dirty != nullptr) f.dirty[(t * kOwnUnits) / kTileUnits] = 1;
     }
+  }
+}
+
+// tile counts of the owned range again (after ddn_fuse_merge_peers removed the cells of the sparse cloud)
+__global__ void __launch_bounds__(kOwnUnits)
+merge_recount_kernel(FuseDev f, const long long* __restrict__ plan, uint32_t* __restrict__ tile_sums) {
+  __shared__ int s_warp[kScanThreads / 32];
+  const long long n_units = f.grid->n_units;
+  const long long t0 = plan[0], t1 = plan[1];
+  const uint4* my_units = reinterpret_cast<const uint4*>(f.units);
+  for (long long t = t0 + blockIdx.x; t < t1; t += gridDim.x) {
+    if (tile_sums[t - t0] == 0u) continue;  // CTA-uniform: nothing was there
+    const long long ui = t * kOwnUnits + threadIdx.x;
+    const int total = block_sum_256(ui < n_units ? popc3(my_units[ui]) : 0, s_warp);
+    if (threadIdx.x == 0) tile_sums[t - t0] = (uint32_t)total;
   }
 }
 
@@ -1131,6 +1173,16 @@ int ddn_fuse_mark_points(const ddn_fuse_session* s, int64_t n_points, const floa
   return launch_mark_points(s, n_points, xyz, votes, std::min(vote_threshold, 255), (cudaStream_t)stream);
 }
 
+int ddn_fuse_unmark_points(const ddn_fuse_session* s, int64_t n_points, const float* xyz, void* stream) {
+  using namespace ddn;
+  DDN_TRY(session_check(s));
+  DDN_REQUIRE(n_points >= 0 && n_points < (1ll << 31) - 1024, "n_points");
+  if (n_points == 0) return DDN_OK;
+  DDN_REQUIRE(xyz != nullptr, "null pointer");
+  unmark_points_kernel<<<(unsigned)((n_points + 255) / 256), 256, 0, (cudaStream_t)stream>>>(fuse_dev(s), n_points, xyz, nullptr);
+  return after_launch("unmark_points_kernel");
+}
+
 int ddn_fuse_finish(const ddn_fuse_session* s, int64_t n_points, int64_t row_len, const float* xyz, const uint8_t* rgb,
                     const uint8_t* votes, int32_t vote_threshold, uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb,
                     int32_t* out_count, int64_t cap_out, void* accum, int64_t accum_bytes, void* stream) {
@@ -1170,9 +1222,10 @@ int ddn_fuse_finish_partial(const ddn_fuse_session* s, int64_t n_points, int64_t
 
 int ddn_fuse_merge_peers(const ddn_fuse_session* s, int32_t rank, int32_t n_ranks, const void* const* peer_units_host,
                          const void* const* peer_records_host, const void* const* peer_tile_prefix_host, int64_t* plan,
-                         uint32_t* prefix_scratch, uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb,
-                         int32_t* out_count, int64_t cap_out, void* accum, int64_t accum_bytes, void* stream) {
+                         uint32_t* prefix_scratch, const float* drop_xyz, int64_t n_drop, uint64_t* out_keys, float* out_xyz,
+                         uint8_t* out_rgb, int32_t* out_count, int64_t cap_out, void* accum, int64_t accum_bytes, void* stream) {
   using namespace ddn;
+  DDN_REQUIRE(n_drop >= 0 && n_drop < (1ll << 31) - 1024 && (n_drop == 0 || drop_xyz != nullptr), "drop points");
   DDN_TRY(session_check(s));
   DDN_REQUIRE(n_ranks >= 1 && n_ranks <= DDN_MAX_PEERS && rank >= 0 && rank < n_ranks, "rank / n_ranks");
   DDN_REQUIRE(peer_units_host && peer_records_host && peer_tile_prefix_host && plan && prefix_scratch, "null pointer");
@@ -1200,6 +1253,12 @@ int ddn_fuse_merge_peers(const ddn_fuse_session* s, int32_t rank, int32_t n_rank
   DDN_TRY(after_launch("merge_copy_prefix_kernel"));
   merge_or_kernel<<<kPersistentCtas, kOwnUnits, 0, st>>>(f, pu, rank, n_ranks, planll, prefix_scratch, stride, s->tile_sums);
   DDN_TRY(after_launch("merge_or_kernel"));
+  if (n_drop > 0) {  // N5: cells of the sparse cloud leave the merged occupancy; tile counts again
+    unmark_points_kernel<<<(unsigned)((n_drop + 255) / 256), 256, 0, st>>>(f, n_drop, drop_xyz, planll);
+    DDN_TRY(after_launch("unmark_points_kernel"));
+    merge_recount_kernel<<<kPersistentCtas, kOwnUnits, 0, st>>>(f, planll, s->tile_sums);
+    DDN_TRY(after_launch("merge_recount_kernel"));
+  }
   tile_scan_kernel<<<1, 1024, 0, st>>>(gp, ScanRange{0, 0}, planll, s->tile_sums, counts);
   DDN_TRY(after_launch("tile_scan_kernel"));
   zero_accum_kernel<<<kPersistentCtas, 256, 0, st>>>((ulonglong2*)acc, counts, kAccWords, cap_out);

@@ -327,7 +327,8 @@ class ShardedDensifier:
         s = cfg.filter.stride
         rgb_s = rgb if s == 1 else rgb[:, ::s, ::s].contiguous()
         if self.device_path:
-            k, x, c, n, counts = mark("voxel_fuse", lambda: self._fuse_device(xyz, rgb_s, votes, mark))
+            drop = self._sparse_for_dedup(sparse_xyz) if cfg.dedup_sparse else None
+            k, x, c, n, counts = mark("voxel_fuse", lambda: self._fuse_device(xyz, rgb_s, votes, mark, drop))
             res.session, res.grid = self.session, grid
             res.voxel_keys, res.voxel_xyz, res.voxel_rgb, res.voxel_count, res.counts = k, x, c, n, counts
             return res
@@ -424,7 +425,25 @@ class ShardedDensifier:
             mark("backproject_filter", lambda: k4(0, self.n_local))
         return xyz, votes, bbox
 
-    def _fuse_device(self, xyz, rgb, votes, mark=None):
+    def _sparse_for_dedup(self, sparse_xyz):
+        """N5: float32 sparse points of ALL ranks (padded with NaN, which falls into no cell).  The per-rank
+        capacity is agreed once (the only host wait, first call)."""
+        mine = sparse_xyz.float().contiguous()
+        if self.peer is None:
+            return mine
+        import torch.distributed as dist
+
+        if getattr(self, "_sparse_cap", None) is None or self._sparse_cap < mine.shape[0]:
+            cap = torch.tensor([mine.shape[0]], dtype=torch.int64, device=self.device)
+            dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=self.group)
+            self._sparse_cap = int(cap.item())
+        pad = torch.full((self._sparse_cap, 3), float("nan"), dtype=torch.float32, device=self.device)
+        pad[: mine.shape[0]] = mine
+        allp = torch.empty((self.world * self._sparse_cap, 3), dtype=torch.float32, device=self.device)
+        dist.all_gather_into_tensor(allp, pad, group=self.group)
+        return allp
+
+    def _fuse_device(self, xyz, rgb, votes, mark=None, drop=None):
         """Stage 4 on the device path.  One rank: rank + accumulate + finalise.  R ranks: partial records into
         peer-visible memory, one barrier, then the owner-side merge that reads the peers' units and records over
         NVLink.  Returns persistent output buffers (valid until the next step) and a snapshot of the counts."""
@@ -433,6 +452,8 @@ class ShardedDensifier:
         sess = self.session
         flat = (xyz.view(-1, 3), rgb.view(-1, 3), votes.view(-1))
         if self.peer is None:
+            if drop is not None and drop.shape[0] > 0:
+                sess.unmark_points(drop)
             k, x, c, n, counts = self.ops.fuse_finish(sess, *flat, self.thr, row_len=xyz.shape[2])
             return k, x, c, n, counts.clone()
         rec, hdl, _ = self.peer.buffer("records", tuple(self.peer_records_shape), torch.int64)
@@ -440,7 +461,7 @@ class ShardedDensifier:
         hdl.barrier()  # every rank's units, tile prefix and records are complete
         k, x, c, n, counts = mark("fuse_merge", lambda: self.ops.fuse_merge_peers(
             sess, self.rank, self.world, self._peer_units, self._peer_records, self._peer_prefix, self._plan,
-            self._prefix_scratch, self._cap_merge, out=self._merge_out))
+            self._prefix_scratch, self._cap_merge, out=self._merge_out, drop_xyz=drop))
         return k, x, c, n, counts.clone()
 
     def _nbr_full(self) -> torch.Tensor:
@@ -651,7 +672,8 @@ class ShardedDensifier:
         if self.device_path:
             comp.wait_event(ev_rgb)
             rgb_s = st["rgb"] if s == 1 else st["rgb"][:, ::s, ::s].contiguous()
-            k, x, c, m, counts = self._fuse_device(xyz, rgb_s, votes)
+            drop = self._sparse_for_dedup(st["sparse_xyz"]) if cfg.dedup_sparse else None
+            k, x, c, m, counts = self._fuse_device(xyz, rgb_s, votes, drop=drop)
             st_grid = self.session.grid_state()  # the one wait of the call: the host needs the voxel count to copy back
             if st_grid.status == 1:
                 return out

@@ -23,6 +23,7 @@ class DensifyConfig:
     vote_threshold: int | None = None  # None -> ceil(K/2); the reference default 5 assumes K = V
     voxel: float | None = 0.01  # None -> no fusion (reference behaviour: keep every point)
     max_grid_cells: int = 1 << 33  # capacity of the fusion session's occupancy bitmap (16 bytes per 96 cells)
+    dedup_sparse: bool = False  # N5: no dense voxel where the sparse cloud already has a point (reference: plain append)
 
 
 def clamp_vote_threshold(thr: int) -> int:
@@ -137,6 +138,8 @@ class DensifyEngine:
         if fuse:
             s = cfg.filter.stride
             rgb_s = rgb if s == 1 else rgb[:, ::s, ::s].contiguous()
+            if cfg.dedup_sparse and sparse_xyz.shape[0] > 0:
+                sess.unmark_points(sparse_xyz.float().contiguous())
             k, x, c, n, counts = ops.fuse_finish(sess, xyz.view(-1, 3), rgb_s.view(-1, 3), votes.view(-1), thr, row_len=xyz.shape[2])
             res.session, res.grid = sess, grid
             res.voxel_keys, res.voxel_xyz, res.voxel_rgb, res.voxel_count, res.counts = k, x, c, n, counts.clone()

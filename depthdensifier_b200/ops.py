@@ -339,6 +339,16 @@ class FuseSession:
             _lib.check(lib.ddn_fuse_mark_points(C.byref(self.c), xyz.shape[0], _p(xyz), _p(votes), int(vote_threshold), _stream()))
 
 
+    def unmark_points(self, xyz) -> None:
+        """N5: the cells of these points (xyz [N,3] f32, e.g. the sparse cloud) leave the occupancy, so no dense
+        voxel is created there.  Between the mark and fuse_finish*."""
+        lib = _lib.load()
+        _require_cuda(xyz)
+        assert xyz.dtype == torch.float32 and xyz.dim() == 2 and xyz.shape[1] == 3
+        with torch.cuda.device(self.device):
+            _lib.check(lib.ddn_fuse_unmark_points(C.byref(self.c), xyz.shape[0], _p(xyz), _stream()))
+
+
 def new_voxel_outputs(cap_out: int, dev):
     return (torch.empty(cap_out, dtype=torch.int64, device=dev), torch.empty((cap_out, 3), dtype=torch.float32, device=dev),
             torch.empty((cap_out, 3), dtype=torch.uint8, device=dev), torch.empty(cap_out, dtype=torch.int32, device=dev))
@@ -373,9 +383,10 @@ def fuse_finish_partial(sess: FuseSession, xyz, rgb, votes, vote_threshold: int,
 
 
 def fuse_merge_peers(sess: FuseSession, rank: int, world: int, peer_units, peer_records, peer_tile_prefix, plan, prefix_scratch,
-                     cap_out: int, out=None):
+                     cap_out: int, out=None, drop_xyz=None):
     """Owner-side exchange + merge over peer memory.  ``peer_*``: per rank, the device address of that rank's
-    units / records / tile prefix as mapped into this process.  Returns keys, xyz, rgb, count, counts."""
+    units / records / tile prefix as mapped into this process.  ``drop_xyz`` [n,3] f32: N5, the sparse points of
+    ALL ranks whose cells are removed from the merged occupancy.  Returns keys, xyz, rgb, count, counts."""
     lib = _lib.load()
     dev = sess.device
     k, x, c, n = out if out is not None else new_voxel_outputs(cap_out, dev)
@@ -383,7 +394,8 @@ def fuse_merge_peers(sess: FuseSession, rank: int, world: int, peer_units, peer_
     arr = lambda ptrs: (C.c_void_p * world)(*[int(v) for v in ptrs])
     with torch.cuda.device(dev):
         _lib.check(lib.ddn_fuse_merge_peers(C.byref(sess.c), int(rank), int(world), arr(peer_units), arr(peer_records),
-                                            arr(peer_tile_prefix), _p(plan), _p(prefix_scratch), _p(k), _p(x), _p(c), _p(n), int(cap_out),
+                                            arr(peer_tile_prefix), _p(plan), _p(prefix_scratch), _p(drop_xyz),
+                                            0 if drop_xyz is None else drop_xyz.shape[0], _p(k), _p(x), _p(c), _p(n), int(cap_out),
                                             _p(acc), acc.numel(), _stream()))
     return k, x, c, n, sess.counts
 

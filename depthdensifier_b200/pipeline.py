@@ -88,6 +88,9 @@ class FusionConfig:
     """new: voxel-grid fusion of the kept points (the reference only concatenates)."""
 
     voxel_size: float | None = None
+    dedup_sparse: bool = False
+    """With voxel_size: no dense voxel is created where the sparse cloud already has a point (N5); the reference
+    appends every dense point."""
 
 
 @dataclass
@@ -248,6 +251,9 @@ def main(config: ScriptConfig, depth_provider: DepthProvider | None = None, retu
     if len(shapes) != 1:
         raise ValueError(f"all depth maps must share one size for the batched kernels, got {sorted(shapes)}")
     V = len(views)
+    if (config.filtering.num_neighbours is None or config.filtering.num_neighbours >= V) and V > 1024:
+        raise ValueError(f"{V} views: testing every view against every view (the reference's behaviour, K = V) is limited to "
+                         "1024 views per call; set --filtering.num-neighbours (e.g. 8) to use a neighbour table")
     timings["inputs"] = time.time() - t0
 
     # --- 4b-6. device pipeline: align -> back-project + consistency vote [-> voxel fusion] ---
@@ -269,7 +275,7 @@ def main(config: ScriptConfig, depth_provider: DepthProvider | None = None, retu
     filt = ops.FilterOptions(depth_threshold=config.filtering.depth_threshold, sample_mode=config.filtering.sample_mode,
                              stride=max(int(config.processing.downsample_density), 1))
     eng = DensifyEngine(DensifyConfig(align=align, filter=filt, vote_threshold=int(config.filtering.vote_threshold),
-                                      voxel=config.fusion.voxel_size), device=dev)
+                                      voxel=config.fusion.voxel_size, dedup_sparse=bool(config.fusion.dedup_sparse)), device=dev)
     offsets = np.concatenate([[0], np.cumsum([len(p) for p in sparse])]).astype(np.int64)
     to = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt).to(dev)
     rgb_dev = to(np.stack(rgbs), torch.uint8)

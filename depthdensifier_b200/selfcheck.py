@@ -16,7 +16,7 @@ from .synthetic import SceneConfig, make_scene
 
 
 def multi_gpu_check(dev, rank: int, world: int, n_views: int = 24, width: int = 320, height: int = 240, k: int = 4,
-                    voxel: float = 0.02, steps: int = 2, verbose: bool = False) -> dict:
+                    voxel: float = 0.02, steps: int = 2, verbose: bool = False, dedup: bool = False) -> dict:
     """Every rank calls this.  Rank 0 returns {"passed": bool, "path": "peer" | "collective", ...}; the other
     ranks the same dict with their local view of ``path``."""
     V, W, H = n_views, width, height
@@ -35,7 +35,7 @@ def multi_gpu_check(dev, rank: int, world: int, n_views: int = 24, width: int = 
                 "votes": res.votes.cpu().numpy(), "refined": res.refined.cpu().numpy(), "n": int(res.counts[0])}
 
     lo, hi = shard_bounds(V, world)[rank]
-    sd = ShardedDensifier(DensifyConfig(voxel=voxel), dev, rank, world, V, lo, hi, sc.cam_from_world, sc.intrinsics, nbr, H, W)
+    sd = ShardedDensifier(DensifyConfig(voxel=voxel, dedup_sparse=dedup), dev, rank, world, V, lo, hi, sc.cam_from_world, sc.intrinsics, nbr, H, W)
     path = "peer" if sd.peer is not None else "collective"
     dev_in = inputs(lo, hi, lambda t: t.to(dev).contiguous())
     mine = None
@@ -43,10 +43,10 @@ def multi_gpu_check(dev, rank: int, world: int, n_views: int = 24, width: int = 
         mine = collect(sd.run(*dev_in))
     gathered = [None] * world
     dist.gather_object(mine, gathered if rank == 0 else None, dst=0)
-    report = {"passed": True, "path": path, "ranks": world, "views": V, "size": [W, H], "steps": steps, "different": []}
+    report = {"passed": True, "path": path, "ranks": world, "views": V, "size": [W, H], "steps": steps, "dedup_sparse": dedup, "different": []}
     one = None
     if rank == 0:
-        sd1 = ShardedDensifier(DensifyConfig(voxel=voxel), dev, 0, 1, V, 0, V, sc.cam_from_world, sc.intrinsics, nbr, H, W)
+        sd1 = ShardedDensifier(DensifyConfig(voxel=voxel, dedup_sparse=dedup), dev, 0, 1, V, 0, V, sc.cam_from_world, sc.intrinsics, nbr, H, W)
         one = collect(sd1.run(*inputs(0, V, lambda t: t.to(dev).contiguous())))
         for name in ("refined", "votes", "keys", "count", "rgb", "xyz"):
             cat = np.concatenate([g[name] for g in gathered])

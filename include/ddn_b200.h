@@ -310,6 +310,11 @@ DDN_API int ddn_fuse_begin_grid(const ddn_fuse_session* s, const ddn_voxel_grid*
 /* Stand-alone mark pass for points that did not come out of ddn_backproject_filter(mark = s). */
 DDN_API int ddn_fuse_mark_points(const ddn_fuse_session* s, int64_t n_points, const float* xyz, const uint8_t* votes,
                          int32_t vote_threshold, void* stream);
+/* N5, sparse-cloud merge with de-duplication (the reference only concatenates,
+ * scripts/test.py:353-359): clears the occupancy of every cell that holds one of the given points (xyz [N,3]
+ * f32, e.g. the COLMAP sparse cloud), so no dense voxel is created there and the points that fell into it do
+ * not participate.  Call between the mark and ddn_fuse_finish*. */
+DDN_API int ddn_fuse_unmark_points(const ddn_fuse_session* s, int64_t n_points, const float* xyz, void* stream);
 /* Rank + accumulate + finalise of the marked points (same xyz / votes / threshold as the mark).  Outputs as
  * ddn_voxel_fuse with capacity cap_out voxels; accum: scratch of cap_out * 40 bytes, 16-byte aligned. */
 DDN_API int ddn_fuse_finish(const ddn_fuse_session* s, int64_t n_points, int64_t row_len, const float* xyz,
@@ -328,12 +333,15 @@ DDN_API int ddn_fuse_finish_partial(const ddn_fuse_session* s, int64_t n_points,
  * n_ranks contiguous ranges balancing the global record count (each computes the same cuts from the summed
  * prefixes); this rank ORs the occupancy of its range over all ranks, ranks it, pulls its share of every
  * rank's records and adds them, and finalises.  plan: device scratch [64] i64 (out: [0],[1] = tile range,
- * [2] = records received); prefix_scratch: device [(cap_units / 256 + 2) * n_ranks] u32.  Outputs as
- * ddn_fuse_finish.  The rank-ordered concatenation of the outputs is globally key-sorted. */
+ * [2] = records received); prefix_scratch: device [(cap_units / 256 + 2) * n_ranks] u32.  drop_xyz [n_drop,3] f32
+ * (optional, n_drop = 0: none): N5 at the owner - the cells of these points (ALL ranks' sparse points) leave the
+ * merged occupancy before it is ranked.  Outputs as ddn_fuse_finish.  The rank-ordered concatenation of the
+ * outputs is globally key-sorted. */
 DDN_API int ddn_fuse_merge_peers(const ddn_fuse_session* s, int32_t rank, int32_t n_ranks, const void* const* peer_units_host,
                          const void* const* peer_records_host, const void* const* peer_tile_prefix_host, int64_t* plan,
-                         uint32_t* prefix_scratch, uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb,
-                         int32_t* out_count, int64_t cap_out, void* accum, int64_t accum_bytes, void* stream);
+                         uint32_t* prefix_scratch, const float* drop_xyz, int64_t n_drop, uint64_t* out_keys,
+                         float* out_xyz, uint8_t* out_rgb, int32_t* out_count, int64_t cap_out, void* accum,
+                         int64_t accum_bytes, void* stream);
 
 /* Stand-alone pieces of stage 4 (used by the multi-GPU path and by tests). */
 DDN_API int ddn_voxel_keys(const ddn_voxel_grid* grid_host, int64_t n_points, const float* xyz,

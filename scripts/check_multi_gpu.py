@@ -26,7 +26,7 @@ def main():
     dev = torch.device("cuda", local)
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     dist.init_process_group("nccl", device_id=dev)
-    reports = [multi_gpu_check(dev, rank, world), multi_gpu_check(dev, rank, world, n_views=29, width=203, height=131, k=3, voxel=0.03)]
+    reports = [multi_gpu_check(dev, rank, world), multi_gpu_check(dev, rank, world, n_views=29, width=203, height=131, k=3, voxel=0.03, dedup=True)]
     if rank == 0:
         print(json.dumps({"multi_gpu_check": reports}))
     dist.barrier()

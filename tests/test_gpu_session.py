@@ -192,3 +192,35 @@ def test_merge_peers_virtual_ranks(lib_built, R):
     cat = [torch.cat([o[i] for o in outs]) for i in range(4)]
     assert torch.equal(cat[0], one[0]) and torch.equal(cat[1], one[1]) and torch.equal(cat[2], one[2]) and torch.equal(cat[3], one[3])
     assert bool((cat[0][1:] > cat[0][:-1]).all())
+
+
+def test_sparse_dedup_n5(lib_built):
+    """N5: with dedup_sparse the fused cloud is the oracle's voxel fusion minus the voxels whose key holds a sparse
+    point (oracle/restatement.py:merge_sparse, dedup=True); everything that remains is bit-identical."""
+    from depthdensifier_b200.engine import DensifyConfig, DensifyEngine
+    from oracle import restatement as R
+
+    sc, nbr, thr = _scene_inputs(V=6, W=160, H=120)
+    args = (sc.mono_depth.cuda(), sc.normal.cuda(), sc.mask.cuda(), sc.rgb.cuda(), sc.cam_from_world.cuda(), sc.intrinsics.cuda(),
+            sc.sparse_xyz.cuda(), sc.sparse_offsets.cuda(), _cuda(nbr.astype(np.int32)))
+    voxel = 0.03
+    plain = DensifyEngine(DensifyConfig(voxel=voxel)).run(*args)
+    dedup = DensifyEngine(DensifyConfig(voxel=voxel, dedup_sparse=True)).run(*args)
+    grid = plain.host_grid()
+    assert list(grid.origin) == list(dedup.host_grid().origin)
+    origin = np.array(list(grid.origin), np.float32)
+    keys = plain.voxel_keys.cpu().numpy().view(np.uint64)
+    dense_xyz = plain.voxel_xyz.cpu().numpy()
+    merged_xyz, merged_rgb = R.merge_sparse(sc.sparse_xyz.numpy(), np.zeros((len(sc.sparse_xyz), 3), np.uint8), dense_xyz,
+                                            plain.voxel_rgb.cpu().numpy(), dense_keys=keys, voxel=voxel, origin=origin, dedup=True)
+    n_sparse = len(sc.sparse_xyz)
+    s32 = sc.sparse_xyz.numpy().astype(np.float32)
+    k3 = np.floor((s32 - origin) / np.float32(voxel)).astype(np.int64)
+    sk = (k3[:, 0] | (k3[:, 1] << 21) | (k3[:, 2] << 42)).astype(np.uint64)[((k3 >= 0) & (k3 < (1 << 21))).all(1)]
+    keep = ~np.isin(keys, sk)
+    assert 0 < keep.sum() < len(keys)  # the sparse points sit on the surface: some dense voxels must go
+    assert np.array_equal(dedup.voxel_keys.cpu().numpy().view(np.uint64), keys[keep])
+    assert np.array_equal(dedup.voxel_xyz.cpu().numpy(), dense_xyz[keep])
+    assert np.array_equal(dedup.voxel_rgb.cpu().numpy(), plain.voxel_rgb.cpu().numpy()[keep])
+    assert np.array_equal(dedup.voxel_count.cpu().numpy(), plain.voxel_count.cpu().numpy()[keep])
+    assert np.array_equal(merged_xyz[n_sparse:], dense_xyz[keep].astype(np.float64)) and len(merged_rgb) == len(merged_xyz)
