@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(kFilterThreads, kBilinear ? 3 : DDN_K4_MINBLOC
         uint64_t left = __shfl_up_sync(0xffffffffu, kLayout == 1 ? cell[kFilterPX - 1] : cell[j], 1);
         if (lane == 0) left = kNoCell;
         if (kLayout == 1 && j > 0) left = cell[j - 1];
-        if (cell[j] != kNoCell && cell[j] != left) set_cell_bit(p.mark.units, p.mark.dirty, cell[j]);
+        if (cell[j] != kNoCell && cell[j] != left) set_cell_bit(p.mark.units, p.mark.dirty, cell[j], left);
       }
       mine = __reduce_add_sync(0xffffffffu, mine);
       if (lane == 0 && mine) atomicAdd(&s_marked, mine);

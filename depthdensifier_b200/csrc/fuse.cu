@@ -182,7 +182,7 @@ mark_points_kernel(FuseDev f, int64_t n, const float* __restrict__ xyz, const ui
   for (int j = 0; j < kMarkPX; ++j) {
     if (cell[j] != kNoCell) {
       ++mine;
-      if (cell[j] != prev) set_cell_bit(f.units, f.dirty, cell[j]);
+      if (cell[j] != prev) set_cell_bit(f.units, f.dirty, cell[j], prev);
     }
     prev = cell[j];
   }

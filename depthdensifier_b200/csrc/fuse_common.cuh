@@ -113,15 +113,19 @@ __device__ __forceinline__ uint64_t cell_of_point(const GridDev& g, float rv, fl
   return (uint64_t)kx + (uint64_t)g.nx * ((uint64_t)ky + (uint64_t)g.ny * (uint64_t)kz);
 }
 
-// Sets the occupancy bit of `cell`.  `dirty` (optional): one byte per scan tile, set when a tile receives
-// its first bit - the rank passes and the clean-up then only touch the tiles a step has actually used.
-__device__ __forceinline__ void set_cell_bit(uint32_t* __restrict__ units, uint8_t* __restrict__ dirty, uint64_t cell) {
+// Sets the occupancy bit of `cell`.  `dirty` (optional): one byte per scan tile, set when a tile receives a
+// bit - the rank passes and the clean-up then only touch the tiles a step has actually used.  The flag is a
+// plain store, issued only when the cell lies in another scan tile than `left` (the cell the caller marked just
+// before, kNoCell if none): consecutive pixels stay in one tile, so the flag costs next to nothing.
+__device__ __forceinline__ uint32_t unit_of_cell(uint64_t cell) { return (uint32_t)(cell >> 5) / 3u; }
+__device__ __forceinline__ void set_cell_bit(uint32_t* __restrict__ units, uint8_t* __restrict__ dirty, uint64_t cell,
+                                             uint64_t left = kNoCell) {
   const uint32_t w32 = (uint32_t)(cell >> 5);  // word index in a plain bitmap
   const uint32_t unit = w32 / 3u;
   atomicOr(units + (size_t)unit * 4 + (w32 - unit * 3u), 1u << (cell & 31));
   if (dirty != nullptr) {
-    uint8_t* d = dirty + unit / (uint32_t)kTileUnits;
-    if (*reinterpret_cast<volatile uint8_t*>(d) == 0) *reinterpret_cast<volatile uint8_t*>(d) = 1;
+    const uint32_t tile = unit / (uint32_t)kTileUnits;
+    if (left == kNoCell || unit_of_cell(left) / (uint32_t)kTileUnits != tile) dirty[tile] = 1;
   }
 }
 

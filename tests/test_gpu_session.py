@@ -107,7 +107,8 @@ def test_k4_layouts_and_fused_mark(lib_built, stride, sample_mode):
     ref = None
     for layout in (None, 0, 1):
         sess = ops.FuseSession("cuda", max_cells=1 << 28)
-        sess.begin([bbox], 0.02)
+        sess.begin([bbox], 0.05)
+        assert sess.grid_state().status == 0
         if layout is None:
             sess.mark_points(flat[0], flat[2], thr)
         else:
