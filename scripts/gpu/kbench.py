@@ -70,6 +70,14 @@ def main():
             k4(layout, mark=sess)
 
         out[f"begin+k4_l{layout}_mark"] = timeit(marked, reps)
+    sess_nd = ops.FuseSession(dev, 1 << 33, dirty=False)
+
+    def marked_nd():
+        sess_nd.begin([box], VOXEL)
+        k4(0, mark=sess_nd)
+
+    out["begin+k4_l0_mark_nodirty"] = timeit(marked_nd, reps)
+    out["begin_nodirty"] = timeit(lambda: sess_nd.begin([box], VOXEL), reps)
     out["begin"] = timeit(lambda: sess.begin([box], VOXEL), reps)
     flat = (xyz.view(-1, 3), sc.rgb.view(-1, 3), votes.view(-1))
 
@@ -89,6 +97,9 @@ def main():
     sess.begin([box], VOXEL)
     k4(0, mark=sess)
     out["finish_only(rank+accumulate+finalize)"] = timeit(lambda: ops.fuse_finish(sess, *flat, thr, row_len=W, out=outs), reps)
+    sess_nd.begin([box], VOXEL)
+    k4(0, mark=sess_nd)
+    out["finish_only_nodirty"] = timeit(lambda: ops.fuse_finish(sess_nd, *flat, thr, row_len=W, out=outs), reps)
     out["counts"] = sess.counts.cpu().tolist()
     print(json.dumps({k: (round(v, 4) if isinstance(v, float) else v) for k, v in out.items()}))
 
