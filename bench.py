@@ -38,6 +38,7 @@ WORKLOADS = {
     "cfg4": (1000, 1600, 1200, 10, 4096, "BASELINE configs[3]: 1000 views at 1600x1200, K=10, 1 cm voxels (use --scaling strong on 8 GPUs)"),
     "cfg5": (300, 3840, 2160, 8, 4096, "BASELINE configs[4]: 300 views at 3840x2160 (4K), K=8 assumed, 1 cm voxels (--scaling strong, 8 GPUs)"),
     "cfg5_slice": (24, 3840, 2160, 8, 4096, "24 of the 300 4K views of BASELINE configs[4] on one GPU (shape coverage, not a BASELINE config)"),
+    "cfg3_25": (25, 1920, 1080, 8, 4096, "one rank's share of BASELINE configs[2] on 8 GPUs (25 of 200 views; kernel timing only)"),
     "small": (12, 320, 240, 4, 1024, "smoke-sized scene (not a BASELINE config)"),
 }
 VOXEL = 0.01

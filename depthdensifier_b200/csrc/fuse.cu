@@ -278,8 +278,9 @@ tile_count_kernel(const GridDev* __restrict__ gp, const uint4* __restrict__ unit
   }
 }
 
-// exclusive scan of the tile sums in place (one CTA), total -> counts[1] and tile_sums[tiles].
-// n_from_plan: the number of entries is plan[1] - plan[0] (merge over a device-side tile range).
+// exclusive scan of the tile sums in place (one CTA, four entries per thread and iteration), total ->
+// counts[1] and tile_sums[tiles].  plan != nullptr: the number of entries is plan[1] - plan[0] (merge over a
+// device-side tile range).
 __global__ void __launch_bounds__(1024)
 tile_scan_kernel(const GridDev* __restrict__ gp, ScanRange range, const long long* __restrict__ plan,
                  uint32_t* __restrict__ tile_sums, unsigned long long* __restrict__ counts) {
@@ -289,10 +290,13 @@ tile_scan_kernel(const GridDev* __restrict__ gp, ScanRange range, const long lon
   if (threadIdx.x == 0) s_carry = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (long long base = 0; base < tiles; base += 1024) {
-    const long long i = base + threadIdx.x;
-    const uint32_t v = i < tiles ? tile_sums[i] : 0u;
-    uint32_t inc = v;
+  for (long long base = 0; base < tiles; base += 4096) {
+    const long long i0 = base + 4 * threadIdx.x;
+    uint32_t v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = i0 + q < tiles ? tile_sums[i0 + q] : 0u;
+    const uint32_t mine = v[0] + v[1] + v[2] + v[3];
+    uint32_t inc = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
@@ -311,8 +315,12 @@ tile_scan_kernel(const GridDev* __restrict__ gp, ScanRange range, const long lon
     }
     __syncthreads();
     const uint32_t carry = s_carry;
-    const uint32_t excl = carry + (warp ? s_warp[warp - 1] : 0u) + inc - v;
-    if (i < tiles) tile_sums[i] = excl;
+    uint32_t excl = carry + (warp ? s_warp[warp - 1] : 0u) + inc - mine;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (i0 + q < tiles) tile_sums[i0 + q] = excl;
+      excl += v[q];
+    }
     __syncthreads();
     if (threadIdx.x == 1023) s_carry = carry + s_warp[31];
     __syncthreads();
@@ -352,11 +360,13 @@ __device__ __forceinline__ void emit_unit_keys(const GridDev& g, uint64_t nxy, l
 }
 
 // Per unit: exclusive rank prefix -> word w of the unit.  Per set bit: canonical key of the cell ->
-// keys[slot].  own_prefix (optional): record index at every ownership-tile boundary, [own_tiles + 1].
+// keys[slot].  own_prefix (optional): record index at every ownership-tile boundary, [own_tiles + 1];
+// own_mask (optional, with own_prefix): which units of every ownership tile are non-empty, 8 words (256 bits)
+// per tile - what lets the owner-side merge of another rank read only those units over NVLink.
 __global__ void __launch_bounds__(kScanThreads)
 unit_prefix_kernel(const GridDev* __restrict__ gp, uint4* __restrict__ units, ScanRange range,
                    const uint32_t* __restrict__ tile_excl, uint64_t* __restrict__ keys, int key_stride, long long cap,
-                   uint32_t* __restrict__ own_prefix) {
+                   uint32_t* __restrict__ own_prefix, uint32_t* __restrict__ own_mask) {
   __shared__ uint32_t s_warp[kScanThreads / 32];
   const GridDev g = *gp;
   const long long n_units = g.n_units;
@@ -376,6 +386,8 @@ unit_prefix_kernel(const GridDev* __restrict__ gp, uint4* __restrict__ units, Sc
       if (own_prefix != nullptr && threadIdx.x <= kOwnPerScanTile && own0 + threadIdx.x <= own_tiles &&
           (threadIdx.x < kOwnPerScanTile || last))
         own_prefix[own0 + threadIdx.x] = carry;
+      if (own_mask != nullptr && threadIdx.x < kOwnPerScanTile * 8 && own0 + threadIdx.x / 8 < own_tiles)
+        own_mask[own0 * 8 + threadIdx.x] = 0u;
       continue;
     }
 #pragma unroll 1
@@ -404,6 +416,10 @@ unit_prefix_kernel(const GridDev* __restrict__ gp, uint4* __restrict__ units, Sc
       if (own_prefix != nullptr && threadIdx.x == 0 && own0 + j <= own_tiles) own_prefix[own0 + j] = carry;
       carry += total;
       if (ui < n_units) units[ui].w = slot;
+      if (own_mask != nullptr) {
+        const uint32_t m = __ballot_sync(0xffffffffu, cnt != 0);
+        if (lane == 0 && own0 + j < own_tiles) own_mask[(own0 + j) * 8 + warp] = m;
+      }
       if (cnt) emit_unit_keys(g, nxy, ui, u, slot, keys, key_stride, cap);
     }
     if (own_prefix != nullptr && threadIdx.x == 0 && last && own0 + kOwnPerScanTile <= own_tiles)
@@ -640,7 +656,7 @@ struct PeerPtrs {
 // cum[t] = sum over ranks of tile_prefix_q[t] is the number of records in tiles [0, t); boundary b is the
 // first t with cum[t] >= total * b / R.  Every rank runs the same search on the same (peer-visible) arrays,
 // so all agree without communicating.  One warp per boundary, one lane per rank per probe.
-__global__ void __launch_bounds__(32 * DDN_MAX_PEERS)
+__global__ void __launch_bounds__(32 * (DDN_MAX_PEERS + 1))
 merge_plan_kernel(const GridDev* __restrict__ gp, PeerPtrs prefix, int rank, int R, long long* __restrict__ plan) {
   __shared__ long long s_bnd[DDN_MAX_PEERS + 1];
   const long long n_own = (gp->n_units + kOwnUnits - 1) / kOwnUnits;
@@ -652,18 +668,21 @@ merge_plan_kernel(const GridDev* __restrict__ gp, PeerPtrs prefix, int rank, int
     for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
     return v;
   };
-  if (warp >= 1 && warp < R) {
+  // warps 1..R-1: the balanced cuts; warp 0: the first tile that holds a record; warp R (or 0 again when R is
+  // DDN_MAX_PEERS): the end of the last one - the empty head and tail of the grid belong to nobody
+  if (warp <= R && warp < DDN_MAX_PEERS + 1) {
     const long long total = cum_at(n_own);
-    const long long target = total * warp / R;
+    const long long target = warp == 0 ? 1 : (warp == R ? total : total * warp / R);
     long long lo = 0, hi = n_own + 1;
     while (lo < hi) {
       const long long mid = (lo + hi) >> 1;
       if (cum_at(mid) < target) lo = mid + 1;
       else hi = mid;
     }
-    if (lane == 0) s_bnd[warp] = min(lo, n_own);
+    lo = min(lo, n_own);
+    if (warp == 0) lo = total > 0 ? max(lo - 1, 0ll) : 0;  // cum[lo] >= 1 > cum[lo - 1]: tile lo - 1 is the first with a record
+    if (lane == 0) s_bnd[warp] = lo;
   }
-  if (threadIdx.x == 0) s_bnd[0] = 0, s_bnd[R] = n_own;
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int b = 1; b <= R; ++b) s_bnd[b] = max(s_bnd[b], s_bnd[b - 1]);  // monotone
@@ -709,7 +728,7 @@ merge_copy_prefix_kernel(PeerPtrs prefix, int R, const long long* __restrict__ p
 // OR of all ranks' occupancy over the owned tiles -> this rank's units (in place: peers only read the units
 // of THEIR ranges), count per tile.  A tile a rank has no record in is not read from that rank.
 __global__ void __launch_bounds__(kOwnUnits)
-merge_or_kernel(FuseDev f, PeerPtrs peer_units, int rank, int R, const long long* __restrict__ plan,
+merge_or_kernel(FuseDev f, PeerPtrs peer_units, PeerPtrs peer_mask, int rank, int R, const long long* __restrict__ plan,
                 const uint32_t* __restrict__ prefix_local, long long stride, uint32_t* __restrict__ tile_sums) {
   __shared__ int s_warp[kScanThreads / 32];
   const long long n_units = f.grid->n_units;
@@ -721,13 +740,16 @@ merge_or_kernel(FuseDev f, PeerPtrs peer_units, int rank, int R, const long long
     for (int q = 0; q < R; ++q) {
       const uint32_t* pl = prefix_local + q * stride + (t - t0);
       if (pl[1] == pl[0]) continue;  // CTA-uniform
-      if (ui < n_units) {
+      // only the units that rank marked non-empty are read (one mask word per warp: 32 units)
+      const uint32_t mask = __ldcv(reinterpret_cast<const uint32_t*>(peer_mask.p[q]) + t * 8 + (threadIdx.x >> 5));
+      if (ui < n_units && ((mask >> (threadIdx.x & 31)) & 1u)) {
         const uint4 u = q == rank ? my_units[ui] : __ldcv(reinterpret_cast<const uint4*>(peer_units.p[q]) + ui);
         m.x |= u.x, m.y |= u.y, m.z |= u.z;
       }
     }
     const int total = block_sum_256(popc3(m), s_warp);
-    // an untouched tile stays untouched; a touched one gets the merged bits (its prefix word follows)
+    // an untouched tile stays untouched; a touched one gets the merged bits (its prefix word follows).  Units this
+    // rank had not marked itself may hold anything the clean-up left (zeros), units it had are overwritten.
     if (ui < n_units && total > 0) my_units[ui] = m;
     if (threadIdx.x == 0) {
       tile_sums[t - t0] = (uint32_t)total;
@@ -856,7 +878,7 @@ static int launch_mark_points(const ddn_fuse_session* s, int64_t n, const float*
 // rank passes over `range` (whole device grid when range.n_tiles < 0): tile counts -> scan -> accumulators
 // cleared -> unit prefixes + keys
 static int launch_rank(const ddn_fuse_session* s, ScanRange range, uint64_t* keys, int key_stride, unsigned long long* zero_base,
-                       int zero_stride, long long cap, uint32_t* own_prefix, cudaStream_t st) {
+                       int zero_stride, long long cap, uint32_t* own_prefix, uint32_t* own_mask, cudaStream_t st) {
   const GridDev* gp = reinterpret_cast<const GridDev*>(s->grid);
   uint4* units = reinterpret_cast<uint4*>(s->units);
   unsigned long long* counts = reinterpret_cast<unsigned long long*>(s->counts);
@@ -868,7 +890,7 @@ static int launch_rank(const ddn_fuse_session* s, ScanRange range, uint64_t* key
   DDN_TRY(after_launch("tile_scan_kernel"));
   zero_accum_kernel<<<kPersistentCtas, 256, 0, st>>>((ulonglong2*)zero_base, counts, zero_stride, cap);
   DDN_TRY(after_launch("zero_accum_kernel"));
-  unit_prefix_kernel<<<ctas, kScanThreads, 0, st>>>(gp, units, range, s->tile_sums, keys, key_stride, cap, own_prefix);
+  unit_prefix_kernel<<<ctas, kScanThreads, 0, st>>>(gp, units, range, s->tile_sums, keys, key_stride, cap, own_prefix, own_mask);
   return after_launch("unit_prefix_kernel");
 }
 
@@ -935,6 +957,7 @@ static int carve_session(const GridDev& g, int64_t n, void* workspace, int64_t w
   s->dirty = nullptr;
   s->tile_sums = reinterpret_cast<uint32_t*>(base + L->tile_sums);
   s->tile_prefix = nullptr;
+  s->tile_mask = nullptr;
   s->counts = counts_out;
   *accum = reinterpret_cast<unsigned long long*>(base + L->accum);
   return DDN_OK;
@@ -993,7 +1016,7 @@ int ddn_voxel_fuse(const ddn_voxel_grid* grid_host, int64_t n_points, int64_t ro
   DDN_TRY(begin_with_grid(&s, g, st));
   DDN_TRY(launch_mark_points(&s, n_points, xyz, votes, vote_threshold, st));
   const long long cap = (long long)std::min<uint64_t>((uint64_t)n_points, L.cells);
-  DDN_TRY(launch_rank(&s, ScanRange{0, -1}, out_keys, 1, accum, kAccWords, cap, nullptr, st));
+  DDN_TRY(launch_rank(&s, ScanRange{0, -1}, out_keys, 1, accum, kAccWords, cap, nullptr, nullptr, st));
   DDN_TRY(launch_accumulate_points(&s, n_points, row_len, xyz, rgb, votes, vote_threshold, accum, kAccWords, cap, st));
   return launch_finalize(&s, accum, out_keys, cap, out_xyz, out_rgb, out_count, st);
 }
@@ -1045,7 +1068,7 @@ int ddn_voxel_partials(const ddn_voxel_grid* grid_host, int64_t n_points, int64_
   DDN_TRY(launch_mark_points(&s, n_points, xyz, votes, vote_threshold, st));
   unsigned long long* rec = (unsigned long long*)records;
   const long long cap = (long long)n_points;
-  DDN_TRY(launch_rank(&s, ScanRange{0, -1}, (uint64_t*)rec, kRecWords, rec, kRecWords, cap, tile_prefix, st));
+  DDN_TRY(launch_rank(&s, ScanRange{0, -1}, (uint64_t*)rec, kRecWords, rec, kRecWords, cap, tile_prefix, nullptr, st));
   return launch_accumulate_points(&s, n_points, row_len, xyz, rgb, votes, vote_threshold, rec + 1, kRecWords, cap, st);
 }
 
@@ -1088,7 +1111,7 @@ int ddn_voxel_merge(const ddn_voxel_grid* grid_host, int64_t n_records, const ui
   mark_records_kernel<<<blocks, 256, 0, st>>>(fuse_dev(&s), n_records, records, cell_begin, cell_end);
   DDN_TRY(after_launch("mark_records_kernel"));
   const long long cap = (long long)std::min<uint64_t>((uint64_t)n_records, L.cells);
-  DDN_TRY(launch_rank(&s, range, out_keys, 1, accum, kAccWords, cap, nullptr, st));
+  DDN_TRY(launch_rank(&s, range, out_keys, 1, accum, kAccWords, cap, nullptr, nullptr, st));
   accumulate_records_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const GridDev*>(s.grid), n_records,
                                                     (const unsigned long long*)records, reinterpret_cast<const uint4*>(s.units),
                                                     cell_begin, cell_end, accum, cap);
@@ -1115,16 +1138,17 @@ int ddn_voxel_keys(const ddn_voxel_grid* grid_host, int64_t n_points, const floa
 
 // ---- fusion session ------------------------------------------------------------------------------
 int ddn_fuse_session_sizes(int64_t max_cells, int64_t* cap_units, int64_t* units_bytes, int64_t* dirty_bytes,
-                           int64_t* tile_sums_bytes, int64_t* tile_prefix_bytes) {
+                           int64_t* tile_sums_bytes, int64_t* tile_prefix_bytes, int64_t* tile_mask_bytes) {
   using namespace ddn;
   DDN_REQUIRE(max_cells > 0 && (uint64_t)max_cells <= kDenseMaxCells, "max_cells must be in (0, 2^35]");
-  DDN_REQUIRE(cap_units && units_bytes && dirty_bytes && tile_sums_bytes && tile_prefix_bytes, "null output");
+  DDN_REQUIRE(cap_units && units_bytes && dirty_bytes && tile_sums_bytes && tile_prefix_bytes && tile_mask_bytes, "null output");
   const int64_t cu = align_up((max_cells + kUnitBits - 1) / kUnitBits, kTileUnits);
   *cap_units = cu;
   *units_bytes = cu * 16;
   *dirty_bytes = align_up(cu / kTileUnits + 1, 256);
   *tile_sums_bytes = align_up((cu / kOwnUnits + 2) * 4, 256);
   *tile_prefix_bytes = align_up((cu / kOwnUnits + 2) * 4, 256);
+  *tile_mask_bytes = align_up((cu / kOwnUnits + 2) * 32, 256);
   return DDN_OK;
 }
 
@@ -1197,7 +1221,7 @@ int ddn_fuse_finish(const ddn_fuse_session* s, int64_t n_points, int64_t row_len
   cudaStream_t st = (cudaStream_t)stream;
   vote_threshold = std::min(vote_threshold, 255);
   unsigned long long* acc = (unsigned long long*)accum;
-  DDN_TRY(launch_rank(s, ScanRange{0, -1}, out_keys, 1, acc, kAccWords, cap_out, nullptr, st));
+  DDN_TRY(launch_rank(s, ScanRange{0, -1}, out_keys, 1, acc, kAccWords, cap_out, nullptr, nullptr, st));
   if (n_points > 0)
     DDN_TRY(launch_accumulate_points(s, n_points, row_len, xyz, rgb, votes, vote_threshold, acc, kAccWords, cap_out, st));
   return launch_finalize(s, acc, out_keys, cap_out, out_xyz, out_rgb, out_count, st);
@@ -1215,31 +1239,36 @@ int ddn_fuse_finish_partial(const ddn_fuse_session* s, int64_t n_points, int64_t
   cudaStream_t st = (cudaStream_t)stream;
   vote_threshold = std::min(vote_threshold, 255);
   unsigned long long* rec = (unsigned long long*)records;
-  DDN_TRY(launch_rank(s, ScanRange{0, -1}, (uint64_t*)rec, kRecWords, rec, kRecWords, cap_records, s->tile_prefix, st));
+  DDN_TRY(launch_rank(s, ScanRange{0, -1}, (uint64_t*)rec, kRecWords, rec, kRecWords, cap_records, s->tile_prefix,
+                      s->tile_prefix != nullptr ? s->tile_mask : nullptr, st));
   if (n_points == 0) return DDN_OK;
   return launch_accumulate_points(s, n_points, row_len, xyz, rgb, votes, vote_threshold, rec + 1, kRecWords, cap_records, st);
 }
 
 int ddn_fuse_merge_peers(const ddn_fuse_session* s, int32_t rank, int32_t n_ranks, const void* const* peer_units_host,
-                         const void* const* peer_records_host, const void* const* peer_tile_prefix_host, int64_t* plan,
-                         uint32_t* prefix_scratch, const float* drop_xyz, int64_t n_drop, uint64_t* out_keys, float* out_xyz,
+                         const void* const* peer_records_host, const void* const* peer_tile_prefix_host,
+                         const void* const* peer_tile_mask_host, int64_t* plan, uint32_t* prefix_scratch,
+                         const float* drop_xyz, int64_t n_drop, uint64_t* out_keys, float* out_xyz,
                          uint8_t* out_rgb, int32_t* out_count, int64_t cap_out, void* accum, int64_t accum_bytes, void* stream) {
   using namespace ddn;
   DDN_REQUIRE(n_drop >= 0 && n_drop < (1ll << 31) - 1024 && (n_drop == 0 || drop_xyz != nullptr), "drop points");
   DDN_TRY(session_check(s));
   DDN_REQUIRE(n_ranks >= 1 && n_ranks <= DDN_MAX_PEERS && rank >= 0 && rank < n_ranks, "rank / n_ranks");
-  DDN_REQUIRE(peer_units_host && peer_records_host && peer_tile_prefix_host && plan && prefix_scratch, "null pointer");
+  DDN_REQUIRE(peer_units_host && peer_records_host && peer_tile_prefix_host && peer_tile_mask_host && plan && prefix_scratch,
+              "null pointer");
   DDN_REQUIRE(cap_out > 0 && cap_out < (1ll << 31), "cap_out");
   DDN_REQUIRE(out_keys && out_xyz && out_rgb && out_count && accum, "null pointer");
   DDN_REQUIRE(accum_bytes >= cap_out * kAccWords * 8 + 16 && (uintptr_t)accum % 16 == 0, "accumulator scratch");
-  PeerPtrs pu, pr, pp;
+  PeerPtrs pu, pr, pp, pm;
   for (int q = 0; q < DDN_MAX_PEERS; ++q) {
     pu.p[q] = q < n_ranks ? peer_units_host[q] : nullptr;
     pr.p[q] = q < n_ranks ? peer_records_host[q] : nullptr;
     pp.p[q] = q < n_ranks ? peer_tile_prefix_host[q] : nullptr;
-    if (q < n_ranks) DDN_REQUIRE(pu.p[q] && pr.p[q] && pp.p[q], "null peer pointer");
+    pm.p[q] = q < n_ranks ? peer_tile_mask_host[q] : nullptr;
+    if (q < n_ranks) DDN_REQUIRE(pu.p[q] && pr.p[q] && pp.p[q] && pm.p[q], "null peer pointer");
   }
-  DDN_REQUIRE(pu.p[rank] == s->units && pp.p[rank] == (const void*)s->tile_prefix, "entry `rank` must be the session's own buffers");
+  DDN_REQUIRE(pu.p[rank] == s->units && pp.p[rank] == (const void*)s->tile_prefix && pm.p[rank] == (const void*)s->tile_mask,
+              "entry `rank` must be the session's own buffers");
   cudaStream_t st = (cudaStream_t)stream;
   const GridDev* gp = reinterpret_cast<const GridDev*>(s->grid);
   const FuseDev f = fuse_dev(s);
@@ -1247,11 +1276,11 @@ int ddn_fuse_merge_peers(const ddn_fuse_session* s, int32_t rank, int32_t n_rank
   long long* planll = reinterpret_cast<long long*>(plan);
   unsigned long long* acc = (unsigned long long*)accum;
   const long long stride = (long long)(s->cap_units / kOwnUnits + 2);
-  merge_plan_kernel<<<1, 32 * DDN_MAX_PEERS, 0, st>>>(gp, pp, rank, n_ranks, planll);
+  merge_plan_kernel<<<1, 32 * (DDN_MAX_PEERS + 1), 0, st>>>(gp, pp, rank, n_ranks, planll);
   DDN_TRY(after_launch("merge_plan_kernel"));
   merge_copy_prefix_kernel<<<kNumSMs, 256, 0, st>>>(pp, n_ranks, planll, prefix_scratch, stride);
   DDN_TRY(after_launch("merge_copy_prefix_kernel"));
-  merge_or_kernel<<<kPersistentCtas, kOwnUnits, 0, st>>>(f, pu, rank, n_ranks, planll, prefix_scratch, stride, s->tile_sums);
+  merge_or_kernel<<<kPersistentCtas, kOwnUnits, 0, st>>>(f, pu, pm, rank, n_ranks, planll, prefix_scratch, stride, s->tile_sums);
   DDN_TRY(after_launch("merge_or_kernel"));
   if (n_drop > 0) {  // N5: cells of the sparse cloud leave the merged occupancy; tile counts again
     unmark_points_kernel<<<(unsigned)((n_drop + 255) / 256), 256, 0, st>>>(f, n_drop, drop_xyz, planll);

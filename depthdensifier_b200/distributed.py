@@ -216,7 +216,7 @@ class ShardedDensifier:
             return
 
         def alloc(name, nbytes):
-            if name in ("units", "tile_prefix"):
+            if name in ("units", "tile_prefix", "tile_mask"):
                 return self.peer.buffer("fuse_" + name, (nbytes,), torch.uint8)[0]
             return None
 
@@ -224,6 +224,7 @@ class ShardedDensifier:
         ptrs = lambda name, shape, dt: [int(v.data_ptr()) for v in self.peer.buffer(name, shape, dt)[2]]
         self._peer_units = ptrs("fuse_units", (self.session.units.numel(),), torch.uint8)
         self._peer_prefix = ptrs("fuse_tile_prefix", (self.session.tile_prefix.numel(),), torch.uint8)
+        self._peer_mask = ptrs("fuse_tile_mask", (self.session.tile_mask.numel(),), torch.uint8)
         self._peer_records = ptrs("records", tuple(self.peer_records_shape), torch.int64)
         self._peer_bbox = ptrs("bbox", (64,), torch.int32)
         self._plan = torch.zeros(64, dtype=torch.int64, device=self.device)
@@ -252,6 +253,11 @@ class ShardedDensifier:
 
     def _interior_range(self) -> tuple[int, int]:
         """Longest run [i0, i1) of own source views whose neighbours are all own views (no halo needed)."""
+        if getattr(self, "_interior", None) is None:
+            self._interior = self._find_interior_range()
+        return self._interior
+
+    def _find_interior_range(self) -> tuple[int, int]:
         local = ((self.plan.nbr_slots < self.n_local)).all(axis=1)
         best, i = (0, 0), 0
         n = self.n_local
@@ -460,7 +466,7 @@ class ShardedDensifier:
         mark("fuse_partials", lambda: self.ops.fuse_finish_partial(sess, *flat, self.thr, rec, row_len=xyz.shape[2]))
         hdl.barrier()  # every rank's units, tile prefix and records are complete
         k, x, c, n, counts = mark("fuse_merge", lambda: self.ops.fuse_merge_peers(
-            sess, self.rank, self.world, self._peer_units, self._peer_records, self._peer_prefix, self._plan,
+            sess, self.rank, self.world, self._peer_units, self._peer_records, self._peer_prefix, self._peer_mask, self._plan,
             self._prefix_scratch, self._cap_merge, out=self._merge_out, drop_xyz=drop))
         return k, x, c, n, counts.clone()
 
@@ -468,8 +474,10 @@ class ShardedDensifier:
         """Neighbour table padded to n_slots rows (build_pair_tables indexes it by global slot)."""
         if self.n_slots == self.n_local:
             return self.nbr_slots
-        pad = torch.full((self.n_slots - self.n_local, self.K), -1, dtype=torch.int32, device=self.device)
-        return torch.cat([self.nbr_slots, pad], 0).contiguous()
+        if getattr(self, "_nbr_padded", None) is None:
+            pad = torch.full((self.n_slots - self.n_local, self.K), -1, dtype=torch.int32, device=self.device)
+            self._nbr_padded = torch.cat([self.nbr_slots, pad], 0).contiguous()
+        return self._nbr_padded
 
     def _fuse_sharded(self, xyz, rgb, votes, grid, mark=None):
         if mark is None:

@@ -268,9 +268,9 @@ class FuseSession:
         if not torch.cuda.is_available():
             raise DDNError("no CUDA device available: depthdensifier_b200 has no CPU fallback")
         self.device = torch.device(device)
-        sizes = [C.c_int64(0) for _ in range(5)]
+        sizes = [C.c_int64(0) for _ in range(6)]
         _lib.check(lib.ddn_fuse_session_sizes(int(max_cells), *[C.byref(x) for x in sizes]))
-        cap_units, units_b, dirty_b, sums_b, prefix_b = (x.value for x in sizes)
+        cap_units, units_b, dirty_b, sums_b, prefix_b, mask_b = (x.value for x in sizes)
         self.max_cells, self.cap_units = int(max_cells), cap_units
         self.n_own_cap = cap_units // 256 + 2
 
@@ -285,11 +285,13 @@ class FuseSession:
         self.dirty = get("dirty", dirty_b) if dirty else None
         self.tile_sums = get("tile_sums", sums_b)
         self.tile_prefix = get("tile_prefix", prefix_b) if tile_prefix else None
+        self.tile_mask = get("tile_mask", mask_b) if tile_prefix else None
         self.grid = torch.zeros(16, dtype=torch.int32, device=self.device)
         self.counts = torch.zeros(2, dtype=torch.int64, device=self.device)
         self.c = _lib.FuseSession(self.grid.data_ptr(), self.units.data_ptr(), cap_units,
                                   self.dirty.data_ptr() if self.dirty is not None else None, self.tile_sums.data_ptr(),
-                                  self.tile_prefix.data_ptr() if self.tile_prefix is not None else None, self.counts.data_ptr())
+                                  self.tile_prefix.data_ptr() if self.tile_prefix is not None else None,
+                                  self.tile_mask.data_ptr() if self.tile_mask is not None else None, self.counts.data_ptr())
         self._accum = None
         with torch.cuda.device(self.device):
             _lib.check(lib.ddn_fuse_session_reset(C.byref(self.c), _stream()))
@@ -382,8 +384,8 @@ def fuse_finish_partial(sess: FuseSession, xyz, rgb, votes, vote_threshold: int,
     return sess.counts
 
 
-def fuse_merge_peers(sess: FuseSession, rank: int, world: int, peer_units, peer_records, peer_tile_prefix, plan, prefix_scratch,
-                     cap_out: int, out=None, drop_xyz=None):
+def fuse_merge_peers(sess: FuseSession, rank: int, world: int, peer_units, peer_records, peer_tile_prefix, peer_tile_mask, plan,
+                     prefix_scratch, cap_out: int, out=None, drop_xyz=None):
     """Owner-side exchange + merge over peer memory.  ``peer_*``: per rank, the device address of that rank's
     units / records / tile prefix as mapped into this process.  ``drop_xyz`` [n,3] f32: N5, the sparse points of
     ALL ranks whose cells are removed from the merged occupancy.  Returns keys, xyz, rgb, count, counts."""
@@ -394,7 +396,7 @@ def fuse_merge_peers(sess: FuseSession, rank: int, world: int, peer_units, peer_
     arr = lambda ptrs: (C.c_void_p * world)(*[int(v) for v in ptrs])
     with torch.cuda.device(dev):
         _lib.check(lib.ddn_fuse_merge_peers(C.byref(sess.c), int(rank), int(world), arr(peer_units), arr(peer_records),
-                                            arr(peer_tile_prefix), _p(plan), _p(prefix_scratch), _p(drop_xyz),
+                                            arr(peer_tile_prefix), arr(peer_tile_mask), _p(plan), _p(prefix_scratch), _p(drop_xyz),
                                             0 if drop_xyz is None else drop_xyz.shape[0], _p(k), _p(x), _p(c), _p(n), int(cap_out),
                                             _p(acc), acc.numel(), _stream()))
     return k, x, c, n, sess.counts

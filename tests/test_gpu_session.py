@@ -172,20 +172,22 @@ def test_merge_peers_virtual_ranks(lib_built, R):
     assert sum(int(s.counts[0]) for s in sessions) == int(one[4][0])
     pu = [s.units.data_ptr() for s in sessions]
     pp = [s.tile_prefix.data_ptr() for s in sessions]
+    pm = [s.tile_mask.data_ptr() for s in sessions]
     pr = [t.data_ptr() for t in records]
     cap = n
     outs, plans = [], []
     for r in range(R):
         plan = torch.zeros(64, dtype=torch.int64, device="cuda")
         scratch = torch.empty(sessions[r].n_own_cap * R, dtype=torch.int32, device="cuda")
-        k, x, c, m, counts = ops.fuse_merge_peers(sessions[r], r, R, pu, pr, pp, plan, scratch, cap)
+        k, x, c, m, counts = ops.fuse_merge_peers(sessions[r], r, R, pu, pr, pp, pm, plan, scratch, cap)
         mv = int(counts[1])
         outs.append((k[:mv].clone(), x[:mv].clone(), c[:mv].clone(), m[:mv].clone()))
         plans.append(plan.cpu().tolist())
-    # the ranks agree on the cuts, the ranges tile the grid, the shares add up to all records
+    # the ranks agree on the cuts, the ranges are contiguous and cover every tile that holds a record (the empty
+    # head and tail of the grid belong to nobody), the shares add up to all records
     for r in range(R):
         assert plans[r][1] >= plans[r][0] and (r == 0 or plans[r][0] == plans[r - 1][1])
-    assert plans[0][0] == 0 and plans[-1][1] == plans[-1][3]
+    assert 0 <= plans[0][0] and plans[-1][1] <= plans[-1][3]
     assert sum(p[2] for p in plans) == sum(n_local)
     tot = sum(n_local)
     for r in range(R):  # balanced up to one tile's worth of records per rank
