@@ -439,12 +439,10 @@ zero_accum_kernel(ulonglong2* __restrict__ accum2, const unsigned long long* __r
 // slot of `cell` in the key-sorted output, or kNoSlot when its occupancy bit is not set (a cell that
 // ddn_fuse_unmark_points removed: its points do not participate)
 constexpr uint32_t kNoSlot = 0xffffffffu;
-__device__ __forceinline__ uint32_t slot_of_cell(uint64_t cell, const uint4* __restrict__ units) {
+__device__ __forceinline__ uint32_t slot_from_unit(uint64_t cell, const uint4& u) {
   const uint32_t w32 = (uint32_t)(cell >> 5);
-  const uint32_t unit = w32 / 3u;
-  const int wi = (int)(w32 - unit * 3u);
+  const int wi = (int)(w32 - (w32 / 3u) * 3u);
   const uint32_t below = (1u << (cell & 31)) - 1u;
-  const uint4 u = __ldg(units + unit);
   const uint32_t word = wi == 0 ? u.x : (wi == 1 ? u.y : u.z);
   if (((word >> (cell & 31)) & 1u) == 0u) return kNoSlot;
   uint32_t s = u.w;
@@ -452,6 +450,9 @@ __device__ __forceinline__ uint32_t slot_of_cell(uint64_t cell, const uint4* __r
   s += wi > 0 ? __popc(u.y & (wi > 1 ? 0xffffffffu : below)) : 0;
   s += wi > 1 ? __popc(u.z & below) : 0;
   return s;
+}
+__device__ __forceinline__ uint32_t slot_of_cell(uint64_t cell, const uint4* __restrict__ units) {
+  return slot_from_unit(cell, __ldg(units + unit_of_cell(cell)));
 }
 
 // accumulate: one point per lane, aggregated ACROSS THE WARP before touching memory.  With a row length
@@ -529,6 +530,26 @@ accumulate_points_kernel(const GridDev* __restrict__ gp, int64_t n, int row_len,
     return r;
   };
   In nxt = load_tile(t_begin);
+#ifndef DDN_ACC_NODEFER
+  bool pend = false;
+  uint4 pend_unit = make_uint4(0, 0, 0, 0);
+  uint64_t pend_cell = 0;
+  int psx = 0, psy = 0, psz = 0;
+  uint32_t psrg = 0, psb = 0, ppop = 0;
+  auto flush = [&]() {
+    if (pend) {
+      const uint32_t slot = slot_from_unit(pend_cell, pend_unit);
+      if ((long long)slot < cap) {
+        unsigned long long* a = accum + (size_t)slot * stride;
+        atomicAdd(a + 0, (unsigned long long)(long long)psx);
+        atomicAdd(a + 1, (unsigned long long)(long long)psy);
+        atomicAdd(a + 2, (unsigned long long)(long long)psz);
+        atomicAdd(a + 3, ((unsigned long long)(psrg >> 16) << 32) | (psrg & 0xffffu));
+        atomicAdd(a + 4, ((unsigned long long)psb << 32) | ppop);
+      }
+    }
+  };
+#endif
 #pragma unroll 1
   for (uint32_t t = t_begin; t < t_end; ++t) {
     const In cur = nxt;
@@ -574,6 +595,7 @@ accumulate_points_kernel(const GridDev* __restrict__ gp, int64_t n, int row_len,
       sb = __reduce_add_sync(peers, bb);
     }
 #endif
+#ifdef DDN_ACC_NODEFER
     if (leader) {
       const uint32_t slot = slot_of_cell(cell, units);
       if ((long long)slot < cap) {
@@ -586,6 +608,19 @@ accumulate_points_kernel(const GridDev* __restrict__ gp, int64_t n, int row_len,
       }
     }
   }
+#else
+    // The atomics of a tile are issued one iteration LATER: the leader only requests its unit here, and the
+    // 16-byte gather has the whole next tile (its cell arithmetic, MATCH and shuffle walk) to arrive.
+    flush();
+    pend = leader;
+    if (leader) {
+      pend_unit = __ldg(units + unit_of_cell(cell));
+      pend_cell = cell;
+      psx = sx, psy = sy, psz = sz, psrg = srg, psb = sb, ppop = (uint32_t)__popc(peers);
+    }
+  }
+  flush();
+#endif
 }
 
 __global__ void __launch_bounds__(256)
@@ -714,14 +749,19 @@ merge_plan_kernel(const GridDev* __restrict__ gp, PeerPtrs prefix, int rank, int
   }
 }
 
-// local copy of every rank's tile prefix over the owned range [t0, t1]: local[q * stride + (t - t0)]
+// local copy of every rank's tile prefix over the owned range [t0, t1]: local[q * stride + (t - t0)], and their
+// sum over the ranks in row R (one compare then tells whether anybody has a record in a tile)
 __global__ void __launch_bounds__(256)
 merge_copy_prefix_kernel(PeerPtrs prefix, int R, const long long* __restrict__ plan, uint32_t* __restrict__ local, long long stride) {
   const long long t0 = plan[0], n = plan[1] - t0 + 1;
-  for (int q = 0; q < R; ++q) {
-    const uint32_t* pq = reinterpret_cast<const uint32_t*>(prefix.p[q]);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-      local[q * stride + i] = __ldcv(pq + t0 + i);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    uint32_t sum = 0;
+    for (int q = 0; q < R; ++q) {
+      const uint32_t v = __ldcv(reinterpret_cast<const uint32_t*>(prefix.p[q]) + t0 + i);
+      local[q * stride + i] = v;
+      sum += v;
+    }
+    local[(long long)R * stride + i] = sum;
   }
 }
 
@@ -734,7 +774,12 @@ merge_or_kernel(FuseDev f, PeerPtrs peer_units, PeerPtrs peer_mask, int rank, in
   const long long n_units = f.grid->n_units;
   const long long t0 = plan[0], t1 = plan[1];
   uint4* my_units = reinterpret_cast<uint4*>(f.units);
+  const uint32_t* cum = prefix_local + (long long)R * stride;
   for (long long t = t0 + blockIdx.x; t < t1; t += gridDim.x) {
+    if (cum[t - t0 + 1] == cum[t - t0]) {  // CTA-uniform: nobody has a record here
+      if (threadIdx.x == 0) tile_sums[t - t0] = 0u;
+      continue;
+    }
     const long long ui = t * kOwnUnits + threadIdx.x;
     uint4 m = make_uint4(0, 0, 0, 0);
     for (int q = 0; q < R; ++q) {

@@ -335,7 +335,7 @@ DDN_API int ddn_fuse_finish_partial(const ddn_fuse_session* s, int64_t n_points,
  * tiles that hold records into n_ranks contiguous ranges balancing the global record count (each computes the
  * same cuts from the summed prefixes); this rank ORs the occupancy of its range over all ranks (reading only the
  * units their masks name), ranks it, pulls its share of every rank's records and adds them, and finalises.  plan: device scratch [64] i64 (out: [0],[1] = tile range,
- * [2] = records received); prefix_scratch: device [(cap_units / 256 + 2) * n_ranks] u32.  drop_xyz [n_drop,3] f32
+ * [2] = records received); prefix_scratch: device [(cap_units / 256 + 2) * (n_ranks + 1)] u32.  drop_xyz [n_drop,3] f32
  * (optional, n_drop = 0: none): N5 at the owner - the cells of these points (ALL ranks' sparse points) leave the
  * merged occupancy before it is ranked.  Outputs as ddn_fuse_finish.  The rank-ordered concatenation of the
  * outputs is globally key-sorted. */
