@@ -530,7 +530,7 @@ accumulate_points_kernel(const GridDev* __restrict__ gp, int64_t n, int row_len,
     return r;
   };
   In nxt = load_tile(t_begin);
-#ifndef DDN_ACC_NODEFER
+#ifdef DDN_ACC_DEFER
   bool pend = false;
   uint4 pend_unit = make_uint4(0, 0, 0, 0);
   uint64_t pend_cell = 0;
@@ -595,7 +595,7 @@ accumulate_points_kernel(const GridDev* __restrict__ gp, int64_t n, int row_len,
       sb = __reduce_add_sync(peers, bb);
     }
 #endif
-#ifdef DDN_ACC_NODEFER
+#ifndef DDN_ACC_DEFER
     if (leader) {
       const uint32_t slot = slot_of_cell(cell, units);
       if ((long long)slot < cap) {
@@ -609,8 +609,9 @@ accumulate_points_kernel(const GridDev* __restrict__ gp, int64_t n, int row_len,
     }
   }
 #else
-    // The atomics of a tile are issued one iteration LATER: the leader only requests its unit here, and the
-    // 16-byte gather has the whole next tile (its cell arithmetic, MATCH and shuffle walk) to arrive.
+    // -DDDN_ACC_DEFER: the atomics of a tile are issued one iteration LATER - the leader only requests its unit
+    // here, and the 16-byte gather has the whole next tile to arrive.  Measured at cfg 2: 56 registers instead of
+    // 38 cost more occupancy than the hidden latency returns (rank + accumulate + finalise 3.62 vs 3.45 ms).
     flush();
     pend = leader;
     if (leader) {

@@ -1,0 +1,15 @@
+#!/bin/bash
+# 8 GPUs: default bench (weak cfg2 + multi-GPU check + strong cfg3 block)
+mkdir -p gpurun_out
+timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/bench_r02g_g8.json 2> gpurun_out/bench_r02g_g8.err; echo "bench g8 rc=$?"
+tail -3 gpurun_out/bench_r02g_g8.err | cut -c1-300
+python - <<'PY'
+import json
+try:
+    d=json.loads([l for l in open("gpurun_out/bench_r02g_g8.json") if l.startswith("{")][-1])
+    print("g8 weak", round(d["ms_per_step"],3), d["path"], {k:round(v,3) for k,v in d["stages_ms"].items()})
+    print("check", d["multi_gpu_check"] and (d["multi_gpu_check"]["passed"], d["multi_gpu_check"]["path"]))
+    s=d["strong"]; print("strong", round(s["ms_per_step"],3), {k:round(v,3) for k,v in s["stages_ms"].items()})
+    print("e2e", d["e2e"] and (round(d["e2e"]["ms_per_step"],2), round(d["e2e"]["ms_per_step_all_copied"],2)))
+except Exception as e: print("ERR", e)
+PY
