@@ -203,7 +203,7 @@ class Ctx:
 
 
 def run_workload(ctx: Ctx, workload: str, scaling: str, steps: int, warmup: int, e2e: bool, sample_mode: str = "nearest",
-                 pixel_layout: int = 0, clocks: bool = True) -> dict:
+                 pixel_layout: int = 0, clocks: bool = True, profile_kernels: bool = False) -> dict:
     """Device-resident timing (+ optionally the end-to-end host path) of one workload on all ranks."""
     from depthdensifier_b200 import _lib, ops
     from depthdensifier_b200.distributed import ShardedDensifier
@@ -274,6 +274,22 @@ def run_workload(ctx: Ctx, workload: str, scaling: str, steps: int, warmup: int,
         "views_local": hi - lo, "limits": {"gather_offset_pixels": f"{sharded.n_slots * H * W} of 2^32 per rank",
                                            "points_per_rank": f"{(hi - lo) * H * W} of 2^31"},
     }
+    if profile_kernels:
+        # two extra, untimed steps with the library's per-launch events on: the kernels of stage 4 (rank passes,
+        # accumulate, and with peers the owner-side merge), averaged per step; max over ranks
+        ctx.barrier()
+        _lib.profile(True)
+        for _ in range(2):
+            sharded.run(*dev_inputs)
+        rows = _lib.profile_report()
+        _lib.profile(False)
+        names = []
+        for name, _ms in rows:
+            if name not in names:
+                names.append(name)
+        agg = {n: sum(ms for nm, ms in rows[1:] if nm == n) / 2 for n in names}
+        agg[rows[0][0] + " (first launch of a step: includes everything before it)"] = agg.pop(rows[0][0]) if rows else 0.0
+        out["stage4_kernels_ms"] = {n: round(ctx.allreduce(v, "max"), 4) for n, v in agg.items()}
     if e2e:
         del res
         torch.cuda.empty_cache()
@@ -404,9 +420,11 @@ def main():
     # ---- strong scaling block: cfg3 (200 views at 1920x1080, K=8) split over the ranks, at every N ----
     strong = None
     if not args.no_strong and args.workload == "cfg2" and args.scaling == "weak":
-        sr = run_workload(ctx, "cfg3", "strong", steps=max(5, min(args.steps, 10)), warmup=3, e2e=False, clocks=False)
+        sr = run_workload(ctx, "cfg3", "strong", steps=max(5, min(args.steps, 10)), warmup=3, e2e=False, clocks=False,
+                          profile_kernels=True)
         strong = {"workload": "cfg3", "scaling": "strong", "ms_per_step": sr["ms_per_step"], "value": sr["value"], "unit": UNIT,
-                  "steps": sr["steps"], "stages_ms": sr["stages_ms"], "path": sr["path"], "workload_stats": sr["stats"],
+                  "steps": sr["steps"], "stages_ms": sr["stages_ms"], "stage4_kernels_ms": sr.get("stage4_kernels_ms"),
+                  "path": sr["path"], "workload_stats": sr["stats"],
                   "config": workload_config("cfg3", world, "strong"),
                   "note": "total work fixed (200 views), divide the n_gpus=1 ms_per_step by this one for the speed-up"}
 

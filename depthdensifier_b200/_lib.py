@@ -89,6 +89,8 @@ SYMBOLS = {
     "ddn_version": (C.c_int, []),
     "ddn_last_error_string": (C.c_char_p, []),
     "ddn_launch_count": (C.c_int64, []),
+    "ddn_profile_enable": (None, [C.c_int]),
+    "ddn_profile_report": (C.c_int, [C.c_char_p, C.c_int64]),
     "ddn_align_config_default": (None, [C.POINTER(AlignConfig)]),
     "ddn_filter_config_default": (None, [C.POINTER(FilterConfig)]),
     "ddn_align_workspace_bytes": (C.c_int, [_i64, _i64, C.POINTER(_i64)]),
@@ -132,6 +134,7 @@ SYMBOLS = {
     ),
     "ddn_voxel_keys": (C.c_int, [C.POINTER(VoxelGrid), _i64, _vp, _vp, _vp]),
     "ddn_fuse_session_sizes": (C.c_int, [_i64] + [C.POINTER(_i64)] * 6),
+    "ddn_fuse_merge_scratch_bytes": (C.c_int, [_i64, _i32, C.POINTER(_i64)]),
     "ddn_fuse_session_reset": (C.c_int, [C.POINTER(FuseSession), _vp]),
     "ddn_fuse_begin": (C.c_int, [C.POINTER(FuseSession), C.POINTER(_vp), _i32, C.c_float, _vp]),
     "ddn_fuse_begin_grid": (C.c_int, [C.POINTER(FuseSession), C.POINTER(VoxelGrid), _vp]),
@@ -177,6 +180,18 @@ def check(rc: int) -> None:
     if rc != 0:
         msg = load().ddn_last_error_string().decode("utf-8", "replace")
         raise DDNError(f"libddn_b200 error {rc}: {msg}")
+
+
+def profile(on: bool) -> None:
+    load().ddn_profile_enable(1 if on else 0)
+
+
+def profile_report() -> list[tuple[str, float]]:
+    """[(kernel, ms since the previous mark)] recorded since profile(True); synchronises."""
+    buf = C.create_string_buffer(1 << 20)
+    check(load().ddn_profile_report(buf, len(buf)))
+    rows = [ln.rsplit(" ", 1) for ln in buf.value.decode().splitlines() if ln]
+    return [(a, float(b)) for a, b in rows]
 
 
 def launch_count() -> int:

@@ -2,9 +2,22 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <string>
+#include <vector>
+
 #include "common.cuh"
 
 namespace ddn {
+
+std::atomic<int> g_profile{0};
+static std::vector<std::pair<std::string, cudaEvent_t>> g_marks;
+
+void profile_mark(const char* name, cudaStream_t st) {
+  cudaEvent_t ev;
+  if (cudaEventCreate(&ev) != cudaSuccess) return;
+  cudaEventRecord(ev, st);
+  g_marks.emplace_back(name, ev);
+}
 
 static thread_local char t_error[512] = "";
 std::atomic<int64_t> g_launches{0};
@@ -25,6 +38,29 @@ int ddn_version(void) { return DDN_VERSION; }
 const char* ddn_last_error_string(void) { return ddn::t_error; }
 
 int64_t ddn_launch_count(void) { return ddn::g_launches.load(std::memory_order_relaxed); }
+
+void ddn_profile_enable(int on) {
+  ddn::g_profile.store(on ? 1 : 0);
+  if (on) ddn::profile_mark("(start)", nullptr);
+}
+
+int ddn_profile_report(char* buf, int64_t size) {
+  using namespace ddn;
+  if (buf == nullptr || size <= 0) return DDN_ERR_INVALID_ARGUMENT;
+  cudaDeviceSynchronize();
+  std::string out;
+  for (size_t i = 1; i < g_marks.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, g_marks[i - 1].second, g_marks[i].second);
+    char line[160];
+    snprintf(line, sizeof(line), "%s %.4f\n", g_marks[i].first.c_str(), ms);
+    out += line;
+  }
+  for (auto& m : g_marks) cudaEventDestroy(m.second);
+  g_marks.clear();
+  snprintf(buf, (size_t)size, "%s", out.c_str());
+  return DDN_OK;
+}
 
 void ddn_align_config_default(ddn_align_config* cfg) {
   memset(cfg, 0, sizeof(*cfg));

@@ -22,10 +22,18 @@ inline int check_cuda(cudaError_t e, const char* what) {
   return DDN_OK;
 }
 
+// Optional per-launch timing (ddn_profile_enable): an event after every launch that passes its stream.
+void profile_mark(const char* name, cudaStream_t st);
+extern std::atomic<int> g_profile;
+
 // Call after every kernel launch: counts it and surfaces launch-configuration errors.
 inline int after_launch(const char* name) {
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return check_cuda(cudaPeekAtLastError(), name);
+}
+inline int after_launch(const char* name, cudaStream_t st) {
+  if (g_profile.load(std::memory_order_relaxed)) profile_mark(name, st);
+  return after_launch(name);
 }
 
 #define DDN_REQUIRE(cond, msg)                      \

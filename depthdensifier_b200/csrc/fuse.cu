@@ -683,115 +683,138 @@ __global__ void canonical_key_kernel(GridDev g, int64_t n, const float* __restri
 // prefix of the lengths (P = DDN_MAX_PEERS).
 constexpr int kPlanWords = 4 + 3 * DDN_MAX_PEERS;
 static_assert(kPlanWords <= 64, "plan scratch is 64 words");
+static_assert(DDN_MAX_PEERS <= 31, "the plan kernel is one warp");
 
 struct PeerPtrs {
   const void* p[DDN_MAX_PEERS];
 };
 
-// The R ranks cut the ownership tiles into R contiguous ranges that balance the GLOBAL record count:
-// cum[t] = sum over ranks of tile_prefix_q[t] is the number of records in tiles [0, t); boundary b is the
-// first t with cum[t] >= total * b / R.  Every rank runs the same search on the same (peer-visible) arrays,
-// so all agree without communicating.  One warp per boundary, one lane per rank per probe.
-__global__ void __launch_bounds__(32 * (DDN_MAX_PEERS + 1))
-merge_plan_kernel(const GridDev* __restrict__ gp, PeerPtrs prefix, int rank, int R, long long* __restrict__ plan) {
-  __shared__ long long s_bnd[DDN_MAX_PEERS + 1];
-  const long long n_own = (gp->n_units + kOwnUnits - 1) / kOwnUnits;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  auto cum_at = [&](long long t) -> long long {  // warp-collective
-    long long v = 0;
-    if (lane < R) v = (long long)__ldcv(reinterpret_cast<const uint32_t*>(prefix.p[lane]) + t);
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-    return v;
-  };
-  // warps 1..R-1: the balanced cuts; warp 0: the first tile that holds a record; warp R (or 0 again when R is
-  // DDN_MAX_PEERS): the end of the last one - the empty head and tail of the grid belong to nobody
-  if (warp <= R && warp < DDN_MAX_PEERS + 1) {
-    const long long total = cum_at(n_own);
-    const long long target = warp == 0 ? 1 : (warp == R ? total : total * warp / R);
-    long long lo = 0, hi = n_own + 1;
-    while (lo < hi) {
-      const long long mid = (lo + hi) >> 1;
-      if (cum_at(mid) < target) lo = mid + 1;
-      else hi = mid;
-    }
-    lo = min(lo, n_own);
-    if (warp == 0) lo = total > 0 ? max(lo - 1, 0ll) : 0;  // cum[lo] >= 1 > cum[lo - 1]: tile lo - 1 is the first with a record
-    if (lane == 0) s_bnd[warp] = lo;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int b = 1; b <= R; ++b) s_bnd[b] = max(s_bnd[b], s_bnd[b - 1]);  // monotone
-    plan[0] = s_bnd[rank];
-    plan[1] = s_bnd[rank + 1];
-    plan[3] = n_own;
-  }
-  __syncthreads();
-  if (warp == 0) {
-    long long begin = 0, count = 0;
-    if (lane < R) {
-      const uint32_t* pq = reinterpret_cast<const uint32_t*>(prefix.p[lane]);
-      begin = (long long)__ldcv(pq + s_bnd[rank]);
-      count = (long long)__ldcv(pq + s_bnd[rank + 1]) - begin;
-    }
-    long long inc = count;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const long long t = __shfl_up_sync(0xffffffffu, inc, d);
-      if (lane >= d) inc += t;
-    }
-    if (lane < DDN_MAX_PEERS) {
-      plan[4 + lane] = begin;
-      plan[4 + DDN_MAX_PEERS + lane] = count;
-      plan[4 + 2 * DDN_MAX_PEERS + lane] = inc - count;
-    }
-    const long long total = __shfl_sync(0xffffffffu, inc, 31);
-    if (lane == 0) plan[2] = total;
-  }
-}
-
-// local copy of every rank's tile prefix over the owned range [t0, t1]: local[q * stride + (t - t0)], and their
-// sum over the ranks in row R (one compare then tells whether anybody has a record in a tile)
+// Step 0 of the merge: every rank's tile prefix (whole array, n_own + 1 entries) is copied into local memory in
+// ONE bulk pass over NVLink - local[q * stride + t] - with their sum over the ranks in row R.  Everything the plan
+// and the occupancy merge decide afterwards reads local memory: no chain of dependent remote round trips.
 __global__ void __launch_bounds__(256)
-merge_copy_prefix_kernel(PeerPtrs prefix, int R, const long long* __restrict__ plan, uint32_t* __restrict__ local, long long stride) {
-  const long long t0 = plan[0], n = plan[1] - t0 + 1;
+merge_gather_prefix_kernel(const GridDev* __restrict__ gp, PeerPtrs prefix, int R, uint32_t* __restrict__ local, long long stride) {
+  const long long n = (gp->n_units + kOwnUnits - 1) / kOwnUnits + 1;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    uint32_t v[DDN_MAX_PEERS];
+#pragma unroll
+    for (int q = 0; q < DDN_MAX_PEERS; ++q) v[q] = q < R ? __ldcv(reinterpret_cast<const uint32_t*>(prefix.p[q]) + i) : 0u;
     uint32_t sum = 0;
-    for (int q = 0; q < R; ++q) {
-      const uint32_t v = __ldcv(reinterpret_cast<const uint32_t*>(prefix.p[q]) + t0 + i);
-      local[q * stride + i] = v;
-      sum += v;
+#pragma unroll
+    for (int q = 0; q < DDN_MAX_PEERS; ++q) {
+      if (q < R) local[q * stride + i] = v[q];
+      sum += v[q];
     }
     local[(long long)R * stride + i] = sum;
   }
 }
 
-// OR of all ranks' occupancy over the owned tiles -> this rank's units (in place: peers only read the units
-// of THEIR ranges), count per tile.  A tile a rank has no record in is not read from that rank.
+// The R ranks cut the ownership tiles into R contiguous ranges that balance the GLOBAL record count:
+// cum[t] = sum over ranks of tile_prefix_q[t] is the number of records in tiles [0, t); boundary b is the
+// first t with cum[t] >= total * b / R.  Every rank runs the same search on the same numbers, so all agree
+// without communicating.  One thread per boundary (binary search in the local cum row).
+__global__ void __launch_bounds__(32)
+merge_plan_kernel(const GridDev* __restrict__ gp, const uint32_t* __restrict__ local, long long stride, int rank, int R,
+                  long long* __restrict__ plan) {
+  __shared__ long long s_bnd[DDN_MAX_PEERS + 1];
+  const long long n_own = (gp->n_units + kOwnUnits - 1) / kOwnUnits;
+  const uint32_t* cum = local + (long long)R * stride;
+  const int b = threadIdx.x;
+  if (b <= R) {
+    // b = 1..R-1: the balanced cuts; b = 0: the first tile that holds a record; b = R: the end of the last one -
+    // the empty head and tail of the grid belong to nobody
+    const long long total = (long long)cum[n_own];
+    const long long target = b == 0 ? 1 : (b == R ? total : total * b / R);
+    long long lo = 0, hi = n_own + 1;
+    while (lo < hi) {
+      const long long mid = (lo + hi) >> 1;
+      if ((long long)cum[mid] < target) lo = mid + 1;
+      else hi = mid;
+    }
+    lo = min(lo, n_own);
+    if (b == 0) lo = total > 0 ? max(lo - 1, 0ll) : 0;  // cum[lo] >= 1 > cum[lo - 1]: tile lo - 1 is the first with a record
+    s_bnd[b] = lo;
+  }
+  __syncwarp();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k <= R; ++k) s_bnd[k] = max(s_bnd[k], s_bnd[k - 1]);  // monotone
+    plan[0] = s_bnd[rank];
+    plan[1] = s_bnd[rank + 1];
+    plan[3] = n_own;
+  }
+  __syncwarp();
+  const int lane = threadIdx.x;
+  long long begin = 0, count = 0;
+  if (lane < R) {
+    begin = (long long)local[lane * stride + s_bnd[rank]];
+    count = (long long)local[lane * stride + s_bnd[rank + 1]] - begin;
+  }
+  long long inc = count;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const long long t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane < DDN_MAX_PEERS) {
+    plan[4 + lane] = begin;
+    plan[4 + DDN_MAX_PEERS + lane] = count;
+    plan[4 + 2 * DDN_MAX_PEERS + lane] = inc - count;
+  }
+  const long long total = __shfl_sync(0xffffffffu, inc, 31);
+  if (lane == 0) plan[2] = total;
+}
+
+// The unit masks of the owned tiles, all ranks, into local memory: masks[(q * n + (t - t0)) * 8 + w] (bulk, coalesced;
+// ranks without a record in a tile are not read: their mask is 0)
+__global__ void __launch_bounds__(256)
+merge_gather_mask_kernel(PeerPtrs peer_mask, int R, const long long* __restrict__ plan, const uint32_t* __restrict__ local,
+                         long long stride, uint32_t* __restrict__ masks) {
+  const long long t0 = plan[0], n = plan[1] - t0;
+  const long long total = n * 8 * R;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i / (n * 8));
+    const long long r = i - (long long)q * n * 8;
+    const long long t = t0 + (r >> 3);
+    const uint32_t* pl = local + q * stride + t;
+    masks[i] = pl[1] != pl[0] ? __ldcv(reinterpret_cast<const uint32_t*>(peer_mask.p[q]) + t * 8 + (r & 7)) : 0u;
+  }
+}
+
+// OR of all ranks' occupancy over the owned tiles -> this rank's units (in place: peers only read the units of
+// THEIR ranges), count per tile.  Which units to read comes from the local mask copies; the loads from all ranks
+// are issued together (one NVLink latency per tile, not one per rank).
 __global__ void __launch_bounds__(kOwnUnits)
-merge_or_kernel(FuseDev f, PeerPtrs peer_units, PeerPtrs peer_mask, int rank, int R, const long long* __restrict__ plan,
-                const uint32_t* __restrict__ prefix_local, long long stride, uint32_t* __restrict__ tile_sums) {
+merge_or_kernel(FuseDev f, PeerPtrs peer_units, int rank, int R, const long long* __restrict__ plan,
+                const uint32_t* __restrict__ local, long long stride, const uint32_t* __restrict__ masks,
+                uint32_t* __restrict__ tile_sums) {
   __shared__ int s_warp[kScanThreads / 32];
   const long long n_units = f.grid->n_units;
-  const long long t0 = plan[0], t1 = plan[1];
+  const long long t0 = plan[0], t1 = plan[1], n = t1 - t0;
   uint4* my_units = reinterpret_cast<uint4*>(f.units);
-  const uint32_t* cum = prefix_local + (long long)R * stride;
+  const uint32_t* cum = local + (long long)R * stride;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (long long t = t0 + blockIdx.x; t < t1; t += gridDim.x) {
-    if (cum[t - t0 + 1] == cum[t - t0]) {  // CTA-uniform: nobody has a record here
+    if (cum[t + 1] == cum[t]) {  // CTA-uniform: nobody has a record here
       if (threadIdx.x == 0) tile_sums[t - t0] = 0u;
       continue;
     }
     const long long ui = t * kOwnUnits + threadIdx.x;
     uint4 m = make_uint4(0, 0, 0, 0);
-    for (int q = 0; q < R; ++q) {
-      const uint32_t* pl = prefix_local + q * stride + (t - t0);
-      if (pl[1] == pl[0]) continue;  // CTA-uniform
-      // only the units that rank marked non-empty are read (one mask word per warp: 32 units)
-      const uint32_t mask = __ldcv(reinterpret_cast<const uint32_t*>(peer_mask.p[q]) + t * 8 + (threadIdx.x >> 5));
-      if (ui < n_units && ((mask >> (threadIdx.x & 31)) & 1u)) {
-        const uint4 u = q == rank ? my_units[ui] : __ldcv(reinterpret_cast<const uint4*>(peer_units.p[q]) + ui);
-        m.x |= u.x, m.y |= u.y, m.z |= u.z;
+#pragma unroll 1
+    for (int q0 = 0; q0 < R; q0 += 8) {
+      uint4 u[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int q = q0 + k;
+        u[k] = make_uint4(0, 0, 0, 0);
+        if (q < R) {
+          const uint32_t mask = masks[((long long)q * n + (t - t0)) * 8 + warp];
+          if (ui < n_units && ((mask >> lane) & 1u))
+            u[k] = q == rank ? my_units[ui] : __ldcv(reinterpret_cast<const uint4*>(peer_units.p[q]) + ui);
+        }
       }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) m.x |= u[k].x, m.y |= u[k].y, m.z |= u[k].z;
     }
     const int total = block_sum_256(popc3(m), s_warp);
     // an untouched tile stays untouched; a touched one gets the merged bits (its prefix word follows).  Units this
@@ -931,13 +954,13 @@ static int launch_rank(const ddn_fuse_session* s, ScanRange range, uint64_t* key
   const unsigned ctas = range.n_tiles >= 0 ? (unsigned)std::max<long long>(1, std::min<long long>(range.n_tiles, kPersistentCtas))
                                             : (unsigned)kPersistentCtas;
   tile_count_kernel<<<ctas, kScanThreads, 0, st>>>(gp, units, s->dirty, range, s->tile_sums);
-  DDN_TRY(after_launch("tile_count_kernel"));
+  DDN_TRY(after_launch("tile_count_kernel", st));
   tile_scan_kernel<<<1, 1024, 0, st>>>(gp, range, nullptr, s->tile_sums, counts);
-  DDN_TRY(after_launch("tile_scan_kernel"));
+  DDN_TRY(after_launch("tile_scan_kernel", st));
   zero_accum_kernel<<<kPersistentCtas, 256, 0, st>>>((ulonglong2*)zero_base, counts, zero_stride, cap);
-  DDN_TRY(after_launch("zero_accum_kernel"));
+  DDN_TRY(after_launch("zero_accum_kernel", st));
   unit_prefix_kernel<<<ctas, kScanThreads, 0, st>>>(gp, units, range, s->tile_sums, keys, key_stride, cap, own_prefix, own_mask);
-  return after_launch("unit_prefix_kernel");
+  return after_launch("unit_prefix_kernel", st);
 }
 
 static int launch_accumulate_points(const ddn_fuse_session* s, int64_t n, int64_t row_len, const float* xyz, const uint8_t* rgb,
@@ -954,14 +977,14 @@ static int launch_accumulate_points(const ddn_fuse_session* s, int64_t n, int64_
     accumulate_points_kernel<kAccTileW><<<ablocks, 256, 0, st>>>(gp, n, (int)row_len, xyz, rgb, votes, thr, units, accum, stride, cap);
   else
     accumulate_points_kernel<0><<<ablocks, 256, 0, st>>>(gp, n, (int)row_len, xyz, rgb, votes, thr, units, accum, stride, cap);
-  return after_launch("accumulate_points_kernel");
+  return after_launch("accumulate_points_kernel", st);
 }
 
 static int launch_finalize(const ddn_fuse_session* s, const unsigned long long* accum, const uint64_t* keys, long long cap,
                            float* out_xyz, uint8_t* out_rgb, int32_t* out_count, cudaStream_t st) {
   finalize_kernel<<<kPersistentCtas, 256, 0, st>>>(reinterpret_cast<const GridDev*>(s->grid), accum, keys,
                                                    reinterpret_cast<long long*>(s->counts), cap, out_xyz, out_rgb, out_count);
-  return after_launch("finalize_kernel");
+  return after_launch("finalize_kernel", st);
 }
 
 // ---- legacy host-grid entry points: a session carved out of the caller's workspace -----------------
@@ -1198,6 +1221,14 @@ int ddn_fuse_session_sizes(int64_t max_cells, int64_t* cap_units, int64_t* units
   return DDN_OK;
 }
 
+int ddn_fuse_merge_scratch_bytes(int64_t cap_units, int32_t n_ranks, int64_t* bytes_out) {
+  using namespace ddn;
+  DDN_REQUIRE(bytes_out != nullptr && cap_units > 0 && n_ranks >= 1 && n_ranks <= DDN_MAX_PEERS, "arguments");
+  const int64_t stride = cap_units / kOwnUnits + 2;
+  *bytes_out = ((int64_t)(n_ranks + 1) * stride + (int64_t)n_ranks * stride * 8) * 4;
+  return DDN_OK;
+}
+
 int ddn_fuse_session_reset(const ddn_fuse_session* s, void* stream) {
   using namespace ddn;
   DDN_TRY(session_check(s));
@@ -1322,26 +1353,30 @@ int ddn_fuse_merge_peers(const ddn_fuse_session* s, int32_t rank, int32_t n_rank
   long long* planll = reinterpret_cast<long long*>(plan);
   unsigned long long* acc = (unsigned long long*)accum;
   const long long stride = (long long)(s->cap_units / kOwnUnits + 2);
-  merge_plan_kernel<<<1, 32 * (DDN_MAX_PEERS + 1), 0, st>>>(gp, pp, rank, n_ranks, planll);
-  DDN_TRY(after_launch("merge_plan_kernel"));
-  merge_copy_prefix_kernel<<<kNumSMs, 256, 0, st>>>(pp, n_ranks, planll, prefix_scratch, stride);
-  DDN_TRY(after_launch("merge_copy_prefix_kernel"));
-  merge_or_kernel<<<kPersistentCtas, kOwnUnits, 0, st>>>(f, pu, pm, rank, n_ranks, planll, prefix_scratch, stride, s->tile_sums);
-  DDN_TRY(after_launch("merge_or_kernel"));
+  uint32_t* local = prefix_scratch;                               // [(R + 1) * stride] prefixes + their sum
+  uint32_t* masks = prefix_scratch + (long long)(n_ranks + 1) * stride;  // [R * stride * 8] worst case
+  merge_gather_prefix_kernel<<<kNumSMs * 2, 256, 0, st>>>(gp, pp, n_ranks, local, stride);
+  DDN_TRY(after_launch("merge_gather_prefix_kernel", st));
+  merge_plan_kernel<<<1, 32, 0, st>>>(gp, local, stride, rank, n_ranks, planll);
+  DDN_TRY(after_launch("merge_plan_kernel", st));
+  merge_gather_mask_kernel<<<kNumSMs * 2, 256, 0, st>>>(pm, n_ranks, planll, local, stride, masks);
+  DDN_TRY(after_launch("merge_gather_mask_kernel", st));
+  merge_or_kernel<<<kPersistentCtas, kOwnUnits, 0, st>>>(f, pu, rank, n_ranks, planll, local, stride, masks, s->tile_sums);
+  DDN_TRY(after_launch("merge_or_kernel", st));
   if (n_drop > 0) {  // N5: cells of the sparse cloud leave the merged occupancy; tile counts again
     unmark_points_kernel<<<(unsigned)((n_drop + 255) / 256), 256, 0, st>>>(f, n_drop, drop_xyz, planll);
-    DDN_TRY(after_launch("unmark_points_kernel"));
+    DDN_TRY(after_launch("unmark_points_kernel", st));
     merge_recount_kernel<<<kPersistentCtas, kOwnUnits, 0, st>>>(f, planll, s->tile_sums);
-    DDN_TRY(after_launch("merge_recount_kernel"));
+    DDN_TRY(after_launch("merge_recount_kernel", st));
   }
   tile_scan_kernel<<<1, 1024, 0, st>>>(gp, ScanRange{0, 0}, planll, s->tile_sums, counts);
-  DDN_TRY(after_launch("tile_scan_kernel"));
+  DDN_TRY(after_launch("tile_scan_kernel", st));
   zero_accum_kernel<<<kPersistentCtas, 256, 0, st>>>((ulonglong2*)acc, counts, kAccWords, cap_out);
-  DDN_TRY(after_launch("zero_accum_kernel"));
+  DDN_TRY(after_launch("zero_accum_kernel", st));
   merge_prefix_kernel<<<kPersistentCtas, kOwnUnits, 0, st>>>(f, planll, s->tile_sums, out_keys, cap_out);
-  DDN_TRY(after_launch("merge_prefix_kernel"));
+  DDN_TRY(after_launch("merge_prefix_kernel", st));
   merge_accumulate_kernel<<<kPersistentCtas, 256, 0, st>>>(f, pr, n_ranks, planll, acc, cap_out);
-  DDN_TRY(after_launch("merge_accumulate_kernel"));
+  DDN_TRY(after_launch("merge_accumulate_kernel", st));
   return launch_finalize(s, acc, out_keys, cap_out, out_xyz, out_rgb, out_count, st);
 }
 

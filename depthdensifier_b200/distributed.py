@@ -228,7 +228,7 @@ class ShardedDensifier:
         self._peer_records = ptrs("records", tuple(self.peer_records_shape), torch.int64)
         self._peer_bbox = ptrs("bbox", (64,), torch.int32)
         self._plan = torch.zeros(64, dtype=torch.int64, device=self.device)
-        self._prefix_scratch = torch.empty(self.session.n_own_cap * (self.world + 1), dtype=torch.int32, device=self.device)
+        self.session.merge_scratch(self.world)
         # a rank's share of the merged voxels: the cuts balance the global record count, up to one tile per rank
         n_max = self._local_max * self.Hs * self.Ws
         self._cap_merge = n_max + 24576 * self.world + 1024
@@ -467,7 +467,7 @@ class ShardedDensifier:
         hdl.barrier()  # every rank's units, tile prefix and records are complete
         k, x, c, n, counts = mark("fuse_merge", lambda: self.ops.fuse_merge_peers(
             sess, self.rank, self.world, self._peer_units, self._peer_records, self._peer_prefix, self._peer_mask, self._plan,
-            self._prefix_scratch, self._cap_merge, out=self._merge_out, drop_xyz=drop))
+            self._cap_merge, out=self._merge_out, drop_xyz=drop))
         return k, x, c, n, counts.clone()
 
     def _nbr_full(self) -> torch.Tensor:

@@ -328,6 +328,14 @@ class FuseSession:
             g.origin[i], g.bits[i], g.dims[i] = st.origin[i], st.bits[i], st.dims[i]
         return g
 
+    def merge_scratch(self, world: int) -> torch.Tensor:
+        """Scratch of fuse_merge_peers for ``world`` ranks (allocated once per session)."""
+        if getattr(self, "_merge_scratch", None) is None or self._merge_scratch[0] != world:
+            nbytes = C.c_int64(0)
+            _lib.check(_lib.load().ddn_fuse_merge_scratch_bytes(self.cap_units, int(world), C.byref(nbytes)))
+            self._merge_scratch = (world, torch.empty(nbytes.value, dtype=torch.uint8, device=self.device))
+        return self._merge_scratch[1]
+
     def accum(self, cap_out: int) -> torch.Tensor:
         nbytes = cap_out * 40 + 16
         if self._accum is None or self._accum.numel() < nbytes:
@@ -385,7 +393,7 @@ def fuse_finish_partial(sess: FuseSession, xyz, rgb, votes, vote_threshold: int,
 
 
 def fuse_merge_peers(sess: FuseSession, rank: int, world: int, peer_units, peer_records, peer_tile_prefix, peer_tile_mask, plan,
-                     prefix_scratch, cap_out: int, out=None, drop_xyz=None):
+                     cap_out: int, out=None, drop_xyz=None):
     """Owner-side exchange + merge over peer memory.  ``peer_*``: per rank, the device address of that rank's
     units / records / tile prefix as mapped into this process.  ``drop_xyz`` [n,3] f32: N5, the sparse points of
     ALL ranks whose cells are removed from the merged occupancy.  Returns keys, xyz, rgb, count, counts."""
@@ -393,6 +401,7 @@ def fuse_merge_peers(sess: FuseSession, rank: int, world: int, peer_units, peer_
     dev = sess.device
     k, x, c, n = out if out is not None else new_voxel_outputs(cap_out, dev)
     acc = sess.accum(cap_out)
+    prefix_scratch = sess.merge_scratch(world)
     arr = lambda ptrs: (C.c_void_p * world)(*[int(v) for v in ptrs])
     with torch.cuda.device(dev):
         _lib.check(lib.ddn_fuse_merge_peers(C.byref(sess.c), int(rank), int(world), arr(peer_units), arr(peer_records),

@@ -46,6 +46,11 @@ DDN_API int ddn_version(void);
 DDN_API const char* ddn_last_error_string(void);
 /* Number of kernels this library has launched in the calling process (for bench.py gpu_launches). */
 DDN_API int64_t ddn_launch_count(void);
+/* Diagnostics (single-threaded use): with profiling on, the multi-GPU merge records a CUDA event after each of its
+ * kernels; ddn_profile_report synchronises the device and writes "name milliseconds" lines (time since the previous
+ * mark on the stream, so the first line of a call also contains whatever ran before it) into buf. */
+DDN_API void ddn_profile_enable(int on);
+DDN_API int ddn_profile_report(char* buf, int64_t size);
 
 /* ------------------------------------------------------------------------------------------
  * Stage 1 - per-view alignment of monocular depth to projected sparse points.
@@ -301,6 +306,8 @@ typedef struct ddn_fuse_session { /* HOST struct of DEVICE pointers, owned by th
 /* Sizes of the session buffers for grids of up to max_cells cells (all outputs in bytes but cap_units). */
 DDN_API int ddn_fuse_session_sizes(int64_t max_cells, int64_t* cap_units, int64_t* units_bytes, int64_t* dirty_bytes,
                            int64_t* tile_sums_bytes, int64_t* tile_prefix_bytes, int64_t* tile_mask_bytes);
+/* Size of ddn_fuse_merge_peers' prefix_scratch for a session of cap_units units and n_ranks ranks. */
+DDN_API int ddn_fuse_merge_scratch_bytes(int64_t cap_units, int32_t n_ranks, int64_t* bytes_out);
 /* Once after allocation (and after any error): clears units and flags. */
 DDN_API int ddn_fuse_session_reset(const ddn_fuse_session* s, void* stream);
 /* Opens a step: grid from the n_boxes (<= DDN_MAX_PEERS) bounding boxes bbox_ptrs_host[i] (HOST array of
@@ -335,7 +342,7 @@ DDN_API int ddn_fuse_finish_partial(const ddn_fuse_session* s, int64_t n_points,
  * tiles that hold records into n_ranks contiguous ranges balancing the global record count (each computes the
  * same cuts from the summed prefixes); this rank ORs the occupancy of its range over all ranks (reading only the
  * units their masks name), ranks it, pulls its share of every rank's records and adds them, and finalises.  plan: device scratch [64] i64 (out: [0],[1] = tile range,
- * [2] = records received); prefix_scratch: device [(cap_units / 256 + 2) * (n_ranks + 1)] u32.  drop_xyz [n_drop,3] f32
+ * [2] = records received); prefix_scratch: device scratch of ddn_fuse_merge_scratch_bytes (local copies of every rank's tile prefix and of the unit masks of the owned tiles, fetched in bulk so that no decision waits on a chain of remote reads).  drop_xyz [n_drop,3] f32
  * (optional, n_drop = 0: none): N5 at the owner - the cells of these points (ALL ranks' sparse points) leave the
  * merged occupancy before it is ranked.  Outputs as ddn_fuse_finish.  The rank-ordered concatenation of the
  * outputs is globally key-sorted. */

@@ -71,11 +71,10 @@ def main():
         outs, times, recv = [], [], []
         for r in range(R):  # every rank once (the merge rewrites the rank's own units inside its range only)
             plan = torch.zeros(64, dtype=torch.int64, device=dev)
-            scratch = torch.empty(sessions[r].n_own_cap * (R + 1), dtype=torch.int32, device=dev)
             out = ops.new_voxel_outputs(cap, dev)
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
             ev[0].record()
-            k, x, c, m, counts = ops.fuse_merge_peers(sessions[r], r, R, pu, pr, pp, pm, plan, scratch, cap, out=out)
+            k, x, c, m, counts = ops.fuse_merge_peers(sessions[r], r, R, pu, pr, pp, pm, plan, cap, out=out)
             ev[1].record()
             torch.cuda.synchronize()
             times.append(ev[0].elapsed_time(ev[1]))

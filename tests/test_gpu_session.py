@@ -178,8 +178,7 @@ def test_merge_peers_virtual_ranks(lib_built, R):
     outs, plans = [], []
     for r in range(R):
         plan = torch.zeros(64, dtype=torch.int64, device="cuda")
-        scratch = torch.empty(sessions[r].n_own_cap * (R + 1), dtype=torch.int32, device="cuda")
-        k, x, c, m, counts = ops.fuse_merge_peers(sessions[r], r, R, pu, pr, pp, pm, plan, scratch, cap)
+        k, x, c, m, counts = ops.fuse_merge_peers(sessions[r], r, R, pu, pr, pp, pm, plan, cap)
         mv = int(counts[1])
         outs.append((k[:mv].clone(), x[:mv].clone(), c[:mv].clone(), m[:mv].clone()))
         plans.append(plan.cpu().tolist())
