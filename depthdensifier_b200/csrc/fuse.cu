@@ -679,8 +679,10 @@ __global__ void canonical_key_kernel(GridDev g, int64_t n, const float* __restri
 // Multi-GPU: owner-side exchange + merge over peer memory
 // ====================================================================================================
 // plan (device, i64): [0] first owned tile, [1] end of owned tiles, [2] records to receive, [3] own tiles,
-// [4 + q] first record of this rank's share in rank q's records, [4 + P + q] its length, [4 + 2P + q] exclusive
-// prefix of the lengths (P = DDN_MAX_PEERS).
+// [4 + k] first record of this rank's share in the records of rank q = (rank + k) % R, [4 + P + k] its length,
+// [4 + 2P + k] exclusive prefix of the lengths (P = DDN_MAX_PEERS).  The shares are walked in this ROTATED order:
+// every rank starts with its own records and then reads a different peer than everybody else, so all NVLink
+// ports carry traffic at once (in natural order all ranks would pull from rank 0 first, then from rank 1, ...).
 constexpr int kPlanWords = 4 + 3 * DDN_MAX_PEERS;
 static_assert(kPlanWords <= 64, "plan scratch is 64 words");
 static_assert(DDN_MAX_PEERS <= 31, "the plan kernel is one warp");
@@ -746,8 +748,9 @@ merge_plan_kernel(const GridDev* __restrict__ gp, const uint32_t* __restrict__ l
   const int lane = threadIdx.x;
   long long begin = 0, count = 0;
   if (lane < R) {
-    begin = (long long)local[lane * stride + s_bnd[rank]];
-    count = (long long)local[lane * stride + s_bnd[rank + 1]] - begin;
+    const int q = (rank + lane) % R;
+    begin = (long long)local[q * stride + s_bnd[rank]];
+    count = (long long)local[q * stride + s_bnd[rank + 1]] - begin;
   }
   long long inc = count;
 #pragma unroll
@@ -768,9 +771,11 @@ merge_plan_kernel(const GridDev* __restrict__ gp, const uint32_t* __restrict__ l
 // ranks without a record in a tile are not read: their mask is 0)
 __global__ void __launch_bounds__(256)
 merge_gather_mask_kernel(PeerPtrs peer_mask, int R, const long long* __restrict__ plan, const uint32_t* __restrict__ local,
-                         long long stride, uint32_t* __restrict__ masks) {
+                         long long stride, uint32_t* __restrict__ masks, uint32_t* __restrict__ tile_sums) {
   const long long t0 = plan[0], n = plan[1] - t0;
   const long long total = n * 8 * R;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (long long)gridDim.x * blockDim.x)
+    tile_sums[i] = 0u;  // merge_or_kernel adds the counts of its sub-tiles
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int q = (int)(i / (n * 8));
     const long long r = i - (long long)q * n * 8;
@@ -781,25 +786,28 @@ merge_gather_mask_kernel(PeerPtrs peer_mask, int R, const long long* __restrict_
 }
 
 // OR of all ranks' occupancy over the owned tiles -> this rank's units (in place: peers only read the units of
-// THEIR ranges), count per tile.  Which units to read comes from the local mask copies; the loads from all ranks
-// are issued together (one NVLink latency per tile, not one per rank).
+// THEIR ranges), count per tile.  The unit of work is a WARP-sized sub-tile (32 units): which units to read comes
+// from the local mask copies, a sub-tile nobody marked costs no remote access at all, the loads from all ranks are
+// issued together, and no block barrier couples the warps - a range of sparse tiles is bound by NVLink latency per
+// warp, not per CTA.
 __global__ void __launch_bounds__(kOwnUnits)
 merge_or_kernel(FuseDev f, PeerPtrs peer_units, int rank, int R, const long long* __restrict__ plan,
                 const uint32_t* __restrict__ local, long long stride, const uint32_t* __restrict__ masks,
                 uint32_t* __restrict__ tile_sums) {
-  __shared__ int s_warp[kScanThreads / 32];
   const long long n_units = f.grid->n_units;
   const long long t0 = plan[0], t1 = plan[1], n = t1 - t0;
   uint4* my_units = reinterpret_cast<uint4*>(f.units);
   const uint32_t* cum = local + (long long)R * stride;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (long long t = t0 + blockIdx.x; t < t1; t += gridDim.x) {
-    if (cum[t + 1] == cum[t]) {  // CTA-uniform: nobody has a record here
-      if (threadIdx.x == 0) tile_sums[t - t0] = 0u;
-      continue;
-    }
-    const long long ui = t * kOwnUnits + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const long long n_warps = (long long)gridDim.x * (kOwnUnits / 32);
+  for (long long item = (long long)blockIdx.x * (kOwnUnits / 32) + (threadIdx.x >> 5); item < n * 8; item += n_warps) {
+    const long long tr = item >> 3;  // tile index inside the range
+    const int w = (int)(item & 7);
+    const long long t = t0 + tr;
+    if (cum[t + 1] == cum[t]) continue;  // nobody has a record in this tile
+    const long long ui = t * kOwnUnits + w * 32 + lane;
     uint4 m = make_uint4(0, 0, 0, 0);
+    uint32_t any = 0;
 #pragma unroll 1
     for (int q0 = 0; q0 < R; q0 += 8) {
       uint4 u[8];
@@ -808,7 +816,8 @@ merge_or_kernel(FuseDev f, PeerPtrs peer_units, int rank, int R, const long long
         const int q = q0 + k;
         u[k] = make_uint4(0, 0, 0, 0);
         if (q < R) {
-          const uint32_t mask = masks[((long long)q * n + (t - t0)) * 8 + warp];
+          const uint32_t mask = masks[((long long)q * n + tr) * 8 + w];
+          any |= mask;
           if (ui < n_units && ((mask >> lane) & 1u))
             u[k] = q == rank ? my_units[ui] : __ldcv(reinterpret_cast<const uint4*>(peer_units.p[q]) + ui);
         }
@@ -816,13 +825,12 @@ merge_or_kernel(FuseDev f, PeerPtrs peer_units, int rank, int R, const long long
 #pragma unroll
       for (int k = 0; k < 8; ++k) m.x |= u[k].x, m.y |= u[k].y, m.z |= u[k].z;
     }
-    const int total = block_sum_256(popc3(m), s_warp);
-    // an untouched tile stays untouched; a touched one gets the merged bits (its prefix word follows).  Units this
-    // rank had not marked itself may hold anything the clean-up left (zeros), units it had are overwritten.
-    if (ui < n_units && total > 0) my_units[ui] = m;
-    if (threadIdx.x == 0) {
-      tile_sums[t - t0] = (uint32_t)total;
-      if (total > 0 && f.dirty != nullptr) f.dirty[(t * kOwnUnits) / kTileUnits] = 1;
+    if (any == 0u) continue;  // warp-uniform: the sub-tile is empty everywhere (this rank's units there are clean)
+    if (ui < n_units) my_units[ui] = m;  // merged bits; the prefix word follows in merge_prefix_kernel
+    const int total = __reduce_add_sync(0xffffffffu, popc3(m));
+    if (lane == 0 && total > 0) {
+      atomicAdd(tile_sums + tr, (uint32_t)total);
+      if (f.dirty != nullptr) f.dirty[(t * kOwnUnits) / kTileUnits] = 1;
     }
   }
 }
@@ -882,7 +890,7 @@ merge_prefix_kernel(FuseDev f, const long long* __restrict__ plan, const uint32_
 // (48 contiguous bytes per thread, 1536 per warp: fully coalesced NVLink reads), looked up in the merged
 // units and added with 64-bit REDs.
 __global__ void __launch_bounds__(256)
-merge_accumulate_kernel(FuseDev f, PeerPtrs peer_records, int R, const long long* __restrict__ plan,
+merge_accumulate_kernel(FuseDev f, PeerPtrs peer_records, int rank, int R, const long long* __restrict__ plan,
                         unsigned long long* __restrict__ accum, long long cap) {
   const GridDev g = *f.grid;
   if (g.n_units == 0) return;
@@ -890,10 +898,12 @@ merge_accumulate_kernel(FuseDev f, PeerPtrs peer_records, int R, const long long
   const uint4* units = reinterpret_cast<const uint4*>(f.units);
   const uint64_t cell_begin = (uint64_t)plan[0] * kOwnUnits * kUnitBits, cell_end = (uint64_t)plan[1] * kOwnUnits * kUnitBits;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int q = 0;
+    int kq = 0;
 #pragma unroll
-    for (int k = 1; k < DDN_MAX_PEERS; ++k) q += (k < R && i >= plan[4 + 2 * DDN_MAX_PEERS + k]) ? 1 : 0;
-    const long long j = plan[4 + q] + (i - plan[4 + 2 * DDN_MAX_PEERS + q]);
+    for (int k = 1; k < DDN_MAX_PEERS; ++k) kq += (k < R && i >= plan[4 + 2 * DDN_MAX_PEERS + k]) ? 1 : 0;
+    const long long j = plan[4 + kq] + (i - plan[4 + 2 * DDN_MAX_PEERS + kq]);
+    int q = rank + kq;
+    q -= q >= R ? R : 0;
     const ulonglong2* r = reinterpret_cast<const ulonglong2*>(reinterpret_cast<const unsigned long long*>(peer_records.p[q]) + j * kRecWords);
     const ulonglong2 a = __ldcv(r), b = __ldcv(r + 1), c = __ldcv(r + 2);
     const uint64_t cell = cell_of_key(g, a.x);
@@ -1359,7 +1369,7 @@ int ddn_fuse_merge_peers(const ddn_fuse_session* s, int32_t rank, int32_t n_rank
   DDN_TRY(after_launch("merge_gather_prefix_kernel", st));
   merge_plan_kernel<<<1, 32, 0, st>>>(gp, local, stride, rank, n_ranks, planll);
   DDN_TRY(after_launch("merge_plan_kernel", st));
-  merge_gather_mask_kernel<<<kNumSMs * 2, 256, 0, st>>>(pm, n_ranks, planll, local, stride, masks);
+  merge_gather_mask_kernel<<<kNumSMs * 2, 256, 0, st>>>(pm, n_ranks, planll, local, stride, masks, s->tile_sums);
   DDN_TRY(after_launch("merge_gather_mask_kernel", st));
   merge_or_kernel<<<kPersistentCtas, kOwnUnits, 0, st>>>(f, pu, rank, n_ranks, planll, local, stride, masks, s->tile_sums);
   DDN_TRY(after_launch("merge_or_kernel", st));
@@ -1375,7 +1385,7 @@ int ddn_fuse_merge_peers(const ddn_fuse_session* s, int32_t rank, int32_t n_rank
   DDN_TRY(after_launch("zero_accum_kernel", st));
   merge_prefix_kernel<<<kPersistentCtas, kOwnUnits, 0, st>>>(f, planll, s->tile_sums, out_keys, cap_out);
   DDN_TRY(after_launch("merge_prefix_kernel", st));
-  merge_accumulate_kernel<<<kPersistentCtas, 256, 0, st>>>(f, pr, n_ranks, planll, acc, cap_out);
+  merge_accumulate_kernel<<<kPersistentCtas, 256, 0, st>>>(f, pr, rank, n_ranks, planll, acc, cap_out);
   DDN_TRY(after_launch("merge_accumulate_kernel", st));
   return launch_finalize(s, acc, out_keys, cap_out, out_xyz, out_rgb, out_count, st);
 }
