@@ -89,6 +89,7 @@ SYMBOLS = {
     "ddn_version": (C.c_int, []),
     "ddn_last_error_string": (C.c_char_p, []),
     "ddn_launch_count": (C.c_int64, []),
+    "ddn_debug_peer_read": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     "ddn_profile_enable": (None, [C.c_int]),
     "ddn_profile_report": (C.c_int, [C.c_char_p, C.c_int64]),
     "ddn_align_config_default": (None, [C.POINTER(AlignConfig)]),

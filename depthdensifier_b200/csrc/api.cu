@@ -29,9 +29,44 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// Diagnostic: read `n16` 16-byte words from `src` (local or NVLink peer memory) with one of three load flavours
+// and fold them into out[0] - measures what SM-issued loads get out of a link (scripts/experiments/peer_read_probe.py).
+template <int kMode>
+__global__ void __launch_bounds__(256) peer_read_kernel(const uint4* __restrict__ src, long long n16, int per_thread, unsigned* out) {
+  unsigned acc = 0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n16; i0 += stride * per_thread) {
+    uint4 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const long long i = i0 + k * stride;
+      v[k] = make_uint4(0, 0, 0, 0);
+      if (k < per_thread && i < n16) {
+        if (kMode == 0) v[k] = __ldcv(src + i);
+        else if (kMode == 1) v[k] = src[i];
+        else v[k] = __ldg(src + i);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc ^= v[k].x ^ v[k].y ^ v[k].z ^ v[k].w;
+  }
+  if (acc == 0x12345679u) out[0] = acc;
+}
+
 }  // namespace ddn
 
 extern "C" {
+
+int ddn_debug_peer_read(const void* src, int64_t bytes, int32_t mode, int32_t per_thread, int32_t ctas, void* out, void* stream) {
+  using namespace ddn;
+  DDN_REQUIRE(src && out && bytes >= 16 && mode >= 0 && mode <= 2 && per_thread >= 1 && per_thread <= 8 && ctas >= 1, "arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n16 = bytes / 16;
+  if (mode == 0) peer_read_kernel<0><<<ctas, 256, 0, st>>>((const uint4*)src, n16, per_thread, (unsigned*)out);
+  else if (mode == 1) peer_read_kernel<1><<<ctas, 256, 0, st>>>((const uint4*)src, n16, per_thread, (unsigned*)out);
+  else peer_read_kernel<2><<<ctas, 256, 0, st>>>((const uint4*)src, n16, per_thread, (unsigned*)out);
+  return after_launch("peer_read_kernel");
+}
 
 int ddn_version(void) { return DDN_VERSION; }
 

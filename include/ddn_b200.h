@@ -49,6 +49,10 @@ DDN_API int64_t ddn_launch_count(void);
 /* Diagnostics (single-threaded use): with profiling on, the multi-GPU merge records a CUDA event after each of its
  * kernels; ddn_profile_report synchronises the device and writes "name milliseconds" lines (time since the previous
  * mark on the stream, so the first line of a call also contains whatever ran before it) into buf. */
+/* Diagnostic: reads `bytes` from src (local or NVLink peer memory) with mode 0 = ld.global.cv, 1 = plain ld.global,
+ * 2 = ld.global.nc; per_thread (1..8) 16-byte loads in flight per thread; out: device [1] u32 scratch. */
+DDN_API int ddn_debug_peer_read(const void* src, int64_t bytes, int32_t mode, int32_t per_thread, int32_t ctas, void* out,
+                        void* stream);
 DDN_API void ddn_profile_enable(int on);
 DDN_API int ddn_profile_report(char* buf, int64_t size);
 
