@@ -886,26 +886,53 @@ merge_prefix_kernel(FuseDev f, const long long* __restrict__ plan, const uint32_
   }
 }
 
-// pull + add: thread i handles one record of this rank's share, read straight out of its owner's HBM
-// (48 contiguous bytes per thread, 1536 per warp: fully coalesced NVLink reads), looked up in the merged
-// units and added with 64-bit REDs.
+// pull + add: a warp handles 32 consecutive records of this rank's share, read straight out of their owner's HBM.
+// The 1536 bytes are fetched as three fully coalesced 512-byte requests (lane l takes bytes 16 l of each) and
+// re-distributed through shared memory - NVLink moves large requests at full rate, while per-thread 48-byte
+// records (three 16-byte pieces at a 48-byte stride) would cross it as twice as many half-used 32-byte sectors:
+// measured 140 GB/s that way against 650 GB/s for coalesced loads (scripts/experiments/peer_read_probe.py).
+// Every record is then looked up in the merged units and added with 64-bit REDs.
 __global__ void __launch_bounds__(256)
 merge_accumulate_kernel(FuseDev f, PeerPtrs peer_records, int rank, int R, const long long* __restrict__ plan,
                         unsigned long long* __restrict__ accum, long long cap) {
+  __shared__ ulonglong2 s_rec[8][96];  // per warp: 32 records x 48 bytes
   const GridDev g = *f.grid;
   if (g.n_units == 0) return;
   const long long total = plan[2];
   const uint4* units = reinterpret_cast<const uint4*>(f.units);
   const uint64_t cell_begin = (uint64_t)plan[0] * kOwnUnits * kUnitBits, cell_end = (uint64_t)plan[1] * kOwnUnits * kUnitBits;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long n_warps = (long long)gridDim.x * 8;
+  for (long long w0 = ((long long)blockIdx.x * 8 + warp) * 32; w0 < total; w0 += n_warps * 32) {
+    const long long i = w0 + lane;
+    const bool in = i < total;
     int kq = 0;
 #pragma unroll
     for (int k = 1; k < DDN_MAX_PEERS; ++k) kq += (k < R && i >= plan[4 + 2 * DDN_MAX_PEERS + k]) ? 1 : 0;
     const long long j = plan[4 + kq] + (i - plan[4 + 2 * DDN_MAX_PEERS + kq]);
     int q = rank + kq;
     q -= q >= R ? R : 0;
-    const ulonglong2* r = reinterpret_cast<const ulonglong2*>(reinterpret_cast<const unsigned long long*>(peer_records.p[q]) + j * kRecWords);
-    const ulonglong2 a = __ldcv(r), b = __ldcv(r + 1), c = __ldcv(r + 2);
+    const unsigned long long* base = reinterpret_cast<const unsigned long long*>(peer_records.p[q]);
+    // whole warp inside one rank's share (the usual case): three coalesced 512-byte loads
+    const int kq0 = __shfl_sync(0xffffffffu, kq, 0);
+    const bool uniform = __all_sync(0xffffffffu, in && kq == kq0);
+    ulonglong2 a, b, c;
+    if (uniform) {
+      const long long j0 = __shfl_sync(0xffffffffu, j, 0);
+      const ulonglong2* src = reinterpret_cast<const ulonglong2*>(base + j0 * kRecWords);
+      s_rec[warp][lane] = __ldcv(src + lane);
+      s_rec[warp][32 + lane] = __ldcv(src + 32 + lane);
+      s_rec[warp][64 + lane] = __ldcv(src + 64 + lane);
+      __syncwarp();
+      a = s_rec[warp][lane * 3 + 0], b = s_rec[warp][lane * 3 + 1], c = s_rec[warp][lane * 3 + 2];
+      __syncwarp();
+    } else {
+      a = b = c = make_ulonglong2(~0ull, 0ull);  // key ~0: no cell
+      if (in) {
+        const ulonglong2* r = reinterpret_cast<const ulonglong2*>(base + j * kRecWords);
+        a = __ldcv(r), b = __ldcv(r + 1), c = __ldcv(r + 2);
+      }
+    }
     const uint64_t cell = cell_of_key(g, a.x);
     if (cell == kNoCell || cell < cell_begin || cell >= cell_end) continue;
     const uint32_t slot = slot_of_cell(cell, units);
