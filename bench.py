@@ -244,9 +244,11 @@ def run_workload(ctx: Ctx, workload: str, scaling: str, steps: int, warmup: int,
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     stage_events = []
+    t_host0 = time.perf_counter()
     for _ in range(steps):
         res = sharded.run(*dev_inputs, record_events=True)
         stage_events.append(res.events)
+    host_ms = (time.perf_counter() - t_host0) * 1e3 / steps  # time the host needs to ENQUEUE one step (no waiting)
     ev1.record()
     ctx.barrier()
     t_wall1 = time.time()
@@ -267,6 +269,7 @@ def run_workload(ctx: Ctx, workload: str, scaling: str, steps: int, warmup: int,
     out = {
         "workload": workload, "scaling": scaling, "ms_per_step": ms_step, "value": n_valid / (ms_step / 1e3), "steps": steps,
         "stages_ms": stage_ms, "k4_local_ms": k4_local_ms, "launches": int(launches), "clocks": clk,
+        "host_enqueue_ms_per_step": round(ctx.allreduce(host_ms, "max"), 3),
         "path": "peer" if sharded.peer is not None else ("single" if world == 1 else "collective"),
         "stats": {"valid_pixels": n_valid, "kept_points": n_kept, "voxels": n_vox, "valid_pixels_rank0": n_valid_local,
                   "views_rank0": hi - lo},
@@ -290,6 +293,12 @@ def run_workload(ctx: Ctx, workload: str, scaling: str, steps: int, warmup: int,
         agg = {n: sum(ms for nm, ms in rows[1:] if nm == n) / 2 for n in names}
         agg[rows[0][0] + " (first launch of a step: includes everything before it)"] = agg.pop(rows[0][0]) if rows else 0.0
         out["stage4_kernels_ms"] = {n: round(ctx.allreduce(v, "max"), 4) for n, v in agg.items()}
+        if ctx.dist is not None:  # per rank, to see imbalance between the ownership ranges
+            vec = torch.tensor([agg[n] for n in agg], dtype=torch.float64, device=dev)
+            allv = [torch.empty_like(vec) for _ in range(world)]
+            ctx.dist.all_gather(allv, vec)
+            out["stage4_kernels_ms_per_rank"] = {n: [round(float(allv[r][i]), 3) for r in range(world)] for i, n in enumerate(agg)
+                                                 if n.startswith("merge_") or n.startswith("accumulate")}
     if e2e:
         del res
         torch.cuda.empty_cache()
@@ -424,6 +433,8 @@ def main():
                           profile_kernels=True)
         strong = {"workload": "cfg3", "scaling": "strong", "ms_per_step": sr["ms_per_step"], "value": sr["value"], "unit": UNIT,
                   "steps": sr["steps"], "stages_ms": sr["stages_ms"], "stage4_kernels_ms": sr.get("stage4_kernels_ms"),
+                  "stage4_kernels_ms_per_rank": sr.get("stage4_kernels_ms_per_rank"),
+                  "host_enqueue_ms_per_step": sr["host_enqueue_ms_per_step"],
                   "path": sr["path"], "workload_stats": sr["stats"],
                   "config": workload_config("cfg3", world, "strong"),
                   "note": "total work fixed (200 views), divide the n_gpus=1 ms_per_step by this one for the speed-up"}
@@ -448,7 +459,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": main_run.get("e2e"), "gpu_launches": main_run["launches"],
             "multi_gpu_check": multi_gpu, "strong": strong,
             "host_cpus_rank0": (f"{numa_cpus[0]}-{numa_cpus[-1]} ({len(numa_cpus)})" if numa_cpus else None),
-            "clocks": main_run["clocks"], "stages_ms": stage_ms,
+            "clocks": main_run["clocks"], "stages_ms": stage_ms, "host_enqueue_ms_per_step": main_run["host_enqueue_ms_per_step"],
             "stage_GBps_algorithmic": {
                 "align_remap": 9 * views_local * H * W / (stage_ms.get("align", float("nan")) * 1e-3) / 1e9,
                 "backproject_filter": achieved,

@@ -193,8 +193,12 @@ class ShardedDensifier:
                 # fails here, on every rank alike, and the collectives take over
                 s_ = cfg.filter.stride
                 self.peer_records_shape = (self._local_max * ((height + s_ - 1) // s_) * ((width + s_ - 1) // s_), 6)
-                self.peer.buffer("refined", (self._slots_max, self.H, self.W), torch.float32)
-                self.peer.buffer("bbox", (64,), torch.int32)
+                # refined maps and bounding boxes are double-buffered (step parity): a rank may start aligning step i+1
+                # while a peer still pulls its step-i maps, so a step needs no barrier at its start
+                self._parity = 0
+                for par in (0, 1):
+                    self.peer.buffer(f"refined{par}", (self._slots_max, self.H, self.W), torch.float32)
+                    self.peer.buffer(f"bbox{par}", (64,), torch.int32)
                 if cfg.voxel is not None:
                     self.peer.buffer("records", self.peer_records_shape, torch.int64)
                     self._make_session()
@@ -226,7 +230,7 @@ class ShardedDensifier:
         self._peer_prefix = ptrs("fuse_tile_prefix", (self.session.tile_prefix.numel(),), torch.uint8)
         self._peer_mask = ptrs("fuse_tile_mask", (self.session.tile_mask.numel(),), torch.uint8)
         self._peer_records = ptrs("records", tuple(self.peer_records_shape), torch.int64)
-        self._peer_bbox = ptrs("bbox", (64,), torch.int32)
+        self._peer_bbox = [ptrs(f"bbox{par}", (64,), torch.int32) for par in (0, 1)]
         self._plan = torch.zeros(64, dtype=torch.int64, device=self.device)
         self.session.merge_scratch(self.world)
         # a rank's share of the merged voxels: the cuts balance the global record count, up to one tile per rank
@@ -277,9 +281,9 @@ class ShardedDensifier:
         """Halo exchange over peer memory: after a device-side barrier (every rank's refined maps are in
         place) the neighbour maps are pulled from the peers' HBM on a side stream, so the caller can keep
         the main stream busy with the source views that need no halo.  Returns the join function."""
-        _, hdl, views = self.peer.buffer("refined", (self._slots_max, self.H, self.W), torch.float32)
+        _, hdl, views = self.peer.buffer(f"refined{self._parity}", (self._slots_max, self.H, self.W), torch.float32)
         cur = torch.cuda.current_stream(self.device)
-        hdl.barrier()
+        hdl.barrier()  # every rank's refined maps and bounding box of this step are in place
         self._side.wait_stream(cur)
         with torch.cuda.stream(self._side):
             for slot, q, j in self._halo_src:
@@ -363,7 +367,7 @@ class ShardedDensifier:
         """Bounding box of this rank's back-projected pixels (filled by the alignment kernel); in peer-visible
         memory when there are peers, whose boxes the grid kernel reads directly."""
         if self.peer is not None:
-            buf = self.peer.buffer("bbox", (64,), torch.int32)[0]
+            buf = self.peer.buffer(f"bbox{self._parity}", (64,), torch.int32)[0]
             return ops.init_bbox(buf[:6])
         return self.ops.new_bbox(self.device)
 
@@ -378,17 +382,20 @@ class ShardedDensifier:
         if grid is not None:
             self.session.begin_grid(grid)
         elif self.peer is not None:
-            self.session.begin(self._peer_bbox, self.cfg.voxel)
+            self.session.begin(self._peer_bbox[self._parity], self.cfg.voxel)
         else:
             self.session.begin([box], self.cfg.voxel)
 
     def _new_refined_slots(self) -> torch.Tensor:
         """[n_slots,H,W] buffer for own + halo refined maps; NVLink-visible when peer memory is in use."""
         if self.peer is not None:
-            buf, hdl, _ = self.peer.buffer("refined", (self._slots_max, self.H, self.W), torch.float32)
-            # start of a step: every peer has finished the previous one, i.e. is done reading this rank's maps,
-            # bounding box, occupancy units and partial records, all of which are about to be overwritten
-            hdl.barrier()
+            # No barrier at the start of a step.  The maps and the box written now belong to the OTHER parity than
+            # the ones peers may still be reading (they were last used two steps ago, and every peer has since passed
+            # the halo barrier of the previous step, which it reaches only after it is done with them); the occupancy
+            # units and partial records are only overwritten after THIS step's halo barrier, which a peer reaches
+            # only after its merge of the previous step has finished.  The returned maps stay valid for two steps.
+            self._parity ^= 1
+            buf = self.peer.buffer(f"refined{self._parity}", (self._slots_max, self.H, self.W), torch.float32)[0]
             return buf[: self.n_slots]
         return torch.empty((self.n_slots, self.H, self.W), dtype=torch.float32, device=self.device)
 
