@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(kStatsThreads, 1)
 align_stats_kernel(ddn_align_config cfg, int H, int W, const float* __restrict__ depth,
                    const double* __restrict__ poses, const double* __restrict__ kmat,
                    const double* __restrict__ sparse_xyz, const int64_t* __restrict__ offsets,
-                   AlignWorkspace ws, ddn_view_stats* __restrict__ stats, int sort_in_smem) {
+                   AlignWorkspace ws, ddn_view_stats* __restrict__ stats, int sort_in_smem, int pairs_in_smem) {
   extern __shared__ __align__(16) unsigned long long s_sort[];
   __shared__ int s_warp[33];
   __shared__ double s_red[32];
@@ -177,11 +177,17 @@ align_stats_kernel(ddn_align_config cfg, int H, int W, const float* __restrict__
   const int tid = threadIdx.x;
   const int64_t lo = offsets[v];
   const int n_sparse = (int)(offsets[v + 1] - lo);
-  float* zd = ws.zd + (size_t)v * ws.C;
-  float* zc = ws.zc + (size_t)v * ws.C;
-  float* ratio = ws.ratio + (size_t)v * ws.C;
-  float* tx = ws.tx + (size_t)v * ws.C;
-  float* ty = ws.ty + (size_t)v * ws.C;
+  // The pair arrays of a view (sampled depth, COLMAP depth, ratio, table x / y) live in shared memory next to the
+  // sort buffer when they fit (5 x 4 C bytes): the kernel is one long chain of block-wide phases, and every
+  // phase that went through the global workspace paid an L2 round trip.  Only the final table goes out.
+  float* const s_pairs = reinterpret_cast<float*>(s_sort + (sort_in_smem ? ws.Cp : 0));
+  float* const gtx = ws.tx + (size_t)v * ws.C;
+  float* const gty = ws.ty + (size_t)v * ws.C;
+  float* zd = pairs_in_smem ? s_pairs : ws.zd + (size_t)v * ws.C;
+  float* zc = pairs_in_smem ? s_pairs + ws.C : ws.zc + (size_t)v * ws.C;
+  float* ratio = pairs_in_smem ? s_pairs + 2 * ws.C : ws.ratio + (size_t)v * ws.C;
+  float* tx = pairs_in_smem ? s_pairs + 3 * ws.C : gtx;
+  float* ty = pairs_in_smem ? s_pairs + 4 * ws.C : gty;
   unsigned long long* sortbuf = sort_in_smem ? s_sort : ws.sortbuf + (size_t)v * ws.Cp;
   const float* __restrict__ dmap = depth + (size_t)v * H * W;
 
@@ -384,8 +390,10 @@ align_stats_kernel(ddn_align_config cfg, int H, int W, const float* __restrict__
   block_sort_by(sortbuf, n3, [&](int i) { return ordered_bits(zd[i]); });
   for (int r = tid; r < n3; r += kStatsThreads) {
     const unsigned i = (unsigned)(sortbuf[r] & 0xffffffffu);
-    tx[r] = zd[i];
-    ty[r] = zc[i];
+    const float x = zd[i], y = zc[i];
+    tx[r] = x;
+    ty[r] = y;
+    if (pairs_in_smem) gtx[r] = x, gty[r] = y;  // K3 reads the table from the workspace
   }
   if (tid == 0) {
     st.num_table = n3;
@@ -663,12 +671,13 @@ int ddn_align_views(const ddn_align_config* cfg, int64_t n_views, int64_t height
   AlignWorkspace ws = carve(workspace, n_views, C);
   cudaStream_t st = (cudaStream_t)stream;
   const int in_smem = ws.Cp <= kSortSmemMax ? 1 : 0;
-  const size_t smem_sort = in_smem ? (size_t)ws.Cp * 8 : 0;
+  const int pairs_smem = (in_smem && (size_t)ws.Cp * 8 + (size_t)ws.C * 20 <= 200 * 1024) ? 1 : 0;
+  const size_t smem_sort = (in_smem ? (size_t)ws.Cp * 8 : 0) + (pairs_smem ? (size_t)ws.C * 20 : 0);
   DDN_TRY(check_cuda(cudaFuncSetAttribute(align_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sort),
                      "cudaFuncSetAttribute(align_stats)"));
   align_stats_kernel<<<(unsigned)n_views, kStatsThreads, smem_sort, st>>>(*cfg, (int)height, (int)width, depth,
                                                                          cam_from_world, kmat, sparse_xyz,
-                                                                         sparse_offsets, ws, stats, in_smem);
+                                                                         sparse_offsets, ws, stats, in_smem, pairs_smem);
   DDN_TRY(after_launch("align_stats_kernel"));
   const int tiles_x = (int)((width + kTileW - 1) / kTileW), tiles_y = (int)((height + kTileH - 1) / kTileH);
   // largest table any view can have: max_pairs when subsampling, else every surviving pair
