@@ -75,7 +75,7 @@ class FuseSession(C.Structure):
     """ddn_fuse_session: host struct of device pointers."""
 
     _fields_ = [("grid", C.c_void_p), ("units", C.c_void_p), ("cap_units", C.c_int64), ("dirty", C.c_void_p),
-                ("tile_sums", C.c_void_p), ("tile_prefix", C.c_void_p), ("tile_mask", C.c_void_p), ("counts", C.c_void_p)]
+                ("tile_sums", C.c_void_p), ("tile_prefix", C.c_void_p), ("counts", C.c_void_p)]
 
 
 GRID_OK, GRID_EMPTY, GRID_TOO_LARGE, GRID_TOO_MANY_BITS = 0, 1, 2, 3
@@ -134,8 +134,8 @@ SYMBOLS = {
         [C.POINTER(VoxelGrid), _i64, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     ),
     "ddn_voxel_keys": (C.c_int, [C.POINTER(VoxelGrid), _i64, _vp, _vp, _vp]),
-    "ddn_fuse_session_sizes": (C.c_int, [_i64] + [C.POINTER(_i64)] * 6),
-    "ddn_fuse_merge_scratch_bytes": (C.c_int, [_i64, _i32, C.POINTER(_i64)]),
+    "ddn_fuse_session_sizes": (C.c_int, [_i64] + [C.POINTER(_i64)] * 5),
+    "ddn_fuse_merge_scratch_bytes": (C.c_int, [_i64, _i32, _i64, C.POINTER(_i64)]),
     "ddn_fuse_session_reset": (C.c_int, [C.POINTER(FuseSession), _vp]),
     "ddn_fuse_begin": (C.c_int, [C.POINTER(FuseSession), C.POINTER(_vp), _i32, C.c_float, _vp]),
     "ddn_fuse_begin_grid": (C.c_int, [C.POINTER(FuseSession), C.POINTER(VoxelGrid), _vp]),
@@ -148,7 +148,7 @@ SYMBOLS = {
     "ddn_fuse_finish_partial": (C.c_int, [C.POINTER(FuseSession), _i64, _i64, _vp, _vp, _vp, _i32, _vp, _i64, _vp]),
     "ddn_fuse_merge_peers": (
         C.c_int,
-        [C.POINTER(FuseSession), _i32, _i32, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _vp, _i64,
+        [C.POINTER(FuseSession), _i32, _i32, C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _i64, _vp, _i64,
          _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp],
     ),
 }

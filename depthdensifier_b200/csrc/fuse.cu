@@ -360,13 +360,11 @@ __device__ __forceinline__ void emit_unit_keys(const GridDev& g, uint64_t nxy, l
 }
 
 // Per unit: exclusive rank prefix -> word w of the unit.  Per set bit: canonical key of the cell ->
-// keys[slot].  own_prefix (optional): record index at every ownership-tile boundary, [own_tiles + 1];
-// own_mask (optional, with own_prefix): which units of every ownership tile are non-empty, 8 words (256 bits)
-// per tile - what lets the owner-side merge of another rank read only those units over NVLink.
+// keys[slot].  own_prefix (optional): record index at every ownership-tile boundary, [own_tiles + 1].
 __global__ void __launch_bounds__(kScanThreads)
 unit_prefix_kernel(const GridDev* __restrict__ gp, uint4* __restrict__ units, ScanRange range,
                    const uint32_t* __restrict__ tile_excl, uint64_t* __restrict__ keys, int key_stride, long long cap,
-                   uint32_t* __restrict__ own_prefix, uint32_t* __restrict__ own_mask) {
+                   uint32_t* __restrict__ own_prefix) {
   __shared__ uint32_t s_warp[kScanThreads / 32];
   const GridDev g = *gp;
   const long long n_units = g.n_units;
@@ -386,8 +384,6 @@ unit_prefix_kernel(const GridDev* __restrict__ gp, uint4* __restrict__ units, Sc
       if (own_prefix != nullptr && threadIdx.x <= kOwnPerScanTile && own0 + threadIdx.x <= own_tiles &&
           (threadIdx.x < kOwnPerScanTile || last))
         own_prefix[own0 + threadIdx.x] = carry;
-      if (own_mask != nullptr && threadIdx.x < kOwnPerScanTile * 8 && own0 + threadIdx.x / 8 < own_tiles)
-        own_mask[own0 * 8 + threadIdx.x] = 0u;
       continue;
     }
 #pragma unroll 1
@@ -416,10 +412,6 @@ unit_prefix_kernel(const GridDev* __restrict__ gp, uint4* __restrict__ units, Sc
       if (own_prefix != nullptr && threadIdx.x == 0 && own0 + j <= own_tiles) own_prefix[own0 + j] = carry;
       carry += total;
       if (ui < n_units) units[ui].w = slot;
-      if (own_mask != nullptr) {
-        const uint32_t m = __ballot_sync(0xffffffffu, cnt != 0);
-        if (lane == 0 && own0 + j < own_tiles) own_mask[(own0 + j) * 8 + warp] = m;
-      }
       if (cnt) emit_unit_keys(g, nxy, ui, u, slot, keys, key_stride, cap);
     }
     if (own_prefix != nullptr && threadIdx.x == 0 && last && own0 + kOwnPerScanTile <= own_tiles)
@@ -767,83 +759,91 @@ merge_plan_kernel(const GridDev* __restrict__ gp, const uint32_t* __restrict__ l
   if (lane == 0) plan[2] = total;
 }
 
-// The unit masks of the owned tiles, all ranks, into local memory: masks[(q * n + (t - t0)) * 8 + w] (bulk, coalesced;
-// ranks without a record in a tile are not read: their mask is 0)
-__global__ void __launch_bounds__(256)
-merge_gather_mask_kernel(PeerPtrs peer_mask, int R, const long long* __restrict__ plan, const uint32_t* __restrict__ local,
-                         long long stride, uint32_t* __restrict__ masks, uint32_t* __restrict__ tile_sums) {
-  const long long t0 = plan[0], n = plan[1] - t0;
-  const long long total = n * 8 * R;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (long long)gridDim.x * blockDim.x)
-    tile_sums[i] = 0u;  // merge_or_kernel adds the counts of its sub-tiles
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int q = (int)(i / (n * 8));
-    const long long r = i - (long long)q * n * 8;
-    const long long t = t0 + (r >> 3);
-    const uint32_t* pl = local + q * stride + t;
-    masks[i] = pl[1] != pl[0] ? __ldcv(reinterpret_cast<const uint32_t*>(peer_mask.p[q]) + t * 8 + (r & 7)) : 0u;
-  }
-}
-
-// OR of all ranks' occupancy over the owned tiles -> this rank's units (in place: peers only read the units of
-// THEIR ranges), count per tile.  The unit of work is a WARP-sized sub-tile (32 units): which units to read comes
-// from the local mask copies, a sub-tile nobody marked costs no remote access at all, the loads from all ranks are
-// issued together, and no block barrier couples the warps - a range of sparse tiles is bound by NVLink latency per
-// warp, not per CTA.
+// The owner's units over its own range start empty: its own partial bits are re-marked from its records like
+// everybody else's (dirty scan tiles only; the flags stay set for the next step's clean-up).
 __global__ void __launch_bounds__(kOwnUnits)
-merge_or_kernel(FuseDev f, PeerPtrs peer_units, int rank, int R, const long long* __restrict__ plan,
-                const uint32_t* __restrict__ local, long long stride, const uint32_t* __restrict__ masks,
-                uint32_t* __restrict__ tile_sums) {
+merge_clear_kernel(FuseDev f, const long long* __restrict__ plan) {
   const long long n_units = f.grid->n_units;
-  const long long t0 = plan[0], t1 = plan[1], n = t1 - t0;
   uint4* my_units = reinterpret_cast<uint4*>(f.units);
-  const uint32_t* cum = local + (long long)R * stride;
-  const int lane = threadIdx.x & 31;
-  const long long n_warps = (long long)gridDim.x * (kOwnUnits / 32);
-  for (long long item = (long long)blockIdx.x * (kOwnUnits / 32) + (threadIdx.x >> 5); item < n * 8; item += n_warps) {
-    const long long tr = item >> 3;  // tile index inside the range
-    const int w = (int)(item & 7);
-    const long long t = t0 + tr;
-    if (cum[t + 1] == cum[t]) continue;  // nobody has a record in this tile
-    const long long ui = t * kOwnUnits + w * 32 + lane;
-    uint4 m = make_uint4(0, 0, 0, 0);
-    uint32_t any = 0;
-#pragma unroll 1
-    for (int q0 = 0; q0 < R; q0 += 8) {
-      uint4 u[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int q = q0 + k;
-        u[k] = make_uint4(0, 0, 0, 0);
-        if (q < R) {
-          const uint32_t mask = masks[((long long)q * n + tr) * 8 + w];
-          any |= mask;
-          if (ui < n_units && ((mask >> lane) & 1u))
-            u[k] = q == rank ? my_units[ui] : __ldcv(reinterpret_cast<const uint4*>(peer_units.p[q]) + ui);
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) m.x |= u[k].x, m.y |= u[k].y, m.z |= u[k].z;
-    }
-    if (any == 0u) continue;  // warp-uniform: the sub-tile is empty everywhere (this rank's units there are clean)
-    if (ui < n_units) my_units[ui] = m;  // merged bits; the prefix word follows in merge_prefix_kernel
-    const int total = __reduce_add_sync(0xffffffffu, popc3(m));
-    if (lane == 0 && total > 0) {
-      atomicAdd(tile_sums + tr, (uint32_t)total);
-      if (f.dirty != nullptr) f.dirty[(t * kOwnUnits) / kTileUnits] = 1;
-    }
+  for (long long t = plan[0] + blockIdx.x; t < plan[1]; t += gridDim.x) {
+    if (f.dirty != nullptr && f.dirty[(t * kOwnUnits) / kTileUnits] == 0) continue;  // CTA-uniform
+    const long long ui = t * kOwnUnits + threadIdx.x;
+    if (ui < n_units) my_units[ui] = make_uint4(0, 0, 0, 0);
   }
 }
 
-// tile counts of the owned range again (after ddn_fuse_merge_peers removed the cells of the sparse cloud)
+// THE exchange: this rank's share of every rank's sorted partial records is pulled straight out of its owner's HBM
+// - once - into a local staging array, and the occupancy bit of every record is set on the way.  A warp handles 32
+// consecutive records: the 1536 bytes are fetched as three fully coalesced 512-byte requests (lane l takes bytes
+// 16 l of each) and re-distributed through shared memory - NVLink moves large requests at full rate, while
+// per-thread 48-byte records (three 16-byte pieces at a 48-byte stride) cross it as twice as many half-used
+// sectors: measured 140 GB/s that way against 650 GB/s coalesced (scripts/experiments/peer_read_probe.py).
+// The shares are walked in rotated rank order, so every rank reads a different peer at any time.
+// Work is proportional to the records, which the cuts balance - the unit-driven occupancy merge this replaces cost
+// the owner of a sparse key range three times what the others paid (profiles/README.md, round 2).
+__global__ void __launch_bounds__(256)
+merge_pull_mark_kernel(FuseDev f, PeerPtrs peer_records, int rank, int R, const long long* __restrict__ plan,
+                       ulonglong2* __restrict__ staging, long long cap) {
+  __shared__ ulonglong2 s_rec[8][96];  // per warp: 32 records x 48 bytes
+  const GridDev g = *f.grid;
+  if (g.n_units == 0) return;
+  const long long total = min(plan[2], cap);
+  const uint64_t cell_begin = (uint64_t)plan[0] * kOwnUnits * kUnitBits, cell_end = (uint64_t)plan[1] * kOwnUnits * kUnitBits;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long n_warps = (long long)gridDim.x * 8;
+  for (long long w0 = ((long long)blockIdx.x * 8 + warp) * 32; w0 < total; w0 += n_warps * 32) {
+    const long long i = w0 + lane;
+    const bool in = i < total;
+    int kq = 0;
+#pragma unroll
+    for (int k = 1; k < DDN_MAX_PEERS; ++k) kq += (k < R && i >= plan[4 + 2 * DDN_MAX_PEERS + k]) ? 1 : 0;
+    const long long j = plan[4 + kq] + (i - plan[4 + 2 * DDN_MAX_PEERS + kq]);
+    int q = rank + kq;
+    q -= q >= R ? R : 0;
+    const unsigned long long* base = reinterpret_cast<const unsigned long long*>(peer_records.p[q]);
+    // whole warp inside one rank's share (the usual case): three coalesced 512-byte loads and stores
+    const int kq0 = __shfl_sync(0xffffffffu, kq, 0);
+    const bool uniform = __all_sync(0xffffffffu, in && kq == kq0);
+    unsigned long long key = ~0ull;
+    if (uniform) {
+      const long long j0 = __shfl_sync(0xffffffffu, j, 0);
+      const ulonglong2* src = reinterpret_cast<const ulonglong2*>(base + j0 * kRecWords);
+      ulonglong2* dst = staging + w0 * 3;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const ulonglong2 v = __ldcv(src + k * 32 + lane);
+        s_rec[warp][k * 32 + lane] = v;
+        dst[k * 32 + lane] = v;
+      }
+      __syncwarp();
+      key = s_rec[warp][lane * 3].x;
+      __syncwarp();
+    } else if (in) {
+      const ulonglong2* r = reinterpret_cast<const ulonglong2*>(base + j * kRecWords);
+      const ulonglong2 a = __ldcv(r), b = __ldcv(r + 1), c = __ldcv(r + 2);
+      staging[i * 3 + 0] = a, staging[i * 3 + 1] = b, staging[i * 3 + 2] = c;
+      key = a.x;
+    }
+    uint64_t cell = cell_of_key(g, key);
+    if (cell < cell_begin || cell >= cell_end) cell = kNoCell;
+    uint64_t left = __shfl_up_sync(0xffffffffu, cell, 1);
+    if (lane == 0) left = kNoCell;
+    if (cell != kNoCell) set_cell_bit(f.units, f.dirty, cell, left);
+  }
+}
+
+// occupied cells per ownership tile of the owned range (a tile whose scan tile was never touched is empty)
 __global__ void __launch_bounds__(kOwnUnits)
-merge_recount_kernel(FuseDev f, const long long* __restrict__ plan, uint32_t* __restrict__ tile_sums) {
+merge_count_kernel(FuseDev f, const long long* __restrict__ plan, uint32_t* __restrict__ tile_sums) {
   __shared__ int s_warp[kScanThreads / 32];
   const long long n_units = f.grid->n_units;
   const long long t0 = plan[0], t1 = plan[1];
   const uint4* my_units = reinterpret_cast<const uint4*>(f.units);
   for (long long t = t0 + blockIdx.x; t < t1; t += gridDim.x) {
-    if (tile_sums[t - t0] == 0u) continue;  // CTA-uniform: nothing was there
+    if (f.dirty != nullptr && f.dirty[(t * kOwnUnits) / kTileUnits] == 0) {  // CTA-uniform
+      if (threadIdx.x == 0) tile_sums[t - t0] = 0u;
+      continue;
+    }
     const long long ui = t * kOwnUnits + threadIdx.x;
     const int total = block_sum_256(ui < n_units ? popc3(my_units[ui]) : 0, s_warp);
     if (threadIdx.x == 0) tile_sums[t - t0] = (uint32_t)total;
@@ -886,53 +886,17 @@ merge_prefix_kernel(FuseDev f, const long long* __restrict__ plan, const uint32_
   }
 }
 
-// pull + add: a warp handles 32 consecutive records of this rank's share, read straight out of their owner's HBM.
-// The 1536 bytes are fetched as three fully coalesced 512-byte requests (lane l takes bytes 16 l of each) and
-// re-distributed through shared memory - NVLink moves large requests at full rate, while per-thread 48-byte
-// records (three 16-byte pieces at a 48-byte stride) would cross it as twice as many half-used 32-byte sectors:
-// measured 140 GB/s that way against 650 GB/s for coalesced loads (scripts/experiments/peer_read_probe.py).
-// Every record is then looked up in the merged units and added with 64-bit REDs.
+// the staged records (local memory now) are looked up in the merged units and added with 64-bit REDs
 __global__ void __launch_bounds__(256)
-merge_accumulate_kernel(FuseDev f, PeerPtrs peer_records, int rank, int R, const long long* __restrict__ plan,
+merge_accumulate_kernel(FuseDev f, const long long* __restrict__ plan, const ulonglong2* __restrict__ staging, long long cap_records,
                         unsigned long long* __restrict__ accum, long long cap) {
-  __shared__ ulonglong2 s_rec[8][96];  // per warp: 32 records x 48 bytes
   const GridDev g = *f.grid;
   if (g.n_units == 0) return;
-  const long long total = plan[2];
+  const long long total = min(plan[2], cap_records);
   const uint4* units = reinterpret_cast<const uint4*>(f.units);
   const uint64_t cell_begin = (uint64_t)plan[0] * kOwnUnits * kUnitBits, cell_end = (uint64_t)plan[1] * kOwnUnits * kUnitBits;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long n_warps = (long long)gridDim.x * 8;
-  for (long long w0 = ((long long)blockIdx.x * 8 + warp) * 32; w0 < total; w0 += n_warps * 32) {
-    const long long i = w0 + lane;
-    const bool in = i < total;
-    int kq = 0;
-#pragma unroll
-    for (int k = 1; k < DDN_MAX_PEERS; ++k) kq += (k < R && i >= plan[4 + 2 * DDN_MAX_PEERS + k]) ? 1 : 0;
-    const long long j = plan[4 + kq] + (i - plan[4 + 2 * DDN_MAX_PEERS + kq]);
-    int q = rank + kq;
-    q -= q >= R ? R : 0;
-    const unsigned long long* base = reinterpret_cast<const unsigned long long*>(peer_records.p[q]);
-    // whole warp inside one rank's share (the usual case): three coalesced 512-byte loads
-    const int kq0 = __shfl_sync(0xffffffffu, kq, 0);
-    const bool uniform = __all_sync(0xffffffffu, in && kq == kq0);
-    ulonglong2 a, b, c;
-    if (uniform) {
-      const long long j0 = __shfl_sync(0xffffffffu, j, 0);
-      const ulonglong2* src = reinterpret_cast<const ulonglong2*>(base + j0 * kRecWords);
-      s_rec[warp][lane] = __ldcv(src + lane);
-      s_rec[warp][32 + lane] = __ldcv(src + 32 + lane);
-      s_rec[warp][64 + lane] = __ldcv(src + 64 + lane);
-      __syncwarp();
-      a = s_rec[warp][lane * 3 + 0], b = s_rec[warp][lane * 3 + 1], c = s_rec[warp][lane * 3 + 2];
-      __syncwarp();
-    } else {
-      a = b = c = make_ulonglong2(~0ull, 0ull);  // key ~0: no cell
-      if (in) {
-        const ulonglong2* r = reinterpret_cast<const ulonglong2*>(base + j * kRecWords);
-        a = __ldcv(r), b = __ldcv(r + 1), c = __ldcv(r + 2);
-      }
-    }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const ulonglong2 a = __ldg(staging + i * 3), b = __ldg(staging + i * 3 + 1), c = __ldg(staging + i * 3 + 2);
     const uint64_t cell = cell_of_key(g, a.x);
     if (cell == kNoCell || cell < cell_begin || cell >= cell_end) continue;
     const uint32_t slot = slot_of_cell(cell, units);
@@ -984,7 +948,7 @@ static int launch_mark_points(const ddn_fuse_session* s, int64_t n, const float*
 // rank passes over `range` (whole device grid when range.n_tiles < 0): tile counts -> scan -> accumulators
 // cleared -> unit prefixes + keys
 static int launch_rank(const ddn_fuse_session* s, ScanRange range, uint64_t* keys, int key_stride, unsigned long long* zero_base,
-                       int zero_stride, long long cap, uint32_t* own_prefix, uint32_t* own_mask, cudaStream_t st) {
+                       int zero_stride, long long cap, uint32_t* own_prefix, cudaStream_t st) {
   const GridDev* gp = reinterpret_cast<const GridDev*>(s->grid);
   uint4* units = reinterpret_cast<uint4*>(s->units);
   unsigned long long* counts = reinterpret_cast<unsigned long long*>(s->counts);
@@ -996,7 +960,7 @@ static int launch_rank(const ddn_fuse_session* s, ScanRange range, uint64_t* key
   DDN_TRY(after_launch("tile_scan_kernel", st));
   zero_accum_kernel<<<kPersistentCtas, 256, 0, st>>>((ulonglong2*)zero_base, counts, zero_stride, cap);
   DDN_TRY(after_launch("zero_accum_kernel", st));
-  unit_prefix_kernel<<<ctas, kScanThreads, 0, st>>>(gp, units, range, s->tile_sums, keys, key_stride, cap, own_prefix, own_mask);
+  unit_prefix_kernel<<<ctas, kScanThreads, 0, st>>>(gp, units, range, s->tile_sums, keys, key_stride, cap, own_prefix);
   return after_launch("unit_prefix_kernel", st);
 }
 
@@ -1063,7 +1027,6 @@ static int carve_session(const GridDev& g, int64_t n, void* workspace, int64_t w
   s->dirty = nullptr;
   s->tile_sums = reinterpret_cast<uint32_t*>(base + L->tile_sums);
   s->tile_prefix = nullptr;
-  s->tile_mask = nullptr;
   s->counts = counts_out;
   *accum = reinterpret_cast<unsigned long long*>(base + L->accum);
   return DDN_OK;
@@ -1122,7 +1085,7 @@ int ddn_voxel_fuse(const ddn_voxel_grid* grid_host, int64_t n_points, int64_t ro
   DDN_TRY(begin_with_grid(&s, g, st));
   DDN_TRY(launch_mark_points(&s, n_points, xyz, votes, vote_threshold, st));
   const long long cap = (long long)std::min<uint64_t>((uint64_t)n_points, L.cells);
-  DDN_TRY(launch_rank(&s, ScanRange{0, -1}, out_keys, 1, accum, kAccWords, cap, nullptr, nullptr, st));
+  DDN_TRY(launch_rank(&s, ScanRange{0, -1}, out_keys, 1, accum, kAccWords, cap, nullptr, st));
   DDN_TRY(launch_accumulate_points(&s, n_points, row_len, xyz, rgb, votes, vote_threshold, accum, kAccWords, cap, st));
   return launch_finalize(&s, accum, out_keys, cap, out_xyz, out_rgb, out_count, st);
 }
@@ -1174,7 +1137,7 @@ int ddn_voxel_partials(const ddn_voxel_grid* grid_host, int64_t n_points, int64_
   DDN_TRY(launch_mark_points(&s, n_points, xyz, votes, vote_threshold, st));
   unsigned long long* rec = (unsigned long long*)records;
   const long long cap = (long long)n_points;
-  DDN_TRY(launch_rank(&s, ScanRange{0, -1}, (uint64_t*)rec, kRecWords, rec, kRecWords, cap, tile_prefix, nullptr, st));
+  DDN_TRY(launch_rank(&s, ScanRange{0, -1}, (uint64_t*)rec, kRecWords, rec, kRecWords, cap, tile_prefix, st));
   return launch_accumulate_points(&s, n_points, row_len, xyz, rgb, votes, vote_threshold, rec + 1, kRecWords, cap, st);
 }
 
@@ -1217,7 +1180,7 @@ int ddn_voxel_merge(const ddn_voxel_grid* grid_host, int64_t n_records, const ui
   mark_records_kernel<<<blocks, 256, 0, st>>>(fuse_dev(&s), n_records, records, cell_begin, cell_end);
   DDN_TRY(after_launch("mark_records_kernel"));
   const long long cap = (long long)std::min<uint64_t>((uint64_t)n_records, L.cells);
-  DDN_TRY(launch_rank(&s, range, out_keys, 1, accum, kAccWords, cap, nullptr, nullptr, st));
+  DDN_TRY(launch_rank(&s, range, out_keys, 1, accum, kAccWords, cap, nullptr, st));
   accumulate_records_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const GridDev*>(s.grid), n_records,
                                                     (const unsigned long long*)records, reinterpret_cast<const uint4*>(s.units),
                                                     cell_begin, cell_end, accum, cap);
@@ -1244,25 +1207,24 @@ int ddn_voxel_keys(const ddn_voxel_grid* grid_host, int64_t n_points, const floa
 
 // ---- fusion session ------------------------------------------------------------------------------
 int ddn_fuse_session_sizes(int64_t max_cells, int64_t* cap_units, int64_t* units_bytes, int64_t* dirty_bytes,
-                           int64_t* tile_sums_bytes, int64_t* tile_prefix_bytes, int64_t* tile_mask_bytes) {
+                           int64_t* tile_sums_bytes, int64_t* tile_prefix_bytes) {
   using namespace ddn;
   DDN_REQUIRE(max_cells > 0 && (uint64_t)max_cells <= kDenseMaxCells, "max_cells must be in (0, 2^35]");
-  DDN_REQUIRE(cap_units && units_bytes && dirty_bytes && tile_sums_bytes && tile_prefix_bytes && tile_mask_bytes, "null output");
+  DDN_REQUIRE(cap_units && units_bytes && dirty_bytes && tile_sums_bytes && tile_prefix_bytes, "null output");
   const int64_t cu = align_up((max_cells + kUnitBits - 1) / kUnitBits, kTileUnits);
   *cap_units = cu;
   *units_bytes = cu * 16;
   *dirty_bytes = align_up(cu / kTileUnits + 1, 256);
   *tile_sums_bytes = align_up((cu / kOwnUnits + 2) * 4, 256);
   *tile_prefix_bytes = align_up((cu / kOwnUnits + 2) * 4, 256);
-  *tile_mask_bytes = align_up((cu / kOwnUnits + 2) * 32, 256);
   return DDN_OK;
 }
 
-int ddn_fuse_merge_scratch_bytes(int64_t cap_units, int32_t n_ranks, int64_t* bytes_out) {
+int ddn_fuse_merge_scratch_bytes(int64_t cap_units, int32_t n_ranks, int64_t cap_out, int64_t* bytes_out) {
   using namespace ddn;
-  DDN_REQUIRE(bytes_out != nullptr && cap_units > 0 && n_ranks >= 1 && n_ranks <= DDN_MAX_PEERS, "arguments");
+  DDN_REQUIRE(bytes_out != nullptr && cap_units > 0 && n_ranks >= 1 && n_ranks <= DDN_MAX_PEERS && cap_out > 0, "arguments");
   const int64_t stride = cap_units / kOwnUnits + 2;
-  *bytes_out = ((int64_t)(n_ranks + 1) * stride + (int64_t)n_ranks * stride * 8) * 4;
+  *bytes_out = align_up(cap_out * kRecWords * 8, 256) + (int64_t)(n_ranks + 1) * stride * 4 + 256;
   return DDN_OK;
 }
 
@@ -1335,7 +1297,7 @@ int ddn_fuse_finish(const ddn_fuse_session* s, int64_t n_points, int64_t row_len
   cudaStream_t st = (cudaStream_t)stream;
   vote_threshold = std::min(vote_threshold, 255);
   unsigned long long* acc = (unsigned long long*)accum;
-  DDN_TRY(launch_rank(s, ScanRange{0, -1}, out_keys, 1, acc, kAccWords, cap_out, nullptr, nullptr, st));
+  DDN_TRY(launch_rank(s, ScanRange{0, -1}, out_keys, 1, acc, kAccWords, cap_out, nullptr, st));
   if (n_points > 0)
     DDN_TRY(launch_accumulate_points(s, n_points, row_len, xyz, rgb, votes, vote_threshold, acc, kAccWords, cap_out, st));
   return launch_finalize(s, acc, out_keys, cap_out, out_xyz, out_rgb, out_count, st);
@@ -1353,36 +1315,33 @@ int ddn_fuse_finish_partial(const ddn_fuse_session* s, int64_t n_points, int64_t
   cudaStream_t st = (cudaStream_t)stream;
   vote_threshold = std::min(vote_threshold, 255);
   unsigned long long* rec = (unsigned long long*)records;
-  DDN_TRY(launch_rank(s, ScanRange{0, -1}, (uint64_t*)rec, kRecWords, rec, kRecWords, cap_records, s->tile_prefix,
-                      s->tile_prefix != nullptr ? s->tile_mask : nullptr, st));
+  DDN_TRY(launch_rank(s, ScanRange{0, -1}, (uint64_t*)rec, kRecWords, rec, kRecWords, cap_records, s->tile_prefix, st));
   if (n_points == 0) return DDN_OK;
   return launch_accumulate_points(s, n_points, row_len, xyz, rgb, votes, vote_threshold, rec + 1, kRecWords, cap_records, st);
 }
 
-int ddn_fuse_merge_peers(const ddn_fuse_session* s, int32_t rank, int32_t n_ranks, const void* const* peer_units_host,
-                         const void* const* peer_records_host, const void* const* peer_tile_prefix_host,
-                         const void* const* peer_tile_mask_host, int64_t* plan, uint32_t* prefix_scratch,
-                         const float* drop_xyz, int64_t n_drop, uint64_t* out_keys, float* out_xyz,
-                         uint8_t* out_rgb, int32_t* out_count, int64_t cap_out, void* accum, int64_t accum_bytes, void* stream) {
+int ddn_fuse_merge_peers(const ddn_fuse_session* s, int32_t rank, int32_t n_ranks, const void* const* peer_records_host,
+                         const void* const* peer_tile_prefix_host, int64_t* plan, void* scratch, int64_t scratch_bytes,
+                         const float* drop_xyz, int64_t n_drop, uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb,
+                         int32_t* out_count, int64_t cap_out, void* accum, int64_t accum_bytes, void* stream) {
   using namespace ddn;
   DDN_REQUIRE(n_drop >= 0 && n_drop < (1ll << 31) - 1024 && (n_drop == 0 || drop_xyz != nullptr), "drop points");
   DDN_TRY(session_check(s));
   DDN_REQUIRE(n_ranks >= 1 && n_ranks <= DDN_MAX_PEERS && rank >= 0 && rank < n_ranks, "rank / n_ranks");
-  DDN_REQUIRE(peer_units_host && peer_records_host && peer_tile_prefix_host && peer_tile_mask_host && plan && prefix_scratch,
-              "null pointer");
+  DDN_REQUIRE(peer_records_host && peer_tile_prefix_host && plan && scratch, "null pointer");
   DDN_REQUIRE(cap_out > 0 && cap_out < (1ll << 31), "cap_out");
   DDN_REQUIRE(out_keys && out_xyz && out_rgb && out_count && accum, "null pointer");
   DDN_REQUIRE(accum_bytes >= cap_out * kAccWords * 8 + 16 && (uintptr_t)accum % 16 == 0, "accumulator scratch");
-  PeerPtrs pu, pr, pp, pm;
+  int64_t need = 0;
+  DDN_TRY(ddn_fuse_merge_scratch_bytes(s->cap_units, n_ranks, cap_out, &need));
+  DDN_REQUIRE(scratch_bytes >= need && (uintptr_t)scratch % 16 == 0, "merge scratch too small (ddn_fuse_merge_scratch_bytes)");
+  PeerPtrs pr, pp;
   for (int q = 0; q < DDN_MAX_PEERS; ++q) {
-    pu.p[q] = q < n_ranks ? peer_units_host[q] : nullptr;
     pr.p[q] = q < n_ranks ? peer_records_host[q] : nullptr;
     pp.p[q] = q < n_ranks ? peer_tile_prefix_host[q] : nullptr;
-    pm.p[q] = q < n_ranks ? peer_tile_mask_host[q] : nullptr;
-    if (q < n_ranks) DDN_REQUIRE(pu.p[q] && pr.p[q] && pp.p[q] && pm.p[q], "null peer pointer");
+    if (q < n_ranks) DDN_REQUIRE(pr.p[q] && pp.p[q], "null peer pointer");
   }
-  DDN_REQUIRE(pu.p[rank] == s->units && pp.p[rank] == (const void*)s->tile_prefix && pm.p[rank] == (const void*)s->tile_mask,
-              "entry `rank` must be the session's own buffers");
+  DDN_REQUIRE(pp.p[rank] == (const void*)s->tile_prefix, "entry `rank` must be the session's own buffers");
   cudaStream_t st = (cudaStream_t)stream;
   const GridDev* gp = reinterpret_cast<const GridDev*>(s->grid);
   const FuseDev f = fuse_dev(s);
@@ -1390,29 +1349,29 @@ int ddn_fuse_merge_peers(const ddn_fuse_session* s, int32_t rank, int32_t n_rank
   long long* planll = reinterpret_cast<long long*>(plan);
   unsigned long long* acc = (unsigned long long*)accum;
   const long long stride = (long long)(s->cap_units / kOwnUnits + 2);
-  uint32_t* local = prefix_scratch;                               // [(R + 1) * stride] prefixes + their sum
-  uint32_t* masks = prefix_scratch + (long long)(n_ranks + 1) * stride;  // [R * stride * 8] worst case
+  ulonglong2* staging = reinterpret_cast<ulonglong2*>(scratch);                                         // [cap_out] records
+  uint32_t* local = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(scratch) + align_up(cap_out * kRecWords * 8, 256));  // [(R + 1) * stride]
   merge_gather_prefix_kernel<<<kNumSMs * 2, 256, 0, st>>>(gp, pp, n_ranks, local, stride);
   DDN_TRY(after_launch("merge_gather_prefix_kernel", st));
   merge_plan_kernel<<<1, 32, 0, st>>>(gp, local, stride, rank, n_ranks, planll);
   DDN_TRY(after_launch("merge_plan_kernel", st));
-  merge_gather_mask_kernel<<<kNumSMs * 2, 256, 0, st>>>(pm, n_ranks, planll, local, stride, masks, s->tile_sums);
-  DDN_TRY(after_launch("merge_gather_mask_kernel", st));
-  merge_or_kernel<<<kPersistentCtas, kOwnUnits, 0, st>>>(f, pu, rank, n_ranks, planll, local, stride, masks, s->tile_sums);
-  DDN_TRY(after_launch("merge_or_kernel", st));
-  if (n_drop > 0) {  // N5: cells of the sparse cloud leave the merged occupancy; tile counts again
+  merge_clear_kernel<<<kPersistentCtas, kOwnUnits, 0, st>>>(f, planll);
+  DDN_TRY(after_launch("merge_clear_kernel", st));
+  merge_pull_mark_kernel<<<kPersistentCtas, 256, 0, st>>>(f, pr, rank, n_ranks, planll, staging, cap_out);
+  DDN_TRY(after_launch("merge_pull_mark_kernel", st));
+  if (n_drop > 0) {  // N5: the cells of the sparse cloud leave the merged occupancy
     unmark_points_kernel<<<(unsigned)((n_drop + 255) / 256), 256, 0, st>>>(f, n_drop, drop_xyz, planll);
     DDN_TRY(after_launch("unmark_points_kernel", st));
-    merge_recount_kernel<<<kPersistentCtas, kOwnUnits, 0, st>>>(f, planll, s->tile_sums);
-    DDN_TRY(after_launch("merge_recount_kernel", st));
   }
+  merge_count_kernel<<<kPersistentCtas, kOwnUnits, 0, st>>>(f, planll, s->tile_sums);
+  DDN_TRY(after_launch("merge_count_kernel", st));
   tile_scan_kernel<<<1, 1024, 0, st>>>(gp, ScanRange{0, 0}, planll, s->tile_sums, counts);
   DDN_TRY(after_launch("tile_scan_kernel", st));
   zero_accum_kernel<<<kPersistentCtas, 256, 0, st>>>((ulonglong2*)acc, counts, kAccWords, cap_out);
   DDN_TRY(after_launch("zero_accum_kernel", st));
   merge_prefix_kernel<<<kPersistentCtas, kOwnUnits, 0, st>>>(f, planll, s->tile_sums, out_keys, cap_out);
   DDN_TRY(after_launch("merge_prefix_kernel", st));
-  merge_accumulate_kernel<<<kPersistentCtas, 256, 0, st>>>(f, pr, rank, n_ranks, planll, acc, cap_out);
+  merge_accumulate_kernel<<<kPersistentCtas, 256, 0, st>>>(f, planll, staging, cap_out, acc, cap_out);
   DDN_TRY(after_launch("merge_accumulate_kernel", st));
   return launch_finalize(s, acc, out_keys, cap_out, out_xyz, out_rgb, out_count, st);
 }

@@ -212,31 +212,29 @@ class ShardedDensifier:
             self._make_session()
 
     def _make_session(self) -> None:
-        """Fusion session of this rank; with peers its occupancy units and tile prefix live in symmetric memory so
-        the owner-side merge of every other rank can read them over NVLink."""
+        """Fusion session of this rank; with peers its tile prefix (and the partial records) live in symmetric memory
+        so the owner-side merge of every other rank can read them over NVLink."""
         cfg = self.cfg
         if self.peer is None:
             self.session = ops.FuseSession(self.device, cfg.max_grid_cells)
             return
 
         def alloc(name, nbytes):
-            if name in ("units", "tile_prefix", "tile_mask"):
+            if name == "tile_prefix":
                 return self.peer.buffer("fuse_" + name, (nbytes,), torch.uint8)[0]
             return None
 
         self.session = ops.FuseSession(self.device, cfg.max_grid_cells, tile_prefix=True, alloc=alloc)
         ptrs = lambda name, shape, dt: [int(v.data_ptr()) for v in self.peer.buffer(name, shape, dt)[2]]
-        self._peer_units = ptrs("fuse_units", (self.session.units.numel(),), torch.uint8)
         self._peer_prefix = ptrs("fuse_tile_prefix", (self.session.tile_prefix.numel(),), torch.uint8)
-        self._peer_mask = ptrs("fuse_tile_mask", (self.session.tile_mask.numel(),), torch.uint8)
         self._peer_records = ptrs("records", tuple(self.peer_records_shape), torch.int64)
         self._peer_bbox = [ptrs(f"bbox{par}", (64,), torch.int32) for par in (0, 1)]
         self._plan = torch.zeros(64, dtype=torch.int64, device=self.device)
-        self.session.merge_scratch(self.world)
         # a rank's share of the merged voxels: the cuts balance the global record count, up to one tile per rank
         n_max = self._local_max * self.Hs * self.Ws
         self._cap_merge = n_max + 24576 * self.world + 1024
         self._merge_out = ops.new_voxel_outputs(self._cap_merge, self.device)
+        self.session.merge_scratch(self.world, self._cap_merge)
 
     # -- exchange steps -------------------------------------------------------------------------------
     def _exchange_halo(self, refined_slots: torch.Tensor) -> None:
@@ -473,8 +471,7 @@ class ShardedDensifier:
         mark("fuse_partials", lambda: self.ops.fuse_finish_partial(sess, *flat, self.thr, rec, row_len=xyz.shape[2]))
         hdl.barrier()  # every rank's units, tile prefix and records are complete
         k, x, c, n, counts = mark("fuse_merge", lambda: self.ops.fuse_merge_peers(
-            sess, self.rank, self.world, self._peer_units, self._peer_records, self._peer_prefix, self._peer_mask, self._plan,
-            self._cap_merge, out=self._merge_out, drop_xyz=drop))
+            sess, self.rank, self.world, self._peer_records, self._peer_prefix, self._plan, self._cap_merge, out=self._merge_out, drop_xyz=drop))
         return k, x, c, n, counts.clone()
 
     def _nbr_full(self) -> torch.Tensor:

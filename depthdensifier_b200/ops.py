@@ -268,9 +268,9 @@ class FuseSession:
         if not torch.cuda.is_available():
             raise DDNError("no CUDA device available: depthdensifier_b200 has no CPU fallback")
         self.device = torch.device(device)
-        sizes = [C.c_int64(0) for _ in range(6)]
+        sizes = [C.c_int64(0) for _ in range(5)]
         _lib.check(lib.ddn_fuse_session_sizes(int(max_cells), *[C.byref(x) for x in sizes]))
-        cap_units, units_b, dirty_b, sums_b, prefix_b, mask_b = (x.value for x in sizes)
+        cap_units, units_b, dirty_b, sums_b, prefix_b = (x.value for x in sizes)
         self.max_cells, self.cap_units = int(max_cells), cap_units
         self.n_own_cap = cap_units // 256 + 2
 
@@ -285,13 +285,11 @@ class FuseSession:
         self.dirty = get("dirty", dirty_b) if dirty else None
         self.tile_sums = get("tile_sums", sums_b)
         self.tile_prefix = get("tile_prefix", prefix_b) if tile_prefix else None
-        self.tile_mask = get("tile_mask", mask_b) if tile_prefix else None
         self.grid = torch.zeros(16, dtype=torch.int32, device=self.device)
         self.counts = torch.zeros(2, dtype=torch.int64, device=self.device)
         self.c = _lib.FuseSession(self.grid.data_ptr(), self.units.data_ptr(), cap_units,
                                   self.dirty.data_ptr() if self.dirty is not None else None, self.tile_sums.data_ptr(),
-                                  self.tile_prefix.data_ptr() if self.tile_prefix is not None else None,
-                                  self.tile_mask.data_ptr() if self.tile_mask is not None else None, self.counts.data_ptr())
+                                  self.tile_prefix.data_ptr() if self.tile_prefix is not None else None, self.counts.data_ptr())
         self._accum = None
         with torch.cuda.device(self.device):
             _lib.check(lib.ddn_fuse_session_reset(C.byref(self.c), _stream()))
@@ -328,12 +326,12 @@ class FuseSession:
             g.origin[i], g.bits[i], g.dims[i] = st.origin[i], st.bits[i], st.dims[i]
         return g
 
-    def merge_scratch(self, world: int) -> torch.Tensor:
-        """Scratch of fuse_merge_peers for ``world`` ranks (allocated once per session)."""
-        if getattr(self, "_merge_scratch", None) is None or self._merge_scratch[0] != world:
+    def merge_scratch(self, world: int, cap_out: int) -> torch.Tensor:
+        """Scratch of fuse_merge_peers for ``world`` ranks and ``cap_out`` records (allocated once per session)."""
+        if getattr(self, "_merge_scratch", None) is None or self._merge_scratch[0] != (world, cap_out):
             nbytes = C.c_int64(0)
-            _lib.check(_lib.load().ddn_fuse_merge_scratch_bytes(self.cap_units, int(world), C.byref(nbytes)))
-            self._merge_scratch = (world, torch.empty(nbytes.value, dtype=torch.uint8, device=self.device))
+            _lib.check(_lib.load().ddn_fuse_merge_scratch_bytes(self.cap_units, int(world), int(cap_out), C.byref(nbytes)))
+            self._merge_scratch = ((world, cap_out), torch.empty(nbytes.value, dtype=torch.uint8, device=self.device))
         return self._merge_scratch[1]
 
     def accum(self, cap_out: int) -> torch.Tensor:
@@ -392,20 +390,20 @@ def fuse_finish_partial(sess: FuseSession, xyz, rgb, votes, vote_threshold: int,
     return sess.counts
 
 
-def fuse_merge_peers(sess: FuseSession, rank: int, world: int, peer_units, peer_records, peer_tile_prefix, peer_tile_mask, plan,
-                     cap_out: int, out=None, drop_xyz=None):
+def fuse_merge_peers(sess: FuseSession, rank: int, world: int, peer_records, peer_tile_prefix, plan, cap_out: int, out=None,
+                     drop_xyz=None):
     """Owner-side exchange + merge over peer memory.  ``peer_*``: per rank, the device address of that rank's
-    units / records / tile prefix as mapped into this process.  ``drop_xyz`` [n,3] f32: N5, the sparse points of
+    records / tile prefix as mapped into this process.  ``drop_xyz`` [n,3] f32: N5, the sparse points of
     ALL ranks whose cells are removed from the merged occupancy.  Returns keys, xyz, rgb, count, counts."""
     lib = _lib.load()
     dev = sess.device
     k, x, c, n = out if out is not None else new_voxel_outputs(cap_out, dev)
     acc = sess.accum(cap_out)
-    prefix_scratch = sess.merge_scratch(world)
+    scratch = sess.merge_scratch(world, cap_out)
     arr = lambda ptrs: (C.c_void_p * world)(*[int(v) for v in ptrs])
     with torch.cuda.device(dev):
-        _lib.check(lib.ddn_fuse_merge_peers(C.byref(sess.c), int(rank), int(world), arr(peer_units), arr(peer_records),
-                                            arr(peer_tile_prefix), arr(peer_tile_mask), _p(plan), _p(prefix_scratch), _p(drop_xyz),
+        _lib.check(lib.ddn_fuse_merge_peers(C.byref(sess.c), int(rank), int(world), arr(peer_records), arr(peer_tile_prefix),
+                                            _p(plan), _p(scratch), scratch.numel(), _p(drop_xyz),
                                             0 if drop_xyz is None else drop_xyz.shape[0], _p(k), _p(x), _p(c), _p(n), int(cap_out),
                                             _p(acc), acc.numel(), _stream()))
     return k, x, c, n, sess.counts

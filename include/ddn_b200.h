@@ -302,16 +302,15 @@ typedef struct ddn_fuse_session { /* HOST struct of DEVICE pointers, owned by th
   uint32_t* tile_sums;   /* [cap_units / 256 + 2] scratch */
   uint32_t* tile_prefix; /* [cap_units / 256 + 2] or NULL: index of the first record of every ownership tile
                             (256 units = 24,576 cells in key order); needed by ddn_fuse_merge_peers */
-  uint32_t* tile_mask;   /* [(cap_units / 256 + 2) * 8] with tile_prefix, else NULL: per ownership tile, which of its
-                            256 units are non-empty - an owner reads only those units of a peer */
   int64_t* counts;       /* [2]: participating points, voxels (the true count even when it exceeds a capacity) */
 } ddn_fuse_session;
 
 /* Sizes of the session buffers for grids of up to max_cells cells (all outputs in bytes but cap_units). */
 DDN_API int ddn_fuse_session_sizes(int64_t max_cells, int64_t* cap_units, int64_t* units_bytes, int64_t* dirty_bytes,
-                           int64_t* tile_sums_bytes, int64_t* tile_prefix_bytes, int64_t* tile_mask_bytes);
-/* Size of ddn_fuse_merge_peers' prefix_scratch for a session of cap_units units and n_ranks ranks. */
-DDN_API int ddn_fuse_merge_scratch_bytes(int64_t cap_units, int32_t n_ranks, int64_t* bytes_out);
+                           int64_t* tile_sums_bytes, int64_t* tile_prefix_bytes);
+/* Size of ddn_fuse_merge_peers' scratch for a session of cap_units units, n_ranks ranks and an output capacity of
+ * cap_out voxels (= the most records this rank can receive). */
+DDN_API int ddn_fuse_merge_scratch_bytes(int64_t cap_units, int32_t n_ranks, int64_t cap_out, int64_t* bytes_out);
 /* Once after allocation (and after any error): clears units and flags. */
 DDN_API int ddn_fuse_session_reset(const ddn_fuse_session* s, void* stream);
 /* Opens a step: grid from the n_boxes (<= DDN_MAX_PEERS) bounding boxes bbox_ptrs_host[i] (HOST array of
@@ -339,23 +338,22 @@ DDN_API int ddn_fuse_finish(const ddn_fuse_session* s, int64_t n_points, int64_t
 DDN_API int ddn_fuse_finish_partial(const ddn_fuse_session* s, int64_t n_points, int64_t row_len, const float* xyz,
                             const uint8_t* rgb, const uint8_t* votes, int32_t vote_threshold, uint64_t* records,
                             int64_t cap_records, void* stream);
-/* Owner-side exchange + merge over PEER MEMORY (NVLink loads inside the kernels, no staging copy, no host
- * plan).  Every rank calls it after all ranks finished ddn_fuse_finish_partial on the same grid (the caller
- * provides that barrier).  peer_*_host: HOST arrays of n_ranks device pointers - every rank's units, records,
- * tile_prefix and tile_mask as mapped into this process (entry `rank` = the local buffers).  The ranks split the
- * tiles that hold records into n_ranks contiguous ranges balancing the global record count (each computes the
- * same cuts from the summed prefixes); this rank ORs the occupancy of its range over all ranks (reading only the
- * units their masks name), ranks it, pulls its share of every rank's records and adds them, and finalises.  plan: device scratch [64] i64 (out: [0],[1] = tile range,
- * [2] = records received); prefix_scratch: device scratch of ddn_fuse_merge_scratch_bytes (local copies of every rank's tile prefix and of the unit masks of the owned tiles, fetched in bulk so that no decision waits on a chain of remote reads).  drop_xyz [n_drop,3] f32
- * (optional, n_drop = 0: none): N5 at the owner - the cells of these points (ALL ranks' sparse points) leave the
- * merged occupancy before it is ranked.  Outputs as ddn_fuse_finish.  The rank-ordered concatenation of the
- * outputs is globally key-sorted. */
-DDN_API int ddn_fuse_merge_peers(const ddn_fuse_session* s, int32_t rank, int32_t n_ranks, const void* const* peer_units_host,
-                         const void* const* peer_records_host, const void* const* peer_tile_prefix_host,
-                         const void* const* peer_tile_mask_host, int64_t* plan, uint32_t* prefix_scratch,
-                         const float* drop_xyz, int64_t n_drop, uint64_t* out_keys,
-                         float* out_xyz, uint8_t* out_rgb, int32_t* out_count, int64_t cap_out, void* accum,
-                         int64_t accum_bytes, void* stream);
+/* Owner-side exchange + merge over PEER MEMORY (NVLink loads inside the kernels, no host plan).  Every rank calls
+ * it after all ranks finished ddn_fuse_finish_partial on the same grid (the caller provides that barrier).
+ * peer_*_host: HOST arrays of n_ranks device pointers - every rank's records and tile_prefix as mapped into this
+ * process (entry `rank` = the local buffers).  The ranks split the tiles that hold records into n_ranks contiguous
+ * ranges balancing the global record count (each computes the same cuts from the summed prefixes, which it first
+ * copies into local memory in one bulk pass); this rank pulls its share of every rank's sorted records ONCE -
+ * coalesced 512-byte requests, peers visited in rotated order - into local staging, setting the occupancy bit of
+ * every record on the way, then ranks the occupancy of its range, adds the staged records and finalises.
+ * plan: device scratch [64] i64 (out: [0],[1] = tile range, [2] = records received); scratch: device,
+ * ddn_fuse_merge_scratch_bytes, 16-byte aligned.  drop_xyz [n_drop,3] f32 (optional, n_drop = 0: none): N5 at the
+ * owner - the cells of these points (ALL ranks' sparse points) leave the merged occupancy before it is ranked.
+ * Outputs as ddn_fuse_finish.  The rank-ordered concatenation of the outputs is globally key-sorted. */
+DDN_API int ddn_fuse_merge_peers(const ddn_fuse_session* s, int32_t rank, int32_t n_ranks, const void* const* peer_records_host,
+                         const void* const* peer_tile_prefix_host, int64_t* plan, void* scratch, int64_t scratch_bytes,
+                         const float* drop_xyz, int64_t n_drop, uint64_t* out_keys, float* out_xyz, uint8_t* out_rgb,
+                         int32_t* out_count, int64_t cap_out, void* accum, int64_t accum_bytes, void* stream);
 
 /* Stand-alone pieces of stage 4 (used by the multi-GPU path and by tests). */
 DDN_API int ddn_voxel_keys(const ddn_voxel_grid* grid_host, int64_t n_points, const float* xyz,

@@ -63,10 +63,8 @@ def main():
             records.append(rec)
         torch.cuda.synchronize()
         n_local = [int(s.counts[1]) for s in sessions]
-        pu = [s.units.data_ptr() for s in sessions]
-        pp = [s.tile_prefix.data_ptr() for s in sessions]
-        pm = [s.tile_mask.data_ptr() for s in sessions]
-        pr = [t.data_ptr() for t in records]
+            pp = [s.tile_prefix.data_ptr() for s in sessions]
+            pr = [t.data_ptr() for t in records]
         cap = max(b - a for a, b in bounds) * P + 24576 * R + 1024
         outs, times, recv = [], [], []
         for r in range(R):  # every rank once (the merge rewrites the rank's own units inside its range only)
@@ -74,7 +72,7 @@ def main():
             out = ops.new_voxel_outputs(cap, dev)
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
             ev[0].record()
-            k, x, c, m, counts = ops.fuse_merge_peers(sessions[r], r, R, pu, pr, pp, pm, plan, cap, out=out)
+            k, x, c, m, counts = ops.fuse_merge_peers(sessions[r], r, R, pr, pp, plan, cap, out=out)
             ev[1].record()
             torch.cuda.synchronize()
             times.append(ev[0].elapsed_time(ev[1]))

@@ -12,6 +12,6 @@ try:
     print("g8 weak", round(d["ms_per_step"],3), d["path"], {k:round(v,3) for k,v in d["stages_ms"].items()})
     print("check", d["multi_gpu_check"] and (d["multi_gpu_check"]["passed"], d["multi_gpu_check"]["path"]))
     s=d["strong"]; print("strong", round(s["ms_per_step"],3), {k:round(v,3) for k,v in s["stages_ms"].items()})
-    print("kernels", s.get("stage4_kernels_ms"))
+    print("kernels", s.get("stage4_kernels_ms")); print("per rank", s.get("stage4_kernels_ms_per_rank")); print("host", s.get("host_enqueue_ms_per_step"), d.get("host_enqueue_ms_per_step"))
 except Exception as e: print("ERR", e)
 PY

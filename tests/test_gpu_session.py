@@ -170,15 +170,13 @@ def test_merge_peers_virtual_ranks(lib_built, R):
     torch.cuda.synchronize()
     n_local = [int(s.counts[1]) for s in sessions]
     assert sum(int(s.counts[0]) for s in sessions) == int(one[4][0])
-    pu = [s.units.data_ptr() for s in sessions]
     pp = [s.tile_prefix.data_ptr() for s in sessions]
-    pm = [s.tile_mask.data_ptr() for s in sessions]
     pr = [t.data_ptr() for t in records]
     cap = n
     outs, plans = [], []
     for r in range(R):
         plan = torch.zeros(64, dtype=torch.int64, device="cuda")
-        k, x, c, m, counts = ops.fuse_merge_peers(sessions[r], r, R, pu, pr, pp, pm, plan, cap)
+        k, x, c, m, counts = ops.fuse_merge_peers(sessions[r], r, R, pr, pp, plan, cap)
         mv = int(counts[1])
         outs.append((k[:mv].clone(), x[:mv].clone(), c[:mv].clone(), m[:mv].clone()))
         plans.append(plan.cpu().tolist())
