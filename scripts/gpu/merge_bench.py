@@ -63,8 +63,8 @@ def main():
             records.append(rec)
         torch.cuda.synchronize()
         n_local = [int(s.counts[1]) for s in sessions]
-            pp = [s.tile_prefix.data_ptr() for s in sessions]
-            pr = [t.data_ptr() for t in records]
+        pp = [s.tile_prefix.data_ptr() for s in sessions]
+        pr = [t.data_ptr() for t in records]
         cap = max(b - a for a, b in bounds) * P + 24576 * R + 1024
         outs, times, recv = [], [], []
         for r in range(R):  # every rank once (the merge rewrites the rank's own units inside its range only)
