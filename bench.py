@@ -38,6 +38,8 @@ WORKLOADS = {
     "cfg4": (1000, 1600, 1200, 10, 4096, "BASELINE configs[3]: 1000 views at 1600x1200, K=10, 1 cm voxels (use --scaling strong on 8 GPUs)"),
     "cfg5": (300, 3840, 2160, 8, 4096, "BASELINE configs[4]: 300 views at 3840x2160 (4K), K=8 assumed, 1 cm voxels (--scaling strong, 8 GPUs)"),
     "cfg5_slice": (24, 3840, 2160, 8, 4096, "24 of the 300 4K views of BASELINE configs[4] on one GPU (shape coverage, not a BASELINE config)"),
+    "cfg4_quarter": (250, 1600, 1200, 10, 4096, "a quarter of BASELINE configs[3] (250 of 1000 views): on 2 GPUs the per-rank footprint of cfg4 on 8"),
+    "cfg5_quarter": (76, 3840, 2160, 8, 4096, "a quarter of BASELINE configs[4] (76 of 300 4K views): on 2 GPUs the per-rank footprint of cfg5 on 8"),
     "cfg3_25": (25, 1920, 1080, 8, 4096, "one rank's share of BASELINE configs[2] on 8 GPUs (25 of 200 views; kernel timing only)"),
     "small": (12, 320, 240, 4, 1024, "smoke-sized scene (not a BASELINE config)"),
 }
@@ -130,6 +132,8 @@ def cpu_port_sample(workload: str, n_sample_views: int | None = None, repeats: i
 
     V, W, H, K, C, _ = WORKLOADS[workload]
     n = min(max(n_sample_views or 0, K + 1), V)
+    if workload == "cfg1":
+        n = V  # the one configuration the reference's CPU path runs whole: all 20 views
     k = min(K, n - 1)
     sc = make_scene(SceneConfig(n_views=V, width=W, height=H, n_sparse=C, seed=0), device="cpu", views=range(n))
     poses = sc.cam_from_world.numpy()[:n]
