@@ -233,7 +233,7 @@ class ShardedDensifier:
         # a rank's share of the merged voxels: the cuts balance the global record count, up to one tile per rank
         n_max = self._local_max * self.Hs * self.Ws
         self._cap_merge = n_max + 24576 * self.world + 1024
-        self._merge_out = ops.new_voxel_outputs(self._cap_merge, self.device)
+        self._merge_out = [ops.new_voxel_outputs(self._cap_merge, self.device), None]  # second set: pipelined host calls
         self.session.merge_scratch(self.world, self._cap_merge)
 
     # -- exchange steps -------------------------------------------------------------------------------
@@ -436,6 +436,11 @@ class ShardedDensifier:
             mark("backproject_filter", lambda: k4(0, self.n_local))
         return xyz, votes, bbox
 
+    def _merge_outputs(self, slot: int):
+        if self._merge_out[slot] is None:
+            self._merge_out[slot] = ops.new_voxel_outputs(self._cap_merge, self.device)
+        return self._merge_out[slot]
+
     def _sparse_for_dedup(self, sparse_xyz):
         """N5: float32 sparse points of ALL ranks (padded with NaN, which falls into no cell).  The per-rank
         capacity is agreed once (the only host wait, first call)."""
@@ -454,7 +459,7 @@ class ShardedDensifier:
         dist.all_gather_into_tensor(allp, pad, group=self.group)
         return allp
 
-    def _fuse_device(self, xyz, rgb, votes, mark=None, drop=None):
+    def _fuse_device(self, xyz, rgb, votes, mark=None, drop=None, out_slot: int = 0):
         """Stage 4 on the device path.  One rank: rank + accumulate + finalise.  R ranks: partial records into
         peer-visible memory, one barrier, then the owner-side merge that reads the peers' units and records over
         NVLink.  Returns persistent output buffers (valid until the next step) and a snapshot of the counts."""
@@ -585,19 +590,24 @@ class ShardedDensifier:
         return tuple(t.contiguous().pin_memory() for t in (depth, normal, mask, rgb, sparse_xyz, sparse_offsets))
 
     def _host_state(self, sparse_xyz, sparse_offsets):
-        """Device staging buffers, copy stream and pinned output buffers, created once."""
+        """Copy streams and TWO sets of device staging / pinned result buffers (a call uses the set its predecessor
+        did not), created once: the uploads of one call overlap the kernels and the downloads of the previous one."""
         if self._host_out is None:
             n, H, W, dev = self.n_local, self.H, self.W, self.device
-            self._host_out = {
-                "copy": torch.cuda.Stream(device=dev),
-                "depth": torch.empty((n, H, W), dtype=torch.float32, device=dev),
-                "mask": torch.empty((n, H, W), dtype=torch.bool, device=dev),
-                "rgb": torch.empty((n, H, W, 3), dtype=torch.uint8, device=dev),
-                "normal": None,
-                "sparse_xyz": torch.empty(tuple(sparse_xyz.shape), dtype=torch.float64, device=dev),
-                "sparse_offsets": torch.empty(tuple(sparse_offsets.shape), dtype=torch.int64, device=dev),
-                "out": None,
-            }
+
+            def slot():
+                return {"depth": torch.empty((n, H, W), dtype=torch.float32, device=dev),
+                        "mask": torch.empty((n, H, W), dtype=torch.bool, device=dev),
+                        "rgb": torch.empty((n, H, W, 3), dtype=torch.uint8, device=dev),
+                        "normal": None,
+                        "sparse_xyz": torch.empty(tuple(sparse_xyz.shape), dtype=torch.float64, device=dev),
+                        "sparse_offsets": torch.empty(tuple(sparse_offsets.shape), dtype=torch.int64, device=dev),
+                        "small": torch.zeros(32, dtype=torch.int64).pin_memory(),  # counts [2] + grid state [8 x i64]
+                        "free": None,  # event: the kernels that read this set's staging buffers have finished
+                        "out": None}
+
+            self._host_out = {"copy": torch.cuda.Stream(device=dev), "d2h": torch.cuda.Stream(device=dev), "slots": [slot(), slot()],
+                              "next": 0}
         return self._host_out
 
     def _pinned_out(self, st, mv):
@@ -613,21 +623,32 @@ class ShardedDensifier:
 
     def run_host(self, depth, normal, mask, rgb, sparse_xyz, sparse_offsets, normals_in_place: bool = True,
                  chunk_views: int = 16):
-        """Public end-to-end call: host arrays of the rank's own views in, fused cloud back on the host.
+        """Public end-to-end call: host arrays of the rank's own views in, fused cloud back on the host
+        (= ``collect_host(submit_host(...))``; a stream of scenes should call the two halves itself, submitting
+        scene i+1 before collecting scene i, so that uploads, kernels and downloads of neighbouring scenes overlap).
 
         Inputs should be pinned (``pin_host_inputs``).  The copy engine and the kernels overlap: depth and
         mask travel in chunks of ``chunk_views`` views and each chunk is aligned as soon as it has landed;
         colours follow while the consistency kernel runs.  With ``normals_in_place`` the normal maps stay
         in pinned host memory and the consistency kernel reads, over PCIe, only the normals of its vote
         candidates (a few percent of the pixels) instead of moving 12 B/pixel to the device.  The fused
-        cloud returns through pinned buffers (views into them: valid until the next call)."""
+        cloud returns through pinned buffers (views into them: valid until the call after the next)."""
+        return self.collect_host(self.submit_host(depth, normal, mask, rgb, sparse_xyz, sparse_offsets, normals_in_place, chunk_views))
+
+    def submit_host(self, depth, normal, mask, rgb, sparse_xyz, sparse_offsets, normals_in_place: bool = True,
+                    chunk_views: int = 16) -> dict:
+        """First half of ``run_host``: enqueues the uploads and every kernel of the step and returns a ticket without
+        waiting for anything."""
         cfg = self.cfg
         if self.device.type != "cuda":
             raise ops.DDNError("run_host needs a CUDA device")
-        st = self._host_state(sparse_xyz, sparse_offsets)
+        hs = self._host_state(sparse_xyz, sparse_offsets)
+        st = hs["slots"][hs["next"]]
+        hs["next"] ^= 1
         comp = torch.cuda.current_stream(self.device)
-        copy = st["copy"]
-        copy.wait_stream(comp)  # the previous call is done with the staging buffers
+        copy = hs["copy"]
+        if st["free"] is not None:
+            copy.wait_event(st["free"])  # the call before the previous one is done with this set's staging buffers
         n = self.n_local
         if self._max_sparse is None:
             off = sparse_offsets.numpy()
@@ -675,44 +696,75 @@ class ShardedDensifier:
             ev_rgb.record(copy)
         xyz, votes, bbox = self._halo_and_filter(refined_slots, normal_arg, lambda name, fn: fn(), pair, src,
                                                  wait_normal=lambda: comp.wait_event(ev_n), box=box)
-        out = {"h2d_bytes": h2d, "d2h_bytes": 0, "num_points": 0, "stats": torch.cat(stats) if stats else None}
-        if not fuse:
-            torch.cuda.synchronize(self.device)
-            return out
+        ticket = {"slot": st, "h2d_bytes": h2d, "stats": torch.cat(stats) if stats else None, "fused": None, "host_grid": None}
         s = cfg.filter.stride
-        grid = None
-        if self.device_path:
+        if fuse and self.device_path:
             comp.wait_event(ev_rgb)
             rgb_s = st["rgb"] if s == 1 else st["rgb"][:, ::s, ::s].contiguous()
             drop = self._sparse_for_dedup(st["sparse_xyz"]) if cfg.dedup_sparse else None
-            k, x, c, m, counts = self._fuse_device(xyz, rgb_s, votes, drop=drop)
-            st_grid = self.session.grid_state()  # the one wait of the call: the host needs the voxel count to copy back
-            if st_grid.status == 1:
-                return out
-            grid = self.session.host_grid()
-        else:
+            # (with peers the merge writes into persistent buffers: each staging set has its own)
+            k, x, c, m, counts = self._fuse_device(xyz, rgb_s, votes, drop=drop, out_slot=hs["next"] ^ 1)
+            st["small"][:2].copy_(counts, non_blocking=True)
+            st["small"][2:10].copy_(self.session.grid.view(torch.int64), non_blocking=True)
+            ticket["fused"] = (k, x, c, m)
+        elif fuse:
+            # collective fallback (host-side grid and plan: it waits for the device on its way)
             bb = self._global_bbox(bbox)
-            out["d2h_bytes"] += 24
-            if not np.all(np.isfinite(bb)):
+            if np.all(np.isfinite(bb)):
+                grid = self.ops.make_grid(bb[:3], bb[3:], cfg.voxel)
+                comp.wait_event(ev_rgb)
+                rgb_s = st["rgb"] if s == 1 else st["rgb"][:, ::s, ::s].contiguous()
+                if self.world == 1:
+                    k, x, c, m, counts = self.ops.voxel_fuse(xyz.view(-1, 3), rgb_s.view(-1, 3), votes.view(-1), self.thr, grid,
+                                                             trim=False, row_len=xyz.shape[2])
+                else:
+                    k, x, c, m, counts = self._fuse_sharded(xyz, rgb_s, votes, grid)
+                st["small"][:2].copy_(counts, non_blocking=True)
+                ticket["fused"], ticket["host_grid"] = (k, x, c, m), grid
+        done = torch.cuda.Event()
+        done.record(comp)
+        st["free"] = done
+        ticket["done"] = done
+        return ticket
+
+    def collect_host(self, ticket: dict) -> dict:
+        """Second half of ``run_host``: waits for the step's kernels, reads the voxel count, downloads exactly that many
+        voxels on the download stream and returns the host views."""
+        hs, st = self._host_out, ticket["slot"]
+        out = {"h2d_bytes": ticket["h2d_bytes"], "d2h_bytes": 0, "num_points": 0, "stats": ticket["stats"]}
+        ticket["done"].synchronize()  # the one wait: the host needs the voxel count to size the download
+        if ticket["fused"] is None:
+            return out
+        k, x, c, m = ticket["fused"]
+        small = st["small"]
+        n_pts, mv = int(small[0]), int(small[1])
+        out["d2h_bytes"] += 16
+        grid = ticket["host_grid"]
+        if grid is None:
+            gs = ops._lib.GridState.from_buffer_copy(small[2:10].numpy().tobytes())
+            out["d2h_bytes"] += 64
+            if gs.status == ops._lib.GRID_EMPTY:
                 return out
-            grid = self.ops.make_grid(bb[:3], bb[3:], cfg.voxel)
-            comp.wait_event(ev_rgb)
-            rgb_s = st["rgb"] if s == 1 else st["rgb"][:, ::s, ::s].contiguous()
-            if self.world == 1:
-                k, x, c, m, counts = self.ops.voxel_fuse(xyz.view(-1, 3), rgb_s.view(-1, 3), votes.view(-1), self.thr, grid,
-                                                         trim=False, row_len=xyz.shape[2])
-            else:
-                k, x, c, m, counts = self._fuse_sharded(xyz, rgb_s, votes, grid)
-        mv = self.ops.checked_voxel_count(counts)
+            if gs.status != ops._lib.GRID_OK:
+                raise ops.DDNError(f"fusion grid: {ops.GRID_STATUS.get(gs.status, gs.status)} (dims {list(gs.dims)}); raise "
+                                   "max_grid_cells or use a larger voxel")
+            grid = ops._lib.VoxelGrid()
+            grid.voxel = gs.voxel
+            for i in range(3):
+                grid.origin[i], grid.bits[i], grid.dims[i] = gs.origin[i], gs.bits[i], gs.dims[i]
+        if n_pts < 0:
+            raise ops.DDNError("voxel fusion: a voxel collected 2^24 or more points (32-bit colour sums); use a smaller voxel")
         if mv > k.shape[0]:
             raise ops.DDNError(f"voxel fusion: {mv} voxels exceed the output capacity {k.shape[0]}")
-        out["d2h_bytes"] += 64 + 16
         po = self._pinned_out(st, mv)
-        for name, t in (("keys", k), ("xyz", x), ("rgb", c), ("count", m)):
-            po[name][:mv].copy_(t[:mv], non_blocking=True)
-            out[name] = po[name][:mv]
-            out["d2h_bytes"] += out[name].numel() * out[name].element_size()
-        torch.cuda.synchronize(self.device)
-        out["num_points"] = int(counts[0].item())
+        d2h = hs["d2h"]
+        with torch.cuda.stream(d2h):
+            for name, t in (("keys", k), ("xyz", x), ("rgb", c), ("count", m)):
+                po[name][:mv].copy_(t[:mv], non_blocking=True)
+                t.record_stream(d2h)
+                out[name] = po[name][:mv]
+                out["d2h_bytes"] += out[name].numel() * out[name].element_size()
+        d2h.synchronize()
+        out["num_points"] = n_pts
         out["grid"] = grid
         return out

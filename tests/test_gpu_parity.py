@@ -357,3 +357,13 @@ def test_run_host_matches_device_pipeline(lib_built, in_place):
     assert np.array_equal(out["count"].numpy(), res.voxel_count[:mv].cpu().numpy())
     expected_h2d = sum(t.numel() * t.element_size() for i, t in enumerate(host) if not (in_place and i == 1))
     assert out["h2d_bytes"] == expected_h2d
+    # the two halves, pipelined: three scenes in flight (the third is submitted before the first is collected)
+    tickets = [sd.submit_host(*pinned, normals_in_place=in_place, chunk_views=4) for _ in range(2)]
+    outs = [sd.collect_host(tickets[0])]
+    tickets.append(sd.submit_host(*pinned, normals_in_place=in_place, chunk_views=2))
+    outs += [sd.collect_host(tickets[1]), sd.collect_host(tickets[2])]
+    for o in outs[1:]:  # (outs[0] shares its pinned buffers with the third call)
+        assert o["num_points"] == int(res.counts[0]) and np.array_equal(o["keys"].numpy(), res.voxel_keys[:mv].cpu().numpy())
+        assert np.array_equal(o["xyz"].numpy(), res.voxel_xyz[:mv].cpu().numpy())
+        assert np.array_equal(o["rgb"].numpy(), res.voxel_rgb[:mv].cpu().numpy())
+        assert np.array_equal(o["count"].numpy(), res.voxel_count[:mv].cpu().numpy())
