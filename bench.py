@@ -320,7 +320,7 @@ def run_workload(ctx: Ctx, workload: str, scaling: str, steps: int, warmup: int,
     if e2e:
         del res
         torch.cuda.empty_cache()
-        host = sharded.pin_host_inputs(*[t.cpu() for t in dev_inputs])
+        host = sharded.pin_host_inputs(*[t.cpu() for t in dev_inputs], pack_mask=True)
 
         def time_e2e(pipelined=True, **kw):
             for _ in range(2):
@@ -359,7 +359,7 @@ def run_workload(ctx: Ctx, workload: str, scaling: str, steps: int, warmup: int,
             "pcie_GBps_per_rank_all_copied": (f_h2d + f_d2h) / (f_ms * 1e-3) / 1e9,
             "api": "ShardedDensifier.submit_host / collect_host (= run_host in two halves; pinned host arrays in, fused cloud out "
                    "through pinned buffers), scene i+1 submitted before scene i is collected",
-            "note": "`value_one_call_at_a_time`: run_host called back to back, nothing overlaps between calls.  `value`: depth, mask, colours and sparse points are copied to the device every step; the normal maps "
+            "note": "`value_one_call_at_a_time`: run_host called back to back, nothing overlaps between calls.  `value`: depth, the mask (one bit per pixel, packed once on the host outside the timed region), colours and sparse points are copied to the device every step; the normal maps "
                     "stay in pinned host memory and the consistency kernel reads only the normals of its vote candidates over "
                     "PCIe (not counted in h2d_bytes_per_step).  `value_all_copied`: the normal maps are copied too."}
     del sharded, sc, dev_inputs

@@ -32,6 +32,7 @@ class AlignConfig(C.Structure):
         ("mode", C.c_int32),
         ("subsample_seed", C.c_uint32),
         ("zero_unmasked_passthrough", C.c_int32),
+        ("mask_packed", C.c_int32),
     ]
 
 

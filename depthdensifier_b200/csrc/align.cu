@@ -529,7 +529,11 @@ remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y
   const int ty0 = (tile / tiles_x) * kTileH, tx0 = (tile % tiles_x) * kTileW;
   const size_t HW = (size_t)H * W;
   const float* __restrict__ dmap = depth + (size_t)v * HW;
-  const uint8_t* __restrict__ mmap = mask ? mask + (size_t)v * HW : nullptr;
+  // mask: one byte per pixel, or (cfg.mask_packed) one BIT per pixel - bit (g & 7) of byte g >> 3 of the view's
+  // ceil(H W / 8) bytes: an eighth of the upload for the host path
+  const bool packed = cfg.mask_packed != 0;
+  const uint8_t* __restrict__ mmap = mask ? mask + (size_t)v * (packed ? (HW + 7) / 8 : HW) : nullptr;
+  auto mask_at = [&](size_t g) -> bool { return packed ? ((__ldg(mmap + (g >> 3)) >> (g & 7)) & 1) != 0 : __ldg(mmap + g) != 0; };
   float* __restrict__ out = refined + (size_t)v * HW;
   const ddn_view_stats st = stats[v];
 
@@ -541,7 +545,7 @@ remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y
         const size_t g = (size_t)y * W + x;
         float d = dmap[g];
         if (st.status == DDN_VIEW_NO_SPARSE) d = 0.f;
-        else if (cfg.zero_unmasked_passthrough && !(mmap ? mmap[g] != 0 : d > 0.f)) d = 0.f;
+        else if (cfg.zero_unmasked_passthrough && !(mmap ? mask_at(g) : d > 0.f)) d = 0.f;
         out[g] = d;
         fold_depth(d);
       }
@@ -582,7 +586,7 @@ remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y
       const int y = min(max(ty0 + hy - 1, 0), H - 1);
       const int g = y * W + x;
       const float d = __ldg(dmap + g);
-      const bool mk = mmap ? (__ldg(mmap + g) != 0) : (d > 0.f);
+      const bool mk = mmap ? mask_at((size_t)g) : (d > 0.f);
       float val = 0.f;
       if (mk) {
         if (bucketed) val = pwl_eval_bucketed(d, sx, sy, n, sb, xmin, bscale);

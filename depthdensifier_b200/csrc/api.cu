@@ -109,6 +109,7 @@ void ddn_align_config_default(ddn_align_config* cfg) {
   cfg->mode = 0;
   cfg->subsample_seed = 0;
   cfg->zero_unmasked_passthrough = 0;
+  cfg->mask_packed = 0;
 }
 
 void ddn_filter_config_default(ddn_filter_config* cfg) {

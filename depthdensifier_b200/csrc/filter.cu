@@ -239,6 +239,21 @@ __device__ __forceinline__ void load_normal(const float* __restrict__ normal_vie
   }
 }
 
+// Bulk asynchronous copy shared -> global (the TMA engine's 1-D form, SASS UBLKCP): one elected lane hands a warp's
+// 1536-byte xyz slice to the copy engine instead of 32 lanes moving it with three LDS.128 + three STG.128 each.
+// -DDDN_K4_BULK=0 restores the per-lane float4 copy.
+#ifndef DDN_K4_BULK
+#define DDN_K4_BULK 1
+#endif
+__device__ __forceinline__ void fence_proxy_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_shared_to_global(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n\tcp.async.bulk.commit_group;"
+               :
+               : "l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 // Pixel ownership.  A CTA owns kFilterChunk consecutive source-grid pixels of one view, a warp 128 of them.
 //   layout 0 ("strided"):  thread pixel j = warp base + j*32 + lane.  Every load, gather and byte store of a
 //                          warp instruction covers 32 consecutive pixels; xyz leaves through a per-warp
@@ -442,6 +457,7 @@ __global__ void __launch_bounds__(kFilterThreads, kBilinear ? 3 : DDN_K4_MINBLOC
   }
 
   // ---- epilogue: world positions (recomputed from the registers), votes, bounding box, occupancy ----
+  bool bulk_pending = false;  // lane 0: a bulk copy out of this warp's staging slice is in flight
   float X[kFilterPX], Y[kFilterPX], Zw[kFilterPX];
   bool keep[kFilterPX];
   unsigned vote_bytes = 0;
@@ -491,14 +507,24 @@ __global__ void __launch_bounds__(kFilterThreads, kBilinear ? 3 : DDN_K4_MINBLOC
       sw[l * 3 + 1] = Y[j];
       sw[l * 3 + 2] = Zw[j];
     }
+#if DDN_K4_BULK
+    fence_proxy_async_shared();  // the slice was written through the generic proxy: make it visible to the copy engine
+#endif
     __syncwarp();
     const int n_w = min(kWarpPix, Ps - wbase);  // pixels of this warp that exist (<= 0: none)
     float* xo = p.xyz + (out0 + wbase) * 3;
     if (n_w == kWarpPix && ((reinterpret_cast<uintptr_t>(xo) & 15) == 0)) {
+#if DDN_K4_BULK
+      if (lane == 0) {
+        bulk_store_shared_to_global(xo, sw, kWarpPix * 3 * sizeof(float));
+        bulk_pending = true;
+      }
+#else
       const float4* s4 = reinterpret_cast<const float4*>(sw);
       float4* g4 = reinterpret_cast<float4*>(xo);
 #pragma unroll
       for (int q = 0; q < 3; ++q) __stcs(g4 + q * 32 + lane, s4[q * 32 + lane]);
+#endif
     } else {
       for (int i = lane; i < n_w * 3; i += 32) __stcs(xo + i, sw[i]);
     }
@@ -565,6 +591,7 @@ __global__ void __launch_bounds__(kFilterThreads, kBilinear ? 3 : DDN_K4_MINBLOC
     }
   }
   if (tid == 6 && s_marked) atomicAdd(p.mark.counts, (unsigned long long)s_marked);
+  if (bulk_pending) bulk_store_wait_read();  // the staging slice must stay intact until the copy engine has read it
 }
 
 __global__ void bbox_init_kernel(int* bbox) {

@@ -586,7 +586,10 @@ class ShardedDensifier:
         return k, x, c, n, counts2
 
     # -- end-to-end with host buffers -----------------------------------------------------------------
-    def pin_host_inputs(self, depth, normal, mask, rgb, sparse_xyz, sparse_offsets):
+    def pin_host_inputs(self, depth, normal, mask, rgb, sparse_xyz, sparse_offsets, pack_mask: bool = False):
+        """Pinned copies of the host inputs.  ``pack_mask``: the mask goes up as one bit per pixel (ops.pack_mask)."""
+        if pack_mask:
+            mask = ops.pack_mask(mask)
         return tuple(t.contiguous().pin_memory() for t in (depth, normal, mask, rgb, sparse_xyz, sparse_offsets))
 
     def _host_state(self, sparse_xyz, sparse_offsets):
@@ -597,7 +600,7 @@ class ShardedDensifier:
 
             def slot():
                 return {"depth": torch.empty((n, H, W), dtype=torch.float32, device=dev),
-                        "mask": torch.empty((n, H, W), dtype=torch.bool, device=dev),
+                        "mask": None,  # bool [n,H,W] or bit-packed uint8 [n, ceil(HW/8)], allocated on first use
                         "rgb": torch.empty((n, H, W, 3), dtype=torch.uint8, device=dev),
                         "normal": None,
                         "sparse_xyz": torch.empty(tuple(sparse_xyz.shape), dtype=torch.float64, device=dev),
@@ -671,6 +674,8 @@ class ShardedDensifier:
         stats = []
         for c0 in range(0, n, max(int(chunk_views), 1)):
             c1 = min(c0 + max(int(chunk_views), 1), n)
+            if st["mask"] is None or st["mask"].shape != mask.shape or st["mask"].dtype != mask.dtype:
+                st["mask"] = torch.empty(tuple(mask.shape), dtype=mask.dtype, device=self.device)
             with torch.cuda.stream(copy):
                 upload(st["depth"][c0:c1], depth[c0:c1])
                 upload(st["mask"][c0:c1], mask[c0:c1])

@@ -64,7 +64,7 @@ class AlignOptions:
     subsample_seed: int = 0
     zero_unmasked_passthrough: bool = False
 
-    def to_c(self) -> _lib.AlignConfig:
+    def to_c(self, mask_packed: bool = False) -> _lib.AlignConfig:
         if self.align_mode not in ("pwl", "affine"):
             raise ValueError("align_mode must be 'pwl' or 'affine'")
         return _lib.AlignConfig(
@@ -78,6 +78,7 @@ class AlignOptions:
             0 if self.align_mode == "pwl" else 1,
             int(self.subsample_seed) & 0xFFFFFFFF,
             int(bool(self.zero_unmasked_passthrough)),
+            int(bool(mask_packed)),
         )
 
 
@@ -117,14 +118,17 @@ def align_views(depth, mask, cam_from_world, kmat, sparse_xyz, sparse_offsets, m
     V, H, W = depth.shape
     assert depth.dtype == torch.float32 and cam_from_world.dtype == torch.float64 and kmat.dtype == torch.float64
     assert sparse_xyz.dtype == torch.float64 and sparse_offsets.dtype == torch.int64
-    assert mask is None or (mask.dtype in (torch.bool, torch.uint8) and mask.shape == depth.shape)
+    # a 2-D uint8 mask [V, ceil(H*W/8)] is the bit-packed form (pack_mask)
+    packed = mask is not None and mask.dtype == torch.uint8 and mask.dim() == 2
+    assert mask is None or (packed and tuple(mask.shape) == (V, (H * W + 7) // 8)) or (
+        mask.dtype in (torch.bool, torch.uint8) and mask.shape == depth.shape)
     assert tuple(cam_from_world.shape) == (V, 3, 4) and tuple(kmat.shape) == (V, 3, 3)
     refined = out if out is not None else torch.empty_like(depth)
     stats = torch.zeros((V, 8), dtype=torch.int32, device=dev)
     nbytes = C.c_int64(0)
     _lib.check(lib.ddn_align_workspace_bytes(V, max_sparse_per_view, C.byref(nbytes)))
     ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
-    cfg = opts.to_c()
+    cfg = opts.to_c(mask_packed=packed)
     with torch.cuda.device(dev):
         _lib.check(
             lib.ddn_align_views(
@@ -134,6 +138,13 @@ def align_views(depth, mask, cam_from_world, kmat, sparse_xyz, sparse_offsets, m
             )
         )
     return refined, stats
+
+
+def pack_mask(mask: torch.Tensor) -> torch.Tensor:
+    """[V,H,W] bool mask -> [V, ceil(H*W/8)] uint8, one bit per pixel (bit g & 7 of byte g >> 3): the form the alignment
+    kernel also accepts, an eighth of the bytes to upload.  Host tensors (numpy packbits)."""
+    m = np.ascontiguousarray(mask.cpu().numpy()).reshape(mask.shape[0], -1)
+    return torch.from_numpy(np.packbits(m, axis=1, bitorder="little"))
 
 
 def decode_stats(stats: torch.Tensor) -> list[dict]:

@@ -74,6 +74,7 @@ typedef struct {
   int32_t mode;                     /* 0 = piecewise-linear LUT (reference); 1 = affine scale/shift LSQ (new) */
   uint32_t subsample_seed;          /* seed of the hash permutation that replaces torch.randperm (:304) */
   int32_t zero_unmasked_passthrough; /* 1: pass-through views are also zeroed outside the mask (scripts/test.py:194) */
+  int32_t mask_packed;              /* 1: mask is one BIT per pixel ([V, ceil(H*W/8)] u8, bit g & 7 of byte g >> 3) */
 } ddn_align_config;
 
 /* status values in ddn_view_stats */
@@ -101,7 +102,7 @@ DDN_API void ddn_align_config_default(ddn_align_config* cfg);
 
 DDN_API int ddn_align_workspace_bytes(int64_t n_views, int64_t max_sparse_per_view, int64_t* bytes_out);
 
-/* depth [V,H,W] f32; mask [V,H,W] u8 or NULL (=> depth > 0, depth_refiner.py:238-241);
+/* depth [V,H,W] f32; mask [V,H,W] u8 (or bit-packed, cfg->mask_packed) or NULL (=> depth > 0, depth_refiner.py:238-241);
  * cam_from_world [V,3,4] f64 row-major; kmat [V,3,3] f64 (only the top two rows are used, :112);
  * sparse_xyz [S,3] f64 world, CSR sparse_offsets [V+1] i64; refined [V,H,W] f32 out;
  * stats [V] out.  A view with no sparse points gets status DDN_VIEW_NO_SPARSE and an all-zero map.

@@ -347,7 +347,7 @@ def test_run_host_matches_device_pipeline(lib_built, in_place):
     host = (sc.mono_depth, sc.normal, sc.mask, sc.rgb, sc.sparse_xyz, sc.sparse_offsets)
     res = sd.run(*[t.cuda() for t in host])
     mv = int(res.counts[1])
-    pinned = sd.pin_host_inputs(*host)
+    pinned = sd.pin_host_inputs(*host, pack_mask=in_place)  # the bit-packed mask in one of the two variants
     for _ in range(2):  # second call reuses the staging buffers
         out = sd.run_host(*pinned, normals_in_place=in_place, chunk_views=3)
     assert out["num_points"] == int(res.counts[0]) and len(out["keys"]) == mv
@@ -355,7 +355,7 @@ def test_run_host_matches_device_pipeline(lib_built, in_place):
     assert np.array_equal(out["xyz"].numpy(), res.voxel_xyz[:mv].cpu().numpy())
     assert np.array_equal(out["rgb"].numpy(), res.voxel_rgb[:mv].cpu().numpy())
     assert np.array_equal(out["count"].numpy(), res.voxel_count[:mv].cpu().numpy())
-    expected_h2d = sum(t.numel() * t.element_size() for i, t in enumerate(host) if not (in_place and i == 1))
+    expected_h2d = sum(t.numel() * t.element_size() for i, t in enumerate(pinned) if not (in_place and i == 1))
     assert out["h2d_bytes"] == expected_h2d
     # the two halves, pipelined: three scenes in flight (the third is submitted before the first is collected)
     tickets = [sd.submit_host(*pinned, normals_in_place=in_place, chunk_views=4) for _ in range(2)]
