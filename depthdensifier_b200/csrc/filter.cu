@@ -239,11 +239,13 @@ __device__ __forceinline__ void load_normal(const float* __restrict__ normal_vie
   }
 }
 
-// Bulk asynchronous copy shared -> global (the TMA engine's 1-D form, SASS UBLKCP): one elected lane hands a warp's
-// 1536-byte xyz slice to the copy engine instead of 32 lanes moving it with three LDS.128 + three STG.128 each.
-// -DDDN_K4_BULK=0 restores the per-lane float4 copy.
+// Bulk asynchronous copy shared -> global (the TMA engine's 1-D form, SASS UBLKCP): with -DDDN_K4_BULK=1 one elected
+// lane hands a warp's 1536-byte xyz slice to the copy engine instead of 32 lanes moving it with three LDS.128 + three
+// streaming STG.128 each.  Measured at cfg 2 (profiles/README.md, round 2): 2.29 ms against 2.23 ms for the per-lane
+// copy (3.03 vs 2.97 ms with the occupancy mark fused in) - the proxy fence and the wait for the engine's read before
+// the CTA may retire cost more than the twelve instructions per thread they replace - so the per-lane copy stays.
 #ifndef DDN_K4_BULK
-#define DDN_K4_BULK 1
+#define DDN_K4_BULK 0
 #endif
 __device__ __forceinline__ void fence_proxy_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void bulk_store_shared_to_global(void* gdst, const void* ssrc, uint32_t bytes) {
