@@ -506,6 +506,9 @@ __device__ __forceinline__ void tile_bbox_epilogue(int* __restrict__ bbox, const
 #ifndef DDN_K3_MINB
 #define DDN_K3_MINB 8
 #endif
+// kPacked: the mask is one bit per pixel; kBox: the bounding-box epilogue is on.  Template parameters, not run-time
+// flags: the kernel is bound by instruction issue, and a per-pixel branch on either costs 5 % (measured).
+template <bool kPacked, bool kBox>
 __global__ void __launch_bounds__(kRemapThreads, DDN_K3_MINB)
 remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y, const float* __restrict__ depth,
                     const uint8_t* __restrict__ mask, const ddn_view_stats* __restrict__ stats, AlignWorkspace ws,
@@ -517,6 +520,7 @@ remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y
   __shared__ int s_dmin, s_dmax;
   int t_dmin = 0x7f800000, t_dmax = 0;
   auto fold_depth = [&](float v) {
+    if (!kBox) return;
     const int b = __float_as_int(v);
     t_dmax = max(t_dmax, b);
     t_dmin = min(t_dmin, v > 0.f ? b : 0x7f800000);
@@ -531,9 +535,8 @@ remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y
   const float* __restrict__ dmap = depth + (size_t)v * HW;
   // mask: one byte per pixel, or (cfg.mask_packed) one BIT per pixel - bit (g & 7) of byte g >> 3 of the view's
   // ceil(H W / 8) bytes: an eighth of the upload for the host path
-  const bool packed = cfg.mask_packed != 0;
-  const uint8_t* __restrict__ mmap = mask ? mask + (size_t)v * (packed ? (HW + 7) / 8 : HW) : nullptr;
-  auto mask_at = [&](size_t g) -> bool { return packed ? ((__ldg(mmap + (g >> 3)) >> (g & 7)) & 1) != 0 : __ldg(mmap + g) != 0; };
+  const uint8_t* __restrict__ mmap = mask ? mask + (size_t)v * (kPacked ? (HW + 7) / 8 : HW) : nullptr;
+  auto mask_at = [&](size_t g) -> bool { return kPacked ? ((__ldg(mmap + (g >> 3)) >> (g & 7)) & 1) != 0 : __ldg(mmap + g) != 0; };
   float* __restrict__ out = refined + (size_t)v * HW;
   const ddn_view_stats st = stats[v];
 
@@ -551,7 +554,7 @@ remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y
       }
     }
     __syncthreads();
-    tile_bbox_epilogue(bbox, src_table, v, tx0, ty0, W, H, t_dmin, t_dmax, &s_dmin, &s_dmax);
+    if (kBox) tile_bbox_epilogue(bbox, src_table, v, tx0, ty0, W, H, t_dmin, t_dmax, &s_dmin, &s_dmax);
     return;
   }
 
@@ -636,7 +639,7 @@ remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y
       fold_depth(o);
     }
   }
-  tile_bbox_epilogue(bbox, src_table, v, tx0, ty0, W, H, t_dmin, t_dmax, &s_dmin, &s_dmax);
+  if (kBox) tile_bbox_epilogue(bbox, src_table, v, tx0, ty0, W, H, t_dmin, t_dmax, &s_dmin, &s_dmax);
 }
 
 }  // namespace ddn
@@ -688,11 +691,22 @@ int ddn_align_views(const ddn_align_config* cfg, int64_t n_views, int64_t height
   int64_t lut = (cfg->adaptive_correspondences && cfg->max_pairs < C) ? cfg->max_pairs : C;
   if (cfg->mode != 0 || lut > kLutSmemMax) lut = 0;  // affine mode has no table; huge tables stay in global
   const size_t smem_lut = lut > 0 ? (size_t)lut * 8 + (size_t)kBuckets * 4 : 0;
-  DDN_TRY(check_cuda(cudaFuncSetAttribute(remap_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lut),
-                     "cudaFuncSetAttribute(remap_median)"));
   dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)n_views);
-  remap_median_kernel<<<grid, kRemapThreads, smem_lut, st>>>(*cfg, (int)height, (int)width, tiles_x, tiles_y, depth, mask,
-                                                            stats, ws, refined, (int)lut, src_table, reinterpret_cast<int*>(bbox));
+#define DDN_LAUNCH_REMAP(P, B)                                                                                              \
+  do {                                                                                                                      \
+    DDN_TRY(check_cuda(cudaFuncSetAttribute(remap_median_kernel<P, B>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                            (int)smem_lut),                                                                 \
+                       "cudaFuncSetAttribute(remap_median)"));                                                              \
+    remap_median_kernel<P, B><<<grid, kRemapThreads, smem_lut, st>>>(*cfg, (int)height, (int)width, tiles_x, tiles_y, depth, \
+                                                                    mask, stats, ws, refined, (int)lut, src_table,         \
+                                                                    reinterpret_cast<int*>(bbox));                         \
+  } while (0)
+  const bool packed = cfg->mask_packed != 0 && mask != nullptr, box = bbox != nullptr;
+  if (packed && box) DDN_LAUNCH_REMAP(true, true);
+  else if (packed) DDN_LAUNCH_REMAP(true, false);
+  else if (box) DDN_LAUNCH_REMAP(false, true);
+  else DDN_LAUNCH_REMAP(false, false);
+#undef DDN_LAUNCH_REMAP
   return after_launch("remap_median_kernel");
 }
 
