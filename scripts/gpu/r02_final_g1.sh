@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 KREGEX='regex:align_stats|remap_median|build_pair|bbox_init|backproject_filter|grid_from|grid_store|clear_units|mark_|tile_count|tile_scan|zero_accum|unit_prefix|accumulate_|finalize_kernel|merge_|unmark'
 timeout 1800 python -m pytest tests -m gpu -q > gpurun_out/r02_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/r02_pytest_gpu.log
 timeout 300 python scripts/gpu/kbench.py cfg2 7 > gpurun_out/r02_kbench.json 2>/dev/null; cat gpurun_out/r02_kbench.json
-DDN_LIB_PATH=$PWD/depthdensifier_b200/libddn_b200_nobulk.so timeout 300 python scripts/gpu/kbench.py cfg2 7 > gpurun_out/r02_kbench_nobulk.json 2>/dev/null; cat gpurun_out/r02_kbench_nobulk.json
+DDN_LIB_PATH=$PWD/depthdensifier_b200/libddn_b200_bulk.so timeout 300 python scripts/gpu/kbench.py cfg2 7 > gpurun_out/r02_kbench_bulk.json 2>/dev/null; cat gpurun_out/r02_kbench_bulk.json
 timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r02_bench_g1.json 2> gpurun_out/r02_bench_g1.err; echo "bench rc=$?"; tail -3 gpurun_out/r02_bench_g1.err
 timeout 600 python bench.py --steps 10 --warmup 3 --sample-mode bilinear --no-strong --no-e2e --no-cpu-baseline > gpurun_out/r02_bench_g1_bilinear.json 2> gpurun_out/r02_bench_g1_bilinear.err; echo "bilinear rc=$?"
 timeout 600 python bench.py --impl reference --workload cfg1 --steps 2 --warmup 1 > gpurun_out/r02_bench_reference_cfg1.json 2> gpurun_out/r02_bench_reference_cfg1.err; echo "ref cfg1 rc=$?"
@@ -16,7 +16,7 @@ for kn in backproject_filter_kernel accumulate_points_kernel remap_median_kernel
   ncu -i gpurun_out/r02_${kn}.ncu-rep --page raw --csv > gpurun_out/r02_${kn}_raw.csv 2>/dev/null
   ncu -i gpurun_out/r02_${kn}.ncu-rep --page source --csv > gpurun_out/r02_${kn}_source.csv 2>/dev/null
 done
-python scripts/summarise_launches.py gpurun_out/r02_launches_cfg2.csv | tail -16
+python scripts/summarise_launches.py gpurun_out/r02_launches_cfg2.csv build_pair_tables 2 | tail -16
 python - <<'PY'
 import json
 for f in ("r02_bench_g1", "r02_bench_g1_bilinear", "r02_bench_g1_cfg1", "r02_bench_reference_cfg1"):

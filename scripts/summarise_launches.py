@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Summarise an `ncu --csv` launch list (ncu -k regex:ddn --metrics gpu__time_duration.sum,dram__bytes_read.sum,
 dram__bytes_write.sum): the kernels of the last bench step, per kernel ms and DRAM GB.
-  python scripts/summarise_launches.py launches.csv [first-kernel-of-a-step (default build_pair_tables)]"""
+  python scripts/summarise_launches.py launches.csv [first-kernel-of-a-step (default build_pair_tables)] [n]
+n: which segment, counted from the end (default 1 = the last; bench.py's trailing K4-alone measurement starts with
+build_pair_tables too, so the timed step of a default bench capture is n = 2)."""
 import collections
 import csv
 import io
@@ -17,11 +19,13 @@ for x in r:
     d["unit_" + x["Metric Name"]] = x["Metric Unit"]
 ids = list(byid)
 starts = [i for i, k in enumerate(ids) if first in byid[k]["name"]]
-last = starts[-1] if starts else 0
+nth = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+last = starts[-nth] if len(starts) >= nth else 0
+end = starts[-nth + 1] if nth > 1 and len(starts) >= nth else len(ids)
 tot = 0.0
 sc = {"byte": 1e-9, "Kbyte": 1e-6, "Mbyte": 1e-3, "Gbyte": 1.0}
 ts = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "nsecond": 1e-6, "usecond": 1e-3, "msecond": 1.0}
-for k in ids[last:]:
+for k in ids[last:end]:
     d = byid[k]
     t_ms = d["gpu__time_duration.sum"] * ts[d["unit_gpu__time_duration.sum"]]
     rd = d.get("dram__bytes_read.sum", 0) * sc.get(d.get("unit_dram__bytes_read.sum", "byte"), 1e-9)
