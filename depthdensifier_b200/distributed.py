@@ -476,7 +476,7 @@ class ShardedDensifier:
         mark("fuse_partials", lambda: self.ops.fuse_finish_partial(sess, *flat, self.thr, rec, row_len=xyz.shape[2]))
         hdl.barrier()  # every rank's units, tile prefix and records are complete
         k, x, c, n, counts = mark("fuse_merge", lambda: self.ops.fuse_merge_peers(
-            sess, self.rank, self.world, self._peer_records, self._peer_prefix, self._plan, self._cap_merge, out=self._merge_out, drop_xyz=drop))
+            sess, self.rank, self.world, self._peer_records, self._peer_prefix, self._plan, self._cap_merge, out=self._merge_outputs(out_slot), drop_xyz=drop))
         return k, x, c, n, counts.clone()
 
     def _nbr_full(self) -> torch.Tensor:
