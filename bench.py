@@ -207,7 +207,8 @@ class Ctx:
 
 
 def run_workload(ctx: Ctx, workload: str, scaling: str, steps: int, warmup: int, e2e: bool, sample_mode: str = "nearest",
-                 pixel_layout: int = 0, clocks: bool = True, profile_kernels: bool = False, dedup_sparse: bool = False) -> dict:
+                 pixel_layout: int = 0, clocks: bool = True, profile_kernels: bool = False, dedup_sparse: bool = False,
+                 overlap_align: bool = True) -> dict:
     """Device-resident timing (+ optionally the end-to-end host path) of one workload on all ranks."""
     from depthdensifier_b200 import _lib, ops
     from depthdensifier_b200.distributed import ShardedDensifier
@@ -229,7 +230,7 @@ def run_workload(ctx: Ctx, workload: str, scaling: str, steps: int, warmup: int,
     thr = default_vote_threshold(K)
     torch.cuda.synchronize()
     cfg = DensifyConfig(voxel=VOXEL, vote_threshold=thr, filter=ops.FilterOptions(sample_mode=sample_mode, pixel_layout=pixel_layout),
-                        dedup_sparse=dedup_sparse)
+                        dedup_sparse=dedup_sparse, overlap_align=overlap_align)
     sharded = ShardedDensifier(cfg, dev, rank, world, V_total, lo, hi, sc.cam_from_world, sc.intrinsics, nbr_np, H, W)
     dev_inputs = (sc.mono_depth, sc.normal, sc.mask, sc.rgb, sc.sparse_xyz, sc.sparse_offsets)
 
@@ -389,6 +390,7 @@ def main():
     ap.add_argument("--sample-mode", default="nearest", choices=["nearest", "bilinear"])
     ap.add_argument("--pixel-layout", type=int, default=0, choices=[0, 1])
     ap.add_argument("--dedup-sparse", action="store_true", help="N5: no dense voxel where the sparse cloud has a point")
+    ap.add_argument("--no-overlap-align", action="store_true", help="stage 1 of a step on the main stream (no overlap with the previous step)")
     ap.add_argument("--cpu-views", type=int, default=0, help="views of the CPU sample (at least K+1 are always used)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -442,6 +444,7 @@ def main():
 
     main_run = run_workload(ctx, args.workload, args.scaling, args.steps, args.warmup, e2e=not args.no_e2e,
                             sample_mode=args.sample_mode, pixel_layout=args.pixel_layout, dedup_sparse=args.dedup_sparse,
+                            overlap_align=not args.no_overlap_align,
                             profile_kernels=args.workload != "cfg2")
     K, H, W = main_run["K"], main_run["H"], main_run["W"]
     n_valid_local, k4_local_ms = main_run["n_valid_local"], main_run["k4_local_ms"]
@@ -482,7 +485,7 @@ def main():
     strong = None
     if not args.no_strong and args.workload == "cfg2" and args.scaling == "weak":
         sr = run_workload(ctx, "cfg3", "strong", steps=max(5, min(args.steps, 10)), warmup=3, e2e=False, clocks=False,
-                          profile_kernels=True)
+                          profile_kernels=True, overlap_align=not args.no_overlap_align)
         strong = {"workload": "cfg3", "scaling": "strong", "ms_per_step": sr["ms_per_step"], "value": sr["value"], "unit": UNIT,
                   "steps": sr["steps"], "stages_ms": sr["stages_ms"], "stage4_kernels_ms": sr.get("stage4_kernels_ms"),
                   "stage4_kernels_ms_per_rank": sr.get("stage4_kernels_ms_per_rank"),
@@ -508,7 +511,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.workload, world, args.scaling, args.sample_mode),
             "workload_stats": main_run["stats"], "limits": main_run["limits"], "path": main_run["path"],
-            "dedup_sparse": bool(args.dedup_sparse), "stage4_kernels_ms": main_run.get("stage4_kernels_ms"),
+            "dedup_sparse": bool(args.dedup_sparse), "overlap_align": not args.no_overlap_align, "stage4_kernels_ms": main_run.get("stage4_kernels_ms"),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": main_run.get("e2e"), "gpu_launches": main_run["launches"],
             "multi_gpu_check": multi_gpu, "strong": strong,
             "host_cpus_rank0": (f"{numa_cpus[0]}-{numa_cpus[-1]} ({len(numa_cpus)})" if numa_cpus else None),

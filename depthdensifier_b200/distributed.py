@@ -282,6 +282,9 @@ class ShardedDensifier:
         _, hdl, views = self.peer.buffer(f"refined{self._parity}", (self._slots_max, self.H, self.W), torch.float32)
         cur = torch.cuda.current_stream(self.device)
         hdl.barrier()  # every rank's refined maps and bounding box of this step are in place
+        if self.cfg.overlap_align:
+            self._ev_stage1_may_start = torch.cuda.Event()
+            self._ev_stage1_may_start.record(cur)
         self._side.wait_stream(cur)
         with torch.cuda.stream(self._side):
             for slot, q, j in self._halo_src:
@@ -321,12 +324,38 @@ class ShardedDensifier:
             off = sparse_offsets.cpu().numpy()
             self._max_sparse = max(int(np.max(np.diff(off))) if len(off) > 1 else 1, 1)
         fuse = cfg.voxel is not None
-        refined_slots = self._new_refined_slots()
-        pair, src = mark("pair_tables", self._pair_tables)
-        box = self._new_box() if (self.device_path and fuse and grid is None) else None
-        _, stats = mark("align", lambda: self.ops.align_views(
-            depth, mask, self.poses_slots[: self.n_local].contiguous(), self.kmat, sparse_xyz, sparse_offsets,
-            self._max_sparse, cfg.align, out=refined_slots[: self.n_local], **self._box_args(src, box)))
+
+        def stage1():
+            refined_slots = self._new_refined_slots()
+            pair, src = mark("pair_tables", self._pair_tables)
+            box = self._new_box() if (self.device_path and fuse and grid is None) else None
+            _, stats = mark("align", lambda: self.ops.align_views(
+                depth, mask, self.poses_slots[: self.n_local].contiguous(), self.kmat, sparse_xyz, sparse_offsets,
+                self._max_sparse, cfg.align, out=refined_slots[: self.n_local], **self._box_args(src, box)))
+            return refined_slots, pair, src, box, stats
+
+        if self.device_path and cfg.overlap_align:
+            # Stage 1 on its own stream.  It may start as soon as the PREVIOUS step has passed its halo barrier (one
+            # rank: has launched its K4) - from then on nobody reads the buffers it writes (the other parity's maps
+            # and box) - i.e. while that step still runs K4, the fusion and the merge on the main stream.
+            main = torch.cuda.current_stream(self.device)
+            if getattr(self, "_align_stream", None) is None:
+                self._align_stream, self._ev_stage1_may_start = torch.cuda.Stream(device=self.device), None
+            side = self._align_stream
+            if self._ev_stage1_may_start is None:
+                side.wait_stream(main)
+            else:
+                side.wait_event(self._ev_stage1_may_start)
+            with torch.cuda.stream(side):
+                refined_slots, pair, src, box, stats = stage1()
+                done = torch.cuda.Event()
+                done.record(side)
+            main.wait_event(done)
+            for t in (refined_slots, pair, src, box, stats):
+                if t is not None and t.is_cuda:
+                    t.record_stream(main)
+        else:
+            refined_slots, pair, src, box, stats = stage1()
         xyz, votes, bbox = self._halo_and_filter(refined_slots, normal, mark, pair, src, box=box, grid=grid)
         res = ShardResult(refined=refined_slots[: self.n_local], stats=stats, xyz=xyz, votes=votes, vote_threshold=self.thr,
                           bbox=bbox, events=ev)
@@ -434,6 +463,9 @@ class ShardedDensifier:
             mark("backproject_filter_boundary", lambda: (k4(0, i0), k4(i1, self.n_local)))
         else:
             mark("backproject_filter", lambda: k4(0, self.n_local))
+            if self.device_path and cfg.overlap_align and self.peer is None:
+                self._ev_stage1_may_start = torch.cuda.Event()
+                self._ev_stage1_may_start.record(torch.cuda.current_stream(self.device))
         return xyz, votes, bbox
 
     def _merge_outputs(self, slot: int):

@@ -24,6 +24,10 @@ class DensifyConfig:
     voxel: float | None = 0.01  # None -> no fusion (reference behaviour: keep every point)
     max_grid_cells: int = 1 << 33  # capacity of the fusion session's occupancy bitmap (16 bytes per 96 cells)
     dedup_sparse: bool = False  # N5: no dense voxel where the sparse cloud already has a point (reference: plain append)
+    # ShardedDensifier.run only: stage 1 of a step runs on its own stream and may start while the previous step is still
+    # fusing / merging (its NVLink-bound exchange leaves the SMs idle).  The caller's inputs must then be complete when
+    # run() is called - they are not ordered against work the caller queued on the current stream just before.
+    overlap_align: bool = False
 
 
 def clamp_vote_threshold(thr: int) -> int:

@@ -35,12 +35,12 @@ def multi_gpu_check(dev, rank: int, world: int, n_views: int = 24, width: int = 
                 "votes": res.votes.cpu().numpy(), "refined": res.refined.cpu().numpy(), "n": int(res.counts[0])}
 
     lo, hi = shard_bounds(V, world)[rank]
-    sd = ShardedDensifier(DensifyConfig(voxel=voxel, dedup_sparse=dedup), dev, rank, world, V, lo, hi, sc.cam_from_world, sc.intrinsics, nbr, H, W)
+    sd = ShardedDensifier(DensifyConfig(voxel=voxel, dedup_sparse=dedup, overlap_align=dedup), dev, rank, world, V, lo, hi, sc.cam_from_world, sc.intrinsics, nbr, H, W)
     path = "peer" if sd.peer is not None else "collective"
     dev_in = inputs(lo, hi, lambda t: t.to(dev).contiguous())
     mine = None
-    for _ in range(max(steps, 1)):  # the second step runs on reused (and cleaned-up) exchange buffers
-        mine = collect(sd.run(*dev_in))
+    results = [sd.run(*dev_in) for _ in range(max(steps, 1) + 1)]  # queued back to back: later steps run on reused (and
+    mine = collect(results[-1])                                     # cleaned-up) exchange buffers, stage 1 possibly overlapped
     gathered = [None] * world
     dist.gather_object(mine, gathered if rank == 0 else None, dst=0)
     report = {"passed": True, "path": path, "ranks": world, "views": V, "size": [W, H], "steps": steps, "dedup_sparse": dedup, "different": []}
