@@ -75,6 +75,37 @@ def test_gradient_mask_signature_matches_reference():
     assert [(p.name, p.default) for p in a.parameters.values()] == [(p.name, p.default) for p in b.parameters.values()]
 
 
+@needs_ref
+def test_batch_config_matches_reference(tmp_path, monkeypatch):
+    """scripts/run_batch.py: same BatchConfig fields (root_dir and output_dir required, the ScriptConfig embedded as
+    `config`), and each scan's model goes to <output_dir>/<scan>/sparse/0 (scripts/run_batch.py:63-65)."""
+    import importlib.util
+    import sys
+    from pathlib import Path
+
+    from depthdensifier_b200 import run_batch as mine
+    from oracle.run_reference import _import_reference_script
+
+    _import_reference_script()  # installs the stand-ins and makes `test` importable the way run_batch.py imports it
+    sys.modules["test"] = sys.modules["ddn_reference_script"]
+    spec = importlib.util.spec_from_file_location("ddn_ref_run_batch", REFERENCE_ROOT / "scripts" / "run_batch.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    theirs = [(f.name, f.default is dataclasses.MISSING and f.default_factory is dataclasses.MISSING) for f in dataclasses.fields(ref.BatchConfig)]
+    ours = [(f.name, f.default is dataclasses.MISSING and f.default_factory is dataclasses.MISSING) for f in dataclasses.fields(mine.BatchConfig)]
+    assert ours[: len(theirs)] == theirs  # root_dir (required), output_dir (required), config; additions follow
+    # output layout: run both mains over a root with one complete scan, densification itself stubbed out
+    (tmp_path / "root" / "scan_a" / "sparse" / "0").mkdir(parents=True)
+    (tmp_path / "root" / "scan_a" / "images").mkdir()
+    (tmp_path / "root" / "incomplete").mkdir()
+    seen = {}
+    monkeypatch.setattr(ref, "densify_main", lambda cfg: seen.setdefault("ref", Path(cfg.paths.output_model_dir)))
+    monkeypatch.setattr(mine, "densify_main", lambda cfg: seen.setdefault("mine", Path(cfg.paths.output_model_dir)))
+    ref.main(ref.BatchConfig(root_dir=tmp_path / "root", output_dir=tmp_path / "out"))
+    mine.main(mine.BatchConfig(root_dir=tmp_path / "root", output_dir=tmp_path / "out"))
+    assert seen["mine"] == seen["ref"] == tmp_path / "out" / "scan_a" / "sparse" / "0"
+
+
 def test_package_exports():
     import depthdensifier_b200 as pkg
 
@@ -91,3 +122,4 @@ def test_cli_flags():
         assert flag in out.stdout, flag
     out = subprocess.run([sys.executable, "-m", "depthdensifier_b200.run_batch", "--help"], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "--root-dir" in out.stdout and "--output-dir" in out.stdout
+    assert "--config.filtering.vote-threshold" in out.stdout  # the flag scripts/run_batch.py:36-37 documents

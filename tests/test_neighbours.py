@@ -42,3 +42,18 @@ def test_covisibility_table():
     none = covisibility_table([np.zeros(0, np.int64)] * 4, 2, _ring_poses(4))  # nothing shared -> nearest views
     assert np.array_equal(np.sort(none, 1), np.sort(nearest_views_table(_ring_poses(4), 2), 1))
     assert covisibility_table(obs[:2], 3).tolist() == [[1, -1, -1], [0, -1, -1]]
+
+
+def test_covisibility_counts_match_brute_force():
+    """The sparse incidence product counts, for every pair of views, the 3D points both observe - against the
+    straightforward set intersection on a random model (with duplicate observations inside a view)."""
+    rng = np.random.default_rng(3)
+    V, P = 23, 900
+    obs = [rng.choice(P, size=rng.integers(0, 200), replace=True).astype(np.int64) for _ in range(V)]
+    k = 5
+    nbr = covisibility_table(obs, k)
+    sets = [set(o.tolist()) for o in obs]
+    for s in range(V):
+        shared = np.array([len(sets[s] & sets[t]) if t != s else -1 for t in range(V)])
+        order = sorted((t for t in range(V) if t != s), key=lambda t: (-shared[t], t))[:k]
+        assert list(nbr[s]) == order, (s, list(nbr[s]), order)
