@@ -358,19 +358,23 @@ def run_workload(ctx: Ctx, workload: str, scaling: str, steps: int, warmup: int,
             e_ms = ctx.allreduce((time.perf_counter() - t0) * 1e3 / e_steps, "max")
             return e_ms, int(out_host["h2d_bytes"]), int(out_host["d2h_bytes"])
 
-        e_ms, h2d, d2h = time_e2e()
+        p_ms, h2d, d2h = time_e2e()
         s_ms, _, _ = time_e2e(pipelined=False)
+        # `value` = the faster of the two public forms on this machine (with 8 ranks sharing one host, two scenes in
+        # flight per rank oversubscribe the host memory system and the one-call form wins); both are reported
+        e_ms, e_mode = (p_ms, "pipelined") if p_ms <= s_ms else (s_ms, "one_call_at_a_time")
         f_ms, f_h2d, f_d2h = time_e2e(normals_in_place=False)
         tot = lambda x: int(ctx.allreduce(float(x), "sum"))
         out["e2e"] = {
             "value": n_valid / (e_ms / 1e3), "unit": UNIT, "ms_per_step": e_ms,
             "h2d_bytes_per_step": tot(h2d), "d2h_bytes_per_step": tot(d2h),
             "pcie_GBps_per_rank": (h2d + d2h) / (e_ms * 1e-3) / 1e9,
+            "mode": e_mode, "value_pipelined": n_valid / (p_ms / 1e3), "ms_per_step_pipelined": p_ms,
             "value_one_call_at_a_time": n_valid / (s_ms / 1e3), "ms_per_step_one_call_at_a_time": s_ms,
             "value_all_copied": n_valid / (f_ms / 1e3), "ms_per_step_all_copied": f_ms, "h2d_bytes_per_step_all_copied": tot(f_h2d),
             "pcie_GBps_per_rank_all_copied": (f_h2d + f_d2h) / (f_ms * 1e-3) / 1e9,
-            "api": "ShardedDensifier.submit_host / collect_host (= run_host in two halves; pinned host arrays in, fused cloud out "
-                   "through pinned buffers), scene i+1 submitted before scene i is collected",
+            "api": "ShardedDensifier.run_host (one_call_at_a_time), or its two halves submit_host / collect_host with scene i+1 "
+                   "submitted before scene i is collected (pipelined); pinned host arrays in, fused cloud out through pinned buffers",
             "note": "`value_one_call_at_a_time`: run_host called back to back, nothing overlaps between calls.  `value`: depth, the mask (one bit per pixel, packed once on the host outside the timed region), colours and sparse points are copied to the device every step; the normal maps "
                     "stay in pinned host memory and the consistency kernel reads only the normals of its vote candidates over "
                     "PCIe (not counted in h2d_bytes_per_step).  `value_all_copied`: the normal maps are copied too."}

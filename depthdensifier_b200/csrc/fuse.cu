@@ -675,6 +675,9 @@ __global__ void canonical_key_kernel(GridDev g, int64_t n, const float* __restri
 // [4 + 2P + k] exclusive prefix of the lengths (P = DDN_MAX_PEERS).  The shares are walked in this ROTATED order:
 // every rank starts with its own records and then reads a different peer than everybody else, so all NVLink
 // ports carry traffic at once (in natural order all ranks would pull from rank 0 first, then from rank 1, ...).
+#ifndef DDN_PULL_CTAS_PER_SM
+#define DDN_PULL_CTAS_PER_SM 2
+#endif
 constexpr int kPlanWords = 4 + 3 * DDN_MAX_PEERS;
 static_assert(kPlanWords <= 64, "plan scratch is 64 words");
 static_assert(DDN_MAX_PEERS <= 31, "the plan kernel is one warp");
@@ -1357,7 +1360,8 @@ int ddn_fuse_merge_peers(const ddn_fuse_session* s, int32_t rank, int32_t n_rank
   DDN_TRY(after_launch("merge_plan_kernel", st));
   merge_clear_kernel<<<kPersistentCtas, kOwnUnits, 0, st>>>(f, planll);
   DDN_TRY(after_launch("merge_clear_kernel", st));
-  merge_pull_mark_kernel<<<kPersistentCtas, 256, 0, st>>>(f, pr, rank, n_ranks, planll, staging, cap_out);
+  // two CTAs per SM keep enough 512-byte requests in flight for the link and leave room for another stream's kernels
+  merge_pull_mark_kernel<<<kNumSMs * DDN_PULL_CTAS_PER_SM, 256, 0, st>>>(f, pr, rank, n_ranks, planll, staging, cap_out);
   DDN_TRY(after_launch("merge_pull_mark_kernel", st));
   if (n_drop > 0) {  // N5: the cells of the sparse cloud leave the merged occupancy
     unmark_points_kernel<<<(unsigned)((n_drop + 255) / 256), 256, 0, st>>>(f, n_drop, drop_xyz, planll);
