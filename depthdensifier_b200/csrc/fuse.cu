@@ -676,7 +676,7 @@ __global__ void canonical_key_kernel(GridDev g, int64_t n, const float* __restri
 // every rank starts with its own records and then reads a different peer than everybody else, so all NVLink
 // ports carry traffic at once (in natural order all ranks would pull from rank 0 first, then from rank 1, ...).
 #ifndef DDN_PULL_CTAS_PER_SM
-#define DDN_PULL_CTAS_PER_SM 2
+#define DDN_PULL_CTAS_PER_SM 4
 #endif
 constexpr int kPlanWords = 4 + 3 * DDN_MAX_PEERS;
 static_assert(kPlanWords <= 64, "plan scratch is 64 words");
