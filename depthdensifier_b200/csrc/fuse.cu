@@ -676,7 +676,7 @@ __global__ void canonical_key_kernel(GridDev g, int64_t n, const float* __restri
 // every rank starts with its own records and then reads a different peer than everybody else, so all NVLink
 // ports carry traffic at once (in natural order all ranks would pull from rank 0 first, then from rank 1, ...).
 #ifndef DDN_PULL_CTAS_PER_SM
-#define DDN_PULL_CTAS_PER_SM 4
+#define DDN_PULL_CTAS_PER_SM 8
 #endif
 constexpr int kPlanWords = 4 + 3 * DDN_MAX_PEERS;
 static_assert(kPlanWords <= 64, "plan scratch is 64 words");
@@ -1360,7 +1360,7 @@ int ddn_fuse_merge_peers(const ddn_fuse_session* s, int32_t rank, int32_t n_rank
   DDN_TRY(after_launch("merge_plan_kernel", st));
   merge_clear_kernel<<<kPersistentCtas, kOwnUnits, 0, st>>>(f, planll);
   DDN_TRY(after_launch("merge_clear_kernel", st));
-  // two CTAs per SM keep enough 512-byte requests in flight for the link and leave room for another stream's kernels
+  // (fewer CTAs per SM, to leave room for another stream's kernels, cost the pull 3-14 % on 2 GPUs: -DDDN_PULL_CTAS_PER_SM)
   merge_pull_mark_kernel<<<kNumSMs * DDN_PULL_CTAS_PER_SM, 256, 0, st>>>(f, pr, rank, n_ranks, planll, staging, cap_out);
   DDN_TRY(after_launch("merge_pull_mark_kernel", st));
   if (n_drop > 0) {  // N5: the cells of the sparse cloud leave the merged occupancy

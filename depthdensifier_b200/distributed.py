@@ -282,7 +282,7 @@ class ShardedDensifier:
         _, hdl, views = self.peer.buffer(f"refined{self._parity}", (self._slots_max, self.H, self.W), torch.float32)
         cur = torch.cuda.current_stream(self.device)
         hdl.barrier()  # every rank's refined maps and bounding box of this step are in place
-        if self.cfg.overlap_align and self.cfg.voxel is None:
+        if self.cfg.overlap_align:
             self._ev_stage1_may_start = torch.cuda.Event()
             self._ev_stage1_may_start.record(cur)
         self._side.wait_stream(cur)
@@ -335,10 +335,11 @@ class ShardedDensifier:
             return refined_slots, pair, src, box, stats
 
         if self.device_path and cfg.overlap_align:
-            # Stage 1 on its own stream.  It may start as soon as the PREVIOUS step has passed its second barrier and
-            # begins to pull and merge records (without fusion: its halo barrier; one rank: has launched its K4).
-            # Nobody reads the buffers it writes (the other parity's maps and box) once that step has passed its
-            # halo barrier, and the merge leaves most of every SM idle.
+            # Stage 1 on its own stream.  It may start as soon as the PREVIOUS step has passed its halo barrier (one
+            # rank: has launched its K4) - from then on nobody reads the buffers it writes (the other parity's maps
+            # and box) - and then fills whatever the main stream leaves idle.  (Holding it back until the previous
+            # step starts its merge was measured on 8 GPUs: strong cfg 3 3.38 instead of 3.42 ms, but weak cfg 2 11.5
+            # instead of 9.9 ms - a whole K3 beside the record pull slows the pull, and every rank then waits.)
             main = torch.cuda.current_stream(self.device)
             if getattr(self, "_align_stream", None) is None:
                 self._align_stream, self._ev_stage1_may_start = torch.cuda.Stream(device=self.device), None
@@ -508,11 +509,6 @@ class ShardedDensifier:
         rec, hdl, _ = self.peer.buffer("records", tuple(self.peer_records_shape), torch.int64)
         mark("fuse_partials", lambda: self.ops.fuse_finish_partial(sess, *flat, self.thr, rec, row_len=xyz.shape[2]))
         hdl.barrier()  # every rank's units, tile prefix and records are complete
-        if self.cfg.overlap_align:
-            # from here on the step only pulls and merges records (NVLink-bound, few SMs busy): the next step's
-            # stage 1 may run beside it.  (Also later than the halo barrier, after which its buffers are free.)
-            self._ev_stage1_may_start = torch.cuda.Event()
-            self._ev_stage1_may_start.record(torch.cuda.current_stream(self.device))
         k, x, c, n, counts = mark("fuse_merge", lambda: self.ops.fuse_merge_peers(
             sess, self.rank, self.world, self._peer_records, self._peer_prefix, self._plan, self._cap_merge, out=self._merge_outputs(out_slot), drop_xyz=drop))
         return k, x, c, n, counts.clone()

@@ -2,7 +2,6 @@
 mkdir -p gpurun_out
 run() { timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 8 "$@"; }
 run --steps 20 --warmup 5 > gpurun_out/r02_bench_g8.json 2> gpurun_out/r02_bench_g8.err; echo "bench g8 rc=$?"
-run --steps 10 --warmup 3 --no-e2e --no-check --no-overlap-align > gpurun_out/r02_bench_g8_nooverlap.json 2> gpurun_out/r02_bench_g8_nooverlap.err; echo "bench g8 no overlap rc=$?"
 python - <<'PY'
 import json
 for f in ("r02_bench_g8", "r02_bench_g8_nooverlap"):
