@@ -33,6 +33,7 @@ class AlignConfig(C.Structure):
         ("subsample_seed", C.c_uint32),
         ("zero_unmasked_passthrough", C.c_int32),
         ("mask_packed", C.c_int32),
+        ("use_tma", C.c_int32),
     ]
 
 

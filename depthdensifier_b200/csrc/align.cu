@@ -9,6 +9,10 @@
 //          median (:194-200) and mask (:203): depth+mask are read once, refined written once
 //          (9 B/pixel instead of the reference's 9x unfold blow-up).  The per-pixel searchsorted runs
 //          through a 1024-bucket index of the table built by K2, the median through sorted row triples.
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no -lcuda)
+
+#include <cuda/barrier>
+
 #include "common.cuh"
 
 namespace ddn {
@@ -508,13 +512,20 @@ __device__ __forceinline__ void tile_bbox_epilogue(int* __restrict__ bbox, const
 #endif
 // kPacked: the mask is one bit per pixel; kBox: the bounding-box epilogue is on.  Template parameters, not run-time
 // flags: the kernel is bound by instruction issue, and a per-pixel branch on either costs 5 % (measured).
-template <bool kPacked, bool kBox>
+// kTma (experiment, ddn_align_config.use_tma): the 128 x 34 depth tile arrives through ONE cp.async.bulk.tensor (TMA, SASS
+// UTMALDG) straight into s_val, is remapped in place, and halo positions outside the image take the value of the clamped
+// pixel afterwards (TMA zero-fills out-of-bounds elements; the remap is pointwise, so copying the remapped neighbour is the
+// replicate padding).  Needs 16-byte multiples for the row pitch, i.e. W % 4 == 0 - cfg 2's 1297-pixel rows do not qualify.
+template <bool kPacked, bool kBox, bool kTma>
 __global__ void __launch_bounds__(kRemapThreads, DDN_K3_MINB)
 remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y, const float* __restrict__ depth,
                     const uint8_t* __restrict__ mask, const ddn_view_stats* __restrict__ stats, AlignWorkspace ws,
-                    float* __restrict__ refined, int lut_cap, const float* __restrict__ src_table, int* __restrict__ bbox) {
+                    float* __restrict__ refined, int lut_cap, const float* __restrict__ src_table, int* __restrict__ bbox,
+                    const __grid_constant__ CUtensorMap depth_map) {
   extern __shared__ __align__(16) float s_dyn[];  // LUT xs | ys | bucket index (when the table fits)
-  __shared__ float s_val[kHaloH][kHaloW];
+  __shared__ __align__(128) float s_val[kHaloH][kHaloW];
+#pragma nv_diag_suppress static_var_with_dynamic_init
+  __shared__ cuda::barrier<cuda::thread_scope_block> s_bar;
   __shared__ uint8_t s_msk[kHaloH][kHaloW + 2];
   // bounding-box epilogue: smallest / largest positive refined depth of the tile (bits of positive floats order as ints)
   __shared__ int s_dmin, s_dmax;
@@ -558,6 +569,21 @@ remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y
     return;
   }
 
+  cuda::barrier<cuda::thread_scope_block>::arrival_token tma_token;
+  if (kTma) {
+    namespace cde = cuda::device::experimental;
+    if (tid == 0) {
+      init(&s_bar, kRemapThreads);
+      cde::fence_proxy_async_shared_cta();
+    }
+    __syncthreads();
+    if (tid == 0) {  // the whole halo tile in one request; elements outside the image arrive as zeros
+      cde::cp_async_bulk_tensor_3d_global_to_shared(&s_val[0][0], &depth_map, tx0 - 1, ty0 - 1, v, s_bar);
+      tma_token = cuda::device::barrier_arrive_tx(s_bar, 1, sizeof(s_val));
+    } else {
+      tma_token = s_bar.arrive();
+    }
+  }
   const int n = st.num_table;
   const float* gxs = ws.tx + (size_t)v * ws.C;
   const float* gys = ws.ty + (size_t)v * ws.C;
@@ -581,6 +607,7 @@ remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y
   // phase 1: remap tile + 1-pixel replicate halo into shared memory.  The halo is exactly 128 wide: a thread owns
   // halo column hx (clamp hoisted) and every second halo row - no index division, no idle lanes.
   static_assert(kHaloW == 128 && kRemapThreads == 256, "phase 1 maps two halo rows per pass");
+  if (kTma) s_bar.wait(std::move(tma_token));
   {
     const int hx = tid & (kHaloW - 1);
     const int x = min(max(tx0 + hx - 1, 0), W - 1);
@@ -588,7 +615,8 @@ remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y
     for (int hy = tid >> 7; hy < kHaloH; hy += 2) {
       const int y = min(max(ty0 + hy - 1, 0), H - 1);
       const int g = y * W + x;
-      const float d = __ldg(dmap + g);
+      if (kTma && (x != tx0 + hx - 1 || y != ty0 + hy - 1)) continue;  // outside the image: filled in below
+      const float d = kTma ? s_val[hy][hx] : __ldg(dmap + g);
       const bool mk = mmap ? mask_at((size_t)g) : (d > 0.f);
       float val = 0.f;
       if (mk) {
@@ -598,6 +626,18 @@ remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y
       }
       s_val[hy][hx] = val;
       s_msk[hy][hx] = mk ? 1 : 0;
+    }
+    if (kTma) {  // replicate padding: positions outside the image <- the (remapped) clamped pixel, which is inside the tile
+      __syncthreads();
+#pragma unroll 1
+      for (int hy = tid >> 7; hy < kHaloH; hy += 2) {
+        const int y = min(max(ty0 + hy - 1, 0), H - 1);
+        if (x != tx0 + hx - 1 || y != ty0 + hy - 1) {
+          const int cx = x - (tx0 - 1), cy = y - (ty0 - 1);
+          s_val[hy][hx] = s_val[cy][cx];
+          s_msk[hy][hx] = s_msk[cy][cx];
+        }
+      }
     }
   }
   __syncthreads();
@@ -692,14 +732,47 @@ int ddn_align_views(const ddn_align_config* cfg, int64_t n_views, int64_t height
   if (cfg->mode != 0 || lut > kLutSmemMax) lut = 0;  // affine mode has no table; huge tables stay in global
   const size_t smem_lut = lut > 0 ? (size_t)lut * 8 + (size_t)kBuckets * 4 : 0;
   dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)n_views);
+  CUtensorMap depth_map;
+  memset(&depth_map, 0, sizeof(depth_map));
+  const bool tma = cfg->use_tma != 0;
+  if (tma) {
+    DDN_REQUIRE(width % 4 == 0 && ((uintptr_t)depth & 15) == 0, "use_tma needs W % 4 == 0 and a 16-byte aligned depth pointer");
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    DDN_TRY(check_cuda(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres), "cudaGetDriverEntryPoint"));
+    DDN_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+    const cuuint64_t dims[3] = {(cuuint64_t)width, (cuuint64_t)height, (cuuint64_t)n_views};
+    const cuuint64_t strides[2] = {(cuuint64_t)width * 4, (cuuint64_t)width * (cuuint64_t)height * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)kHaloW, (cuuint32_t)kHaloH, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = ((EncodeFn)fn)(&depth_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(depth), dims, strides, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled failed: %d", (int)r);
+      return DDN_ERR_CUDA;
+    }
+  }
 #define DDN_LAUNCH_REMAP(P, B)                                                                                              \
   do {                                                                                                                      \
-    DDN_TRY(check_cuda(cudaFuncSetAttribute(remap_median_kernel<P, B>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
-                                            (int)smem_lut),                                                                 \
-                       "cudaFuncSetAttribute(remap_median)"));                                                              \
-    remap_median_kernel<P, B><<<grid, kRemapThreads, smem_lut, st>>>(*cfg, (int)height, (int)width, tiles_x, tiles_y, depth, \
-                                                                    mask, stats, ws, refined, (int)lut, src_table,         \
-                                                                    reinterpret_cast<int*>(bbox));                         \
+    if (tma) {                                                                                                              \
+      DDN_TRY(check_cuda(cudaFuncSetAttribute(remap_median_kernel<P, B, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                              (int)smem_lut),                                                               \
+                         "cudaFuncSetAttribute(remap_median)"));                                                            \
+      remap_median_kernel<P, B, true><<<grid, kRemapThreads, smem_lut, st>>>(                                               \
+          *cfg, (int)height, (int)width, tiles_x, tiles_y, depth, mask, stats, ws, refined, (int)lut, src_table,            \
+          reinterpret_cast<int*>(bbox), depth_map);                                                                         \
+    } else {                                                                                                                \
+      DDN_TRY(check_cuda(cudaFuncSetAttribute(remap_median_kernel<P, B, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                              (int)smem_lut),                                                               \
+                         "cudaFuncSetAttribute(remap_median)"));                                                            \
+      remap_median_kernel<P, B, false><<<grid, kRemapThreads, smem_lut, st>>>(                                              \
+          *cfg, (int)height, (int)width, tiles_x, tiles_y, depth, mask, stats, ws, refined, (int)lut, src_table,            \
+          reinterpret_cast<int*>(bbox), depth_map);                                                                         \
+    }                                                                                                                       \
   } while (0)
   const bool packed = cfg->mask_packed != 0 && mask != nullptr, box = bbox != nullptr;
   if (packed && box) DDN_LAUNCH_REMAP(true, true);

@@ -110,6 +110,7 @@ void ddn_align_config_default(ddn_align_config* cfg) {
   cfg->subsample_seed = 0;
   cfg->zero_unmasked_passthrough = 0;
   cfg->mask_packed = 0;
+  cfg->use_tma = 0;
 }
 
 void ddn_filter_config_default(ddn_filter_config* cfg) {

@@ -63,6 +63,7 @@ class AlignOptions:
     align_mode: str = "pwl"
     subsample_seed: int = 0
     zero_unmasked_passthrough: bool = False
+    use_tma: bool = False  # experiment: K3 loads its depth tile with one TMA tensor copy (needs W % 4 == 0); same results
 
     def to_c(self, mask_packed: bool = False) -> _lib.AlignConfig:
         if self.align_mode not in ("pwl", "affine"):
@@ -79,6 +80,7 @@ class AlignOptions:
             int(self.subsample_seed) & 0xFFFFFFFF,
             int(bool(self.zero_unmasked_passthrough)),
             int(bool(mask_packed)),
+            int(bool(self.use_tma)),
         )
 
 
