@@ -9,9 +9,9 @@
 //          median (:194-200) and mask (:203): depth+mask are read once, refined written once
 //          (9 B/pixel instead of the reference's 9x unfold blow-up).  The per-pixel searchsorted runs
 //          through a 1024-bucket index of the table built by K2, the median through sorted row triples.
-#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no -lcuda)
+#include <stdlib.h>
 
-#include <cuda/barrier>
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no -lcuda)
 
 #include "common.cuh"
 
@@ -28,6 +28,7 @@ struct AlignWorkspace {
   float* ty;     // [V,C] table y
   unsigned long long* sortbuf;  // [V,Cp]
   uint32_t* bucket;             // [V,kBuckets] search acceleration of the table: start | end << 16
+  void* tensor_map;             // device copy of the TMA descriptor of the depth maps (use_tma)
   int64_t C, Cp;
 };
 
@@ -52,7 +53,7 @@ static int64_t next_pow2(int64_t x) {
 
 static int64_t align_ws_bytes(int64_t V, int64_t C) {
   const int64_t Cp = next_pow2(C > 1 ? C : 2);
-  return align_up(V * C * 4, 256) * 5 + align_up(V * Cp * 8, 256) + align_up(V * 1024 * 4, 256) + 256;
+  return align_up(V * C * 4, 256) * 5 + align_up(V * Cp * 8, 256) + align_up(V * 1024 * 4, 256) + 256 + 256;  // + a TMA descriptor
 }
 
 static AlignWorkspace carve(void* ws, int64_t V, int64_t C) {
@@ -68,6 +69,8 @@ static AlignWorkspace carve(void* ws, int64_t V, int64_t C) {
   w.ty = (float*)p; p += fb;
   w.sortbuf = (unsigned long long*)p; p += align_up(V * w.Cp * 8, 256);
   w.bucket = (uint32_t*)p;
+  p += align_up(V * 1024 * 4, 256);
+  w.tensor_map = (void*)p;  // 128 bytes, 256-byte aligned
   return w;
 }
 
@@ -512,8 +515,8 @@ __device__ __forceinline__ void tile_bbox_epilogue(int* __restrict__ bbox, const
 #endif
 // kPacked: the mask is one bit per pixel; kBox: the bounding-box epilogue is on.  Template parameters, not run-time
 // flags: the kernel is bound by instruction issue, and a per-pixel branch on either costs 5 % (measured).
-// kTma (experiment, ddn_align_config.use_tma): the 128 x 34 depth tile arrives through ONE cp.async.bulk.tensor (TMA, SASS
-// UTMALDG) straight into s_val, is remapped in place, and halo positions outside the image take the value of the clamped
+// kTma (UNFINISHED experiment, ddn_align_config.use_tma - faults on first launch, see ddn_align_views): the 128 x 34
+// depth tile arrives through ONE cp.async.bulk.tensor (TMA, SASS UTMALDG) straight into s_val, is remapped in place, and halo positions outside the image take the value of the clamped
 // pixel afterwards (TMA zero-fills out-of-bounds elements; the remap is pointwise, so copying the remapped neighbour is the
 // replicate padding).  Needs 16-byte multiples for the row pitch, i.e. W % 4 == 0 - cfg 2's 1297-pixel rows do not qualify.
 template <bool kPacked, bool kBox, bool kTma>
@@ -521,11 +524,10 @@ __global__ void __launch_bounds__(kRemapThreads, DDN_K3_MINB)
 remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y, const float* __restrict__ depth,
                     const uint8_t* __restrict__ mask, const ddn_view_stats* __restrict__ stats, AlignWorkspace ws,
                     float* __restrict__ refined, int lut_cap, const float* __restrict__ src_table, int* __restrict__ bbox,
-                    const __grid_constant__ CUtensorMap depth_map) {
+                    const CUtensorMap* __restrict__ depth_map) {
   extern __shared__ __align__(16) float s_dyn[];  // LUT xs | ys | bucket index (when the table fits)
   __shared__ __align__(128) float s_val[kHaloH][kHaloW];
-#pragma nv_diag_suppress static_var_with_dynamic_init
-  __shared__ cuda::barrier<cuda::thread_scope_block> s_bar;
+  __shared__ __align__(8) unsigned long long s_bar;  // mbarrier of the TMA load (kTma)
   __shared__ uint8_t s_msk[kHaloH][kHaloW + 2];
   // bounding-box epilogue: smallest / largest positive refined depth of the tile (bits of positive floats order as ints)
   __shared__ int s_dmin, s_dmax;
@@ -569,19 +571,19 @@ remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y
     return;
   }
 
-  cuda::barrier<cuda::thread_scope_block>::arrival_token tma_token;
   if (kTma) {
-    namespace cde = cuda::device::experimental;
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar), dst = (uint32_t)__cvta_generic_to_shared(&s_val[0][0]);
     if (tid == 0) {
-      init(&s_bar, kRemapThreads);
-      cde::fence_proxy_async_shared_cta();
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (tid == 0) {  // the whole halo tile in one request; elements outside the image arrive as zeros
-      cde::cp_async_bulk_tensor_3d_global_to_shared(&s_val[0][0], &depth_map, tx0 - 1, ty0 - 1, v, s_bar);
-      tma_token = cuda::device::barrier_arrive_tx(s_bar, 1, sizeof(s_val));
-    } else {
-      tma_token = s_bar.arrive();
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)sizeof(s_val)) : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+          "l"(reinterpret_cast<uint64_t>(depth_map)), "r"(tx0 - 1), "r"(ty0 - 1), "r"(v), "r"(bar)
+          : "memory");
     }
   }
   const int n = st.num_table;
@@ -607,7 +609,16 @@ remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y
   // phase 1: remap tile + 1-pixel replicate halo into shared memory.  The halo is exactly 128 wide: a thread owns
   // halo column hx (clamp hoisted) and every second halo row - no index division, no idle lanes.
   static_assert(kHaloW == 128 && kRemapThreads == 256, "phase 1 maps two halo rows per pass");
-  if (kTma) s_bar.wait(std::move(tma_token));
+  if (kTma) {  // phase 0 of the barrier completes when the tile's 17,408 bytes have landed
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+    uint32_t ok = 0;
+    do {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok)
+                   : "r"(bar)
+                   : "memory");
+    } while (!ok);
+  }
   {
     const int hx = tid & (kHaloW - 1);
     const int x = min(max(tx0 + hx - 1, 0), W - 1);
@@ -736,6 +747,15 @@ int ddn_align_views(const ddn_align_config* cfg, int64_t n_views, int64_t height
   memset(&depth_map, 0, sizeof(depth_map));
   const bool tma = cfg->use_tma != 0;
   if (tma) {
+    // NOT WORKING YET: on the pool's B200s the first launch of the TMA variant raised cudaErrorIllegalInstruction, in three
+    // forms (libcu++ cuda::barrier + cp_async_bulk_tensor_3d_global_to_shared, raw PTX mbarrier + cp.async.bulk.tensor.3d
+    // with the descriptor as a __grid_constant__ parameter, and with the descriptor in global memory); the SASS
+    // (UTMALDG.3D, SYNCS.ARRIVE.TRANS64, SYNCS.PHASECHK.TRANS64.TRYWAIT) looks as expected and the cause was not found
+    // before the round's GPU budget ran out.  Kept behind an environment variable for the next attempt.
+    if (getenv("DDN_K3_TMA_EXPERIMENT") == nullptr) {
+      set_error("use_tma is an unfinished experiment (device fault on first launch); set DDN_K3_TMA_EXPERIMENT=1 to run it anyway");
+      return DDN_ERR_UNSUPPORTED;
+    }
     DDN_REQUIRE(width % 4 == 0 && ((uintptr_t)depth & 15) == 0, "use_tma needs W % 4 == 0 and a 16-byte aligned depth pointer");
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -755,7 +775,9 @@ int ddn_align_views(const ddn_align_config* cfg, int64_t n_views, int64_t height
       set_error("cuTensorMapEncodeTiled failed: %d", (int)r);
       return DDN_ERR_CUDA;
     }
+    DDN_TRY(check_cuda(cudaMemcpyAsync(ws.tensor_map, &depth_map, sizeof(depth_map), cudaMemcpyHostToDevice, st), "tensor map upload"));
   }
+  const CUtensorMap* depth_map_dev = reinterpret_cast<const CUtensorMap*>(ws.tensor_map);
 #define DDN_LAUNCH_REMAP(P, B)                                                                                              \
   do {                                                                                                                      \
     if (tma) {                                                                                                              \
@@ -764,14 +786,14 @@ int ddn_align_views(const ddn_align_config* cfg, int64_t n_views, int64_t height
                          "cudaFuncSetAttribute(remap_median)"));                                                            \
       remap_median_kernel<P, B, true><<<grid, kRemapThreads, smem_lut, st>>>(                                               \
           *cfg, (int)height, (int)width, tiles_x, tiles_y, depth, mask, stats, ws, refined, (int)lut, src_table,            \
-          reinterpret_cast<int*>(bbox), depth_map);                                                                         \
+          reinterpret_cast<int*>(bbox), depth_map_dev);                                                                     \
     } else {                                                                                                                \
       DDN_TRY(check_cuda(cudaFuncSetAttribute(remap_median_kernel<P, B, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                               (int)smem_lut),                                                               \
                          "cudaFuncSetAttribute(remap_median)"));                                                            \
       remap_median_kernel<P, B, false><<<grid, kRemapThreads, smem_lut, st>>>(                                              \
           *cfg, (int)height, (int)width, tiles_x, tiles_y, depth, mask, stats, ws, refined, (int)lut, src_table,            \
-          reinterpret_cast<int*>(bbox), depth_map);                                                                         \
+          reinterpret_cast<int*>(bbox), depth_map_dev);                                                                     \
     }                                                                                                                       \
   } while (0)
   const bool packed = cfg->mask_packed != 0 && mask != nullptr, box = bbox != nullptr;

@@ -63,7 +63,7 @@ class AlignOptions:
     align_mode: str = "pwl"
     subsample_seed: int = 0
     zero_unmasked_passthrough: bool = False
-    use_tma: bool = False  # experiment: K3 loads its depth tile with one TMA tensor copy (needs W % 4 == 0); same results
+    use_tma: bool = False  # UNFINISHED experiment (K3 depth tile via a TMA tensor copy): faults on the device, gated by DDN_K3_TMA_EXPERIMENT
 
     def to_c(self, mask_packed: bool = False) -> _lib.AlignConfig:
         if self.align_mode not in ("pwl", "affine"):
