@@ -6,7 +6,7 @@ depth of each source view's K neighbours, stage 4 is a global group-by on the vo
 
 * halo exchange of refined depth: a rank receives only the neighbour views its own rows of the
   neighbour table reference (with ring-ordered cameras that is <= K maps per shard boundary instead
-  of the all-gather of all V maps), as one NCCL all-to-all-v;
+  of the all-gather of all V maps);
 * voxel exchange: every rank fuses its own points into per-voxel PARTIAL SUMS (integer fixed point,
   so the result does not depend on how points are split over ranks); the grid's tiles are cut into R
   contiguous ranges that balance the global record count - each rank owns one disjoint key range, so a
@@ -18,8 +18,8 @@ Two implementations of the same steps:
 * the DEVICE path (CUDA): no host round trip anywhere in a step.  The grid is derived on the device from
   the bounding boxes the alignment kernels produce (all ranks' boxes are read through NVLink peer
   memory), the consistency kernel marks the occupancy of the points it keeps, and the owner-side merge
-  reads the peers' occupancy units and partial records straight out of their HBM inside its kernels
-  (ddn_fuse_merge_peers) - no staging copy, no host-side plan;
+  pulls its share of every rank's partial records straight out of their HBM inside its own kernels
+  (ddn_fuse_merge_peers: coalesced NVLink loads, peers visited in rotated order) - no host-side plan;
 * the COLLECTIVE path (all-to-all-v over torch.distributed; host-side grid and plan): what the gloo tests
   drive on CPU with a stand-in backend, and the fallback when symmetric memory cannot be set up.
 
