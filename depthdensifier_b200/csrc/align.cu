@@ -515,10 +515,18 @@ __device__ __forceinline__ void tile_bbox_epilogue(int* __restrict__ bbox, const
 #endif
 // kPacked: the mask is one bit per pixel; kBox: the bounding-box epilogue is on.  Template parameters, not run-time
 // flags: the kernel is bound by instruction issue, and a per-pixel branch on either costs 5 % (measured).
-// kTma (UNFINISHED experiment, ddn_align_config.use_tma - faults on first launch, see ddn_align_views): the 128 x 34
-// depth tile arrives through ONE cp.async.bulk.tensor (TMA, SASS UTMALDG) straight into s_val, is remapped in place, and halo positions outside the image take the value of the clamped
-// pixel afterwards (TMA zero-fills out-of-bounds elements; the remap is pointwise, so copying the remapped neighbour is the
-// replicate padding).  Needs 16-byte multiples for the row pitch, i.e. W % 4 == 0 - cfg 2's 1297-pixel rows do not qualify.
+// kTma (ddn_align_config.use_tma): the depth tile arrives through ONE cp.async.bulk.tensor (TMA, SASS UTMALDG), is
+// remapped in place, and halo positions outside the image take the value of the clamped pixel afterwards (TMA
+// zero-fills elements past the far edges; the remap is pointwise, so copying the remapped neighbour is the replicate
+// padding).  A tensor copy faults ("illegal instruction") when a start coordinate is negative or the innermost one is
+// not a multiple of 16 bytes (scripts/experiments/tma_min2.cu, profiles/r02_tma_min2.log), and the halo starts one pixel
+// left of a 126-pixel tile, so the box is 132 x 34: it starts at the 4-pixel boundary at or below max(tx0 - 1, 0), row
+// max(ty0 - 1, 0), and the kernel indexes it with the tile's own column / row offset (-1..3 / -1..0; a guard band in
+// front of the box takes the two negative cases, whose positions lie outside the image and are filled by the replicate
+// pass).  Needs 16-byte multiples for the row pitch, i.e. W % 4 == 0 - cfg 2's 1297-pixel rows do not qualify.
+constexpr int kTmaBoxW = 132;                                // 128 halo columns + up to 3 columns of alignment slack, x4 B = 528 B
+constexpr int kTmaGuard = 160;                               // floats in front of the box (>= one row + 1; 640 B keeps 128-B alignment)
+constexpr int kTmaFloats = kTmaGuard + kHaloH * kTmaBoxW;    // 18,592 B
 template <bool kPacked, bool kBox, bool kTma>
 __global__ void __launch_bounds__(kRemapThreads, DDN_K3_MINB)
 remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y, const float* __restrict__ depth,
@@ -526,7 +534,7 @@ remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y
                     float* __restrict__ refined, int lut_cap, const float* __restrict__ src_table, int* __restrict__ bbox,
                     const CUtensorMap* __restrict__ depth_map) {
   extern __shared__ __align__(16) float s_dyn[];  // LUT xs | ys | bucket index (when the table fits)
-  __shared__ __align__(128) float s_val[kHaloH][kHaloW];
+  __shared__ __align__(128) float s_buf[kTma ? kTmaFloats : kHaloH * kHaloW];
   __shared__ __align__(8) unsigned long long s_bar;  // mbarrier of the TMA load (kTma)
   __shared__ uint8_t s_msk[kHaloH][kHaloW + 2];
   // bounding-box epilogue: smallest / largest positive refined depth of the tile (bits of positive floats order as ints)
@@ -571,18 +579,23 @@ remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y
     return;
   }
 
+  // halo position (hy, hx) <-> pixel (ty0 - 1 + hy, tx0 - 1 + hx); with TMA the box starts at (by0, bx0) instead
+  const int bx0 = max(tx0 - 1, 0) & ~3, by0 = max(ty0 - 1, 0);
+  const int val_base = kTma ? kTmaGuard + (ty0 - 1 - by0) * kTmaBoxW + (tx0 - 1 - bx0) : 0;
+  constexpr int kValPitch = kTma ? kTmaBoxW : kHaloW;
+  auto val_at = [&](int hy, int hx) -> float& { return s_buf[val_base + hy * kValPitch + hx]; };
   if (kTma) {
-    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar), dst = (uint32_t)__cvta_generic_to_shared(&s_val[0][0]);
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar), dst = (uint32_t)__cvta_generic_to_shared(s_buf + kTmaGuard);
     if (tid == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tid == 0) {  // the whole halo tile in one request; elements outside the image arrive as zeros
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)sizeof(s_val)) : "memory");
+    if (tid == 0) {  // the whole box in one request; elements past the right / bottom edge of the image arrive as zeros
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(kTmaBoxW * kHaloH * 4)) : "memory");
       asm volatile(
           "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
-          "l"(reinterpret_cast<uint64_t>(depth_map)), "r"(tx0 - 1), "r"(ty0 - 1), "r"(v), "r"(bar)
+          "l"(reinterpret_cast<uint64_t>(depth_map)), "r"(bx0), "r"(by0), "r"(v), "r"(bar)
           : "memory");
     }
   }
@@ -609,7 +622,7 @@ remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y
   // phase 1: remap tile + 1-pixel replicate halo into shared memory.  The halo is exactly 128 wide: a thread owns
   // halo column hx (clamp hoisted) and every second halo row - no index division, no idle lanes.
   static_assert(kHaloW == 128 && kRemapThreads == 256, "phase 1 maps two halo rows per pass");
-  if (kTma) {  // phase 0 of the barrier completes when the tile's 17,408 bytes have landed
+  if (kTma) {  // phase 0 of the barrier completes when the box's 17,952 bytes have landed
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
     uint32_t ok = 0;
     do {
@@ -627,7 +640,7 @@ remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y
       const int y = min(max(ty0 + hy - 1, 0), H - 1);
       const int g = y * W + x;
       if (kTma && (x != tx0 + hx - 1 || y != ty0 + hy - 1)) continue;  // outside the image: filled in below
-      const float d = kTma ? s_val[hy][hx] : __ldg(dmap + g);
+      const float d = kTma ? val_at(hy, hx) : __ldg(dmap + g);
       const bool mk = mmap ? mask_at((size_t)g) : (d > 0.f);
       float val = 0.f;
       if (mk) {
@@ -635,7 +648,7 @@ remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y
         else if (cfg.mode == 0) val = (n >= 2) ? pwl_eval(d, gxs, gys, n) : __fmul_rn(d, __fdiv_rn(gys[0], __fadd_rn(gxs[0], 1e-6f)));
         else val = fmaxf(__fadd_rn(__fmul_rn(d, a_s), a_t), 1e-3f);
       }
-      s_val[hy][hx] = val;
+      val_at(hy, hx) = val;
       s_msk[hy][hx] = mk ? 1 : 0;
     }
     if (kTma) {  // replicate padding: positions outside the image <- the (remapped) clamped pixel, which is inside the tile
@@ -645,7 +658,7 @@ remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y
         const int y = min(max(ty0 + hy - 1, 0), H - 1);
         if (x != tx0 + hx - 1 || y != ty0 + hy - 1) {
           const int cx = x - (tx0 - 1), cy = y - (ty0 - 1);
-          s_val[hy][hx] = s_val[cy][cx];
+          val_at(hy, hx) = val_at(cy, cx);
           s_msk[hy][hx] = s_msk[cy][cx];
         }
       }
@@ -664,14 +677,14 @@ remap_median_kernel(ddn_align_config cfg, int H, int W, int tiles_x, int tiles_y
     for (int r = 0; r < kRowsPerThread; ++r) {
       const int y = ty0 + ly0 + r;
       if (y >= H) break;
-      const float o = s_msk[ly0 + r + 1][lx + 1] ? s_val[ly0 + r + 1][lx + 1] : 0.f;
+      const float o = s_msk[ly0 + r + 1][lx + 1] ? val_at(ly0 + r + 1, lx + 1) : 0.f;
       out[(size_t)y * W + x] = o;
       fold_depth(o);
     }
   } else if (active) {
     float lo[3], mi[3], hi[3];
     auto load_row = [&](int hy, int slot) {
-      float a = s_val[hy][lx], b = s_val[hy][lx + 1], c = s_val[hy][lx + 2];
+      float a = val_at(hy, lx), b = val_at(hy, lx + 1), c = val_at(hy, lx + 2);
       const float ab_lo = fminf(a, b), ab_hi = fmaxf(a, b);
       lo[slot] = fminf(ab_lo, c);
       hi[slot] = fmaxf(ab_hi, c);
@@ -722,6 +735,10 @@ int ddn_align_views(const ddn_align_config* cfg, int64_t n_views, int64_t height
   DDN_REQUIRE(depth && cam_from_world && kmat && sparse_offsets && refined && stats && workspace, "null pointer");
   const int64_t C = max_sparse_per_view > 0 ? max_sparse_per_view : 1;
   DDN_REQUIRE(C < (1ll << 30), "max_sparse_per_view");
+  if (cfg->use_tma) {  // tensor-copy form of the remap kernel: checked before anything is launched
+    DDN_REQUIRE(width % 4 == 0 && ((uintptr_t)depth & 15) == 0, "use_tma needs W % 4 == 0 and a 16-byte aligned depth pointer");
+    DDN_REQUIRE(width >= kTmaBoxW && height >= kHaloH, "use_tma needs an image of at least 132 x 34 pixels");
+  }
   if (workspace_bytes < align_ws_bytes(n_views, C)) {
     set_error("align workspace too small: %lld < %lld", (long long)workspace_bytes, (long long)align_ws_bytes(n_views, C));
     return DDN_ERR_WORKSPACE_TOO_SMALL;
@@ -736,7 +753,7 @@ int ddn_align_views(const ddn_align_config* cfg, int64_t n_views, int64_t height
   align_stats_kernel<<<(unsigned)n_views, kStatsThreads, smem_sort, st>>>(*cfg, (int)height, (int)width, depth,
                                                                          cam_from_world, kmat, sparse_xyz,
                                                                          sparse_offsets, ws, stats, in_smem, pairs_smem);
-  DDN_TRY(after_launch("align_stats_kernel"));
+  DDN_TRY(after_launch("align_stats_kernel", st));
   const int tiles_x = (int)((width + kTileW - 1) / kTileW), tiles_y = (int)((height + kTileH - 1) / kTileH);
   // largest table any view can have: max_pairs when subsampling, else every surviving pair
   int64_t lut = (cfg->adaptive_correspondences && cfg->max_pairs < C) ? cfg->max_pairs : C;
@@ -747,16 +764,6 @@ int ddn_align_views(const ddn_align_config* cfg, int64_t n_views, int64_t height
   memset(&depth_map, 0, sizeof(depth_map));
   const bool tma = cfg->use_tma != 0;
   if (tma) {
-    // NOT WORKING YET: on the pool's B200s the first launch of the TMA variant raised cudaErrorIllegalInstruction, in three
-    // forms (libcu++ cuda::barrier + cp_async_bulk_tensor_3d_global_to_shared, raw PTX mbarrier + cp.async.bulk.tensor.3d
-    // with the descriptor as a __grid_constant__ parameter, and with the descriptor in global memory); the SASS
-    // (UTMALDG.3D, SYNCS.ARRIVE.TRANS64, SYNCS.PHASECHK.TRANS64.TRYWAIT) looks as expected and the cause was not found
-    // before the round's GPU budget ran out.  Kept behind an environment variable for the next attempt.
-    if (getenv("DDN_K3_TMA_EXPERIMENT") == nullptr) {
-      set_error("use_tma is an unfinished experiment (device fault on first launch); set DDN_K3_TMA_EXPERIMENT=1 to run it anyway");
-      return DDN_ERR_UNSUPPORTED;
-    }
-    DDN_REQUIRE(width % 4 == 0 && ((uintptr_t)depth & 15) == 0, "use_tma needs W % 4 == 0 and a 16-byte aligned depth pointer");
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -766,7 +773,7 @@ int ddn_align_views(const ddn_align_config* cfg, int64_t n_views, int64_t height
     DDN_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
     const cuuint64_t dims[3] = {(cuuint64_t)width, (cuuint64_t)height, (cuuint64_t)n_views};
     const cuuint64_t strides[2] = {(cuuint64_t)width * 4, (cuuint64_t)width * (cuuint64_t)height * 4};
-    const cuuint32_t box[3] = {(cuuint32_t)kHaloW, (cuuint32_t)kHaloH, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)kTmaBoxW, (cuuint32_t)kHaloH, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = ((EncodeFn)fn)(&depth_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(depth), dims, strides, box, estr,
                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -802,7 +809,7 @@ int ddn_align_views(const ddn_align_config* cfg, int64_t n_views, int64_t height
   else if (box) DDN_LAUNCH_REMAP(false, true);
   else DDN_LAUNCH_REMAP(false, false);
 #undef DDN_LAUNCH_REMAP
-  return after_launch("remap_median_kernel");
+  return after_launch("remap_median_kernel", st);
 }
 
 }  // extern "C"

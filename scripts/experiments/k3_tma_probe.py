@@ -1,15 +1,14 @@
 #!/usr/bin/env python
 """K3 with its depth tile loaded by one TMA tensor copy (ddn_align_config.use_tma) against the default LDG path:
-bit-identity on small scenes with partial tiles, then timing at 1920x1080 (the TMA form needs W % 4 == 0, so not cfg 2)."""
+bit-identity on small scenes with partial tiles, then timing at 1920x1080 (the TMA form needs W % 4 == 0, so not cfg 2).
+The measurement of record was taken with the no-Python harness k3_tma_check.cu (profiles/r02_k3_tma_check.log)."""
 import json
-import os
 import sys
 from pathlib import Path
 
 import numpy as np
 import torch
 
-os.environ["DDN_K3_TMA_EXPERIMENT"] = "1"  # the variant is gated: it faulted (illegal instruction) on its first launches
 ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path.insert(0, str(ROOT))
 from depthdensifier_b200 import ops  # noqa: E402
